@@ -1,0 +1,212 @@
+/*
+ * b200rl.h -- C ABI of the B200-native policy-gradient update engine (libb200rl.so).
+ *
+ * The reference (rl_replicas 0.0.7) is pure Python and has NO FFI / plugin layer: its drop-in seam is the Python
+ * class API.  This header is the native boundary underneath our Python mirror of that API:
+ * every entry point names the reference function(s) whose arithmetic it replaces (paths relative to
+ * /root/reference/src/rl_replicas/).  INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only: pointers + sizes; no torch / C++ types cross the boundary.
+ *   - every function returns 0 on success, non-zero on failure; b200rl_last_error() describes the last failure of
+ *     the calling thread.  CUDA errors are reported the same way (never swallowed, never a CPU fallback).
+ *   - "device pointer" arguments must be 16-byte aligned and live on the current CUDA device.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All launchers are asynchronous.
+ *   - MLP parameters are ONE flat float32 vector in torch.nn.utils.parameters_to_vector order:
+ *     W0 [out0,in0] row-major, b0 [out0], W1, b1, ...  (torch.nn.Linear layout, ref: networks/mlp.py:24-31).
+ */
+#ifndef B200RL_H
+#define B200RL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_VERSION 100
+#define B200RL_MAX_LAYERS 4   /* Linear layers per MLP */
+#define B200RL_N_SCALARS 8    /* per-launch scalar sums, see b200rl_mlp_loss_grad */
+
+enum b200rl_activation { B200RL_ACT_IDENTITY = 0, B200RL_ACT_TANH = 1, B200RL_ACT_RELU = 2 };
+enum b200rl_dist { B200RL_DIST_NONE = 0, B200RL_DIST_GAUSSIAN = 1, B200RL_DIST_CATEGORICAL = 2 };
+enum b200rl_loss {
+  B200RL_LOSS_EVAL = 0,           /* forward only: per-row output (value, or log-prob when dist != NONE) + scalar sums */
+  B200RL_LOSS_PPO_CLIP = 1,       /* -mean(min(r A, clamp(r,1-c,1+c) A))        ref: algorithms/ppo.py:237-257 */
+  B200RL_LOSS_VPG = 2,            /* -mean(logp A)                               ref: algorithms/vpg.py:194-207 */
+  B200RL_LOSS_TRPO_SURROGATE = 3, /* -mean(r A)                                  ref: algorithms/trpo.py:154-165 */
+  B200RL_LOSS_MSE = 4             /* mean((out - target)^2)                      ref: algorithms/ppo.py:282-287 */
+};
+
+/* MLP description (ref: networks/mlp.py:15-31). */
+typedef struct {
+  int32_t n_layers;                     /* number of Linear layers, 1..B200RL_MAX_LAYERS */
+  int32_t sizes[B200RL_MAX_LAYERS + 1]; /* widths: input, hidden..., output */
+  int32_t hidden_act;                   /* enum b200rl_activation */
+  int32_t out_act;
+} b200rl_mlp_desc;
+
+const char* b200rl_last_error(void);
+int b200rl_version(void);
+/* kernels launched by this library in this process so far (bench.py reports gpu_launches from it) */
+int64_t b200rl_launch_count(void);
+/* number of float32 parameters of the MLP (sum of out*in + out); -1 if the description is invalid */
+int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp);
+/* CTAs the fused MLP kernels use for n_rows rows on the current device (= rows of `partials`); -1 on error */
+int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * gae_scan -- bootstrapped rewards, discounted returns, TD residuals, GAE  (one segmented reverse scan, float64 carry)
+ *   replaces: utils.py:14-28 (discounted_cumulative_sums), :31-44 (gae), :74-87 (bootstrap_rewards_with_last_values)
+ *             and the per-episode loops of algorithms/ppo.py:142-161.
+ *   rewards     [n]     float32 (rewards_f64 = 0) or float64 (rewards_f64 = 1)
+ *   values      [n]     V(obs_t)
+ *   last_values [n_ep]  V(last_observation_e)
+ *   ep_offsets  [n_ep+1] CSR offsets into the flat transition arrays (every episode has >= 1 step)
+ *   ep_done     [n_ep]  1 = the episode ended (terminated or truncated) => no bootstrap (utils.py:81-82)
+ *   adv_raw, ret [n]    outputs (float32 casts of the float64 recurrences, ppo.py:151,160)
+ *   stats       [3]     float64: sum(adv_raw), sum(adv_raw^2), n   (for normalize_tensor, utils.py:90-92)
+ *   workspace           b200rl_gae_scan_workspace_bytes(n) bytes of device memory
+ * ------------------------------------------------------------------------------------------------------------ */
+size_t b200rl_gae_scan_workspace_bytes(int64_t n);
+int b200rl_gae_scan(const void* rewards, int rewards_f64, const float* values, const float* last_values,
+                    const int64_t* ep_offsets, const uint8_t* ep_done, int64_t n, int64_t n_ep, double gamma,
+                    double gae_lambda, float* adv_raw, float* ret, double* stats, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * mlp_loss_grad -- ONE fused kernel: MLP forward -> distribution log-prob -> loss -> dLoss/dOut -> MLP backward,
+ * activations never leave the SM.  Per-CTA partial gradients go to `partials`; reduce with b200rl_reduce_adam.
+ *   replaces: networks/mlp.py:33-41, policies/gaussian_policy.py:25-37, policies/categorical_policy.py:22-32,
+ *             algorithms/ppo.py:237-257 (+ autograd backward at :234), :259-269 (approx KL), :282-287 (+ :277),
+ *             algorithms/vpg.py:200-206, algorithms/trpo.py:154-165, utils.py:60-71 (compute_values, loss = EVAL),
+ *             utils.py:90-92 (normalize_tensor, applied on load from adv_stats).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  b200rl_mlp_desc mlp;
+  int32_t loss;            /* enum b200rl_loss */
+  int32_t dist;            /* enum b200rl_dist */
+  int64_t n_rows;          /* rows handled by this launch (this rank's shard) */
+  int64_t n_global;        /* denominator of the mean (= n_rows on one GPU; sum over ranks otherwise) */
+  float clip_range;        /* PPO clip epsilon */
+  const float* params;     /* [P] device */
+  const float* obs;        /* [n_rows, sizes[0]] device, row-major */
+  const float* actions;    /* Gaussian: [n_rows, sizes[L]]; Categorical: [n_rows] (index as float, ppo.py:154) */
+  const float* log_std;    /* Gaussian: [sizes[L]] */
+  const float* adv_raw;    /* [n_rows] un-normalised advantages (policy losses) */
+  const double* adv_stats; /* [3] global sum, sum of squares, count -> mean / unbiased std; NULL = use adv_raw as is */
+  const float* old_logp;   /* [n_rows] (PPO / TRPO) */
+  const float* target;     /* [n_rows] (MSE: discounted returns) */
+  float* row_out;          /* optional [n_rows]: value (dist NONE) or log-prob (dist set); may be NULL */
+  float* partials;         /* [grid, P] per-CTA partial gradients (losses other than EVAL) */
+  double* scalar_partials; /* [grid, B200RL_N_SCALARS] per-CTA partial sums:
+                              0 sum(loss terms)  1 sum(old_logp - logp)  2 sum(entropy)  3 sum(logp)  4 sum(logp^2)
+                              5 rows processed   6,7 reserved */
+  const int32_t* skip_flag; /* optional device flag: non-zero => the launch is a no-op (early stop) */
+} b200rl_mlp_loss_grad_args;
+
+int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * reduce_adam -- fixed-order reduction of the per-CTA partials into the flat gradient, then torch.optim.Adam's
+ * single-tensor update on the flat parameter vector.
+ *   replaces: optimizer.zero_grad()/loss.backward() accumulation + torch.optim.Adam.step() at
+ *             algorithms/ppo.py:233-235, :276-278 (torch 2.5.1 _single_tensor_adam; no weight decay / amsgrad).
+ *   b200rl_reduce_partials: grad[p] = sum_c partials[c,p]; scalars[k] = sum_c scalar_partials[c,k]  (c ascending).
+ *     If grad_tail != 0 the scalar sums are ALSO written as float32 to grad[n_params .. n_params+B200RL_N_SCALARS)
+ *     so that ONE all-reduce of [n_params + B200RL_N_SCALARS] floats carries gradient, loss and KL.
+ *     partials may be NULL (scalars only, for EVAL launches).
+ *   b200rl_adam_step: m,v,params updated in place; `step` is the 1-based step number of THIS update (host-known).
+ *     Early stop (ppo.py:176-181): kl_sum points at sum(old_logp - logp) of this step's forward pass (float64, or
+ *     float32 when kl_is_f32); if kl_sum/n_global > kl_limit, or *stop_flag != 0, the update is skipped and
+ *     *stop_flag is set; applied_counter (optional) counts applied updates.  If tail_src != NULL its
+ *     B200RL_N_SCALARS float32 values (the all-reduced tail) are stored as float64 to tail_dst.
+ * ------------------------------------------------------------------------------------------------------------ */
+int b200rl_reduce_partials(const float* partials, const double* scalar_partials, int32_t grid, int64_t n_params,
+                           float* grad, double* scalars, int grad_tail, const int32_t* skip_flag, void* stream);
+int b200rl_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n_params,
+                     int64_t step, double lr, double beta1, double beta2, double eps, const void* kl_sum,
+                     int kl_is_f32, double n_global, double kl_limit, int32_t* stop_flag, int32_t* applied_counter,
+                     const float* tail_src, double* tail_dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * On-policy update engine: owns the device-resident batch, flat parameters, Adam state and workspaces of ONE
+ * PPO / VPG / TRPO learner, and runs the whole per-epoch update (the reference's `train(experience)`).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct b200rl_onpolicy b200rl_onpolicy;
+
+typedef struct {
+  b200rl_mlp_desc policy;
+  b200rl_mlp_desc value;
+  int32_t dist;            /* enum b200rl_dist */
+  int32_t rewards_f64;     /* dtype of the rewards buffer handed to load_batch */
+  int64_t max_rows;        /* capacity (transitions) */
+  int64_t max_episodes;    /* capacity (episodes) */
+} b200rl_onpolicy_config;
+
+/* all-reduce(sum) hook for data-parallel runs: called from inside b200rl_ppo_update on the engine's stream order;
+ * `buf` is a device pointer owned by the engine, dtype 0 = float32, 1 = float64.  NULL = single GPU. */
+typedef int (*b200rl_allreduce_fn)(void* user, void* buf, int64_t count, int32_t dtype, void* stream);
+
+typedef struct {
+  double gamma, gae_lambda, clip_range, max_kl_divergence;
+  int32_t num_policy_gradients, num_value_gradients;
+  double policy_lr, policy_beta1, policy_beta2, policy_eps;
+  double value_lr, value_beta1, value_beta2, value_eps;
+  int64_t n_global_rows;   /* 0 = single GPU (use local rows) */
+} b200rl_ppo_hparams;
+
+typedef struct {
+  double policy_loss_before;    /* ppo.py:166-168 */
+  double entropy_before;        /* ppo.py:170,202 */
+  double logp_std_before;       /* ppo.py:169,208 (unbiased) */
+  double kl_divergence;         /* ppo.py:176-178,214 (last evaluated) */
+  double value_loss_mean;       /* ppo.py:192,220 */
+  int32_t policy_steps_applied; /* Adam steps actually taken by the policy loop */
+  int32_t value_steps_applied;
+  int32_t kernel_launches;      /* kernels launched by this update */
+  int32_t reserved;
+  double adv_mean, adv_std;     /* normalize_tensor statistics actually used */
+  double value_loss_first, value_loss_last;
+} b200rl_update_stats;
+
+int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_onpolicy** out);
+void b200rl_onpolicy_destroy(b200rl_onpolicy* h);
+
+/* which: 0 policy, 1 old_policy, 2 value.  Host <-> device copies of the flat parameter vectors. */
+int b200rl_onpolicy_set_params(b200rl_onpolicy* h, int which, const float* host_flat, int64_t n, void* stream);
+int b200rl_onpolicy_get_params(b200rl_onpolicy* h, int which, float* host_flat, int64_t n, void* stream);
+/* which: 0 policy optimizer, 2 value optimizer; step = number of Adam steps already taken (optimizer.state[p]["step"]) */
+int b200rl_onpolicy_set_adam(b200rl_onpolicy* h, int which, const float* exp_avg, const float* exp_avg_sq,
+                             int64_t n, int64_t step, void* stream);
+int b200rl_onpolicy_get_adam(b200rl_onpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             int64_t* step, void* stream);
+int b200rl_onpolicy_set_log_std(b200rl_onpolicy* h, const float* host_log_std, int64_t n, void* stream);
+
+/* Packed trajectory batch.  src_on_device = 0: HOST buffers (pinned or pageable), copied
+ * with cudaMemcpyAsync; 1: device buffers (device-to-device copy). */
+int b200rl_onpolicy_load_batch(b200rl_onpolicy* h, const float* obs, const float* actions, const void* rewards,
+                               const float* last_obs, const int64_t* ep_offsets, const uint8_t* ep_done,
+                               int64_t n_rows, int64_t n_episodes, int src_on_device, void* stream);
+
+/* The reference's PPO.train(experience) on the loaded batch (algorithms/ppo.py:139-223).  Asynchronous device work,
+ * then one device->host read of the statistics (synchronises the stream). */
+int b200rl_ppo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn allreduce, void* user,
+                      b200rl_update_stats* stats, void* stream);
+/* The reference's VPG.train (algorithms/vpg.py:127-192): one policy step on -mean(logp A), then value steps. */
+int b200rl_vpg_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn allreduce, void* user,
+                      b200rl_update_stats* stats, void* stream);
+
+/* Device views for tests / profiling (pointers stay owned by the engine):
+ * name: "values","last_values","adv_raw","ret","old_logp","adv_stats","policy_grad","value_grad",
+ *       "policy_params","old_policy_params","value_params" */
+int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr, int64_t* count, int32_t* dtype);
+
+/* Whole path through HOST buffers (what `e2e` in bench.py times): H2D batch + parameters/Adam state, update, D2H. */
+int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, const b200rl_ppo_hparams* hp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H */

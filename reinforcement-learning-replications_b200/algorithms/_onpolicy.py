@@ -1,0 +1,180 @@
+"""Shared host logic of the on-policy trainers: introspect the user's modules, keep the native engine's device
+state in sync with them, and mirror the reference's train() side effects:
+  (1) policy.network / value_function.network parameters updated in place,
+  (2) optimizer.state[p] = {step, exp_avg, exp_avg_sq} updated,
+  (3) old_policy synced, (4) the logged scalars recorded.
+"""
+from __future__ import annotations
+
+import logging
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from ..engine import OLD_POLICY, POLICY, VALUE, OnPolicyEngine
+from ..packing import pack_experience
+from ..policies import CategoricalPolicy, GaussianPolicy
+
+logger = logging.getLogger(__name__)
+
+_ACT_NAMES = {nn.Tanh: "tanh", nn.ReLU: "relu", nn.Identity: "identity"}
+
+
+def describe_mlp(module: nn.Module) -> Tuple[List[int], str, str, List[nn.Linear]]:
+    """(sizes, hidden activation, output activation, Linear layers) of an MLP built like ref networks/mlp.py:24-31.
+    Anything else is refused loudly -- the engine has no generic-module fallback."""
+    seq = getattr(module, "network", module)
+    mods = list(seq.children()) if isinstance(seq, nn.Sequential) else None
+    if not mods:
+        raise NotImplementedError(f"B200 engine supports MLP(Linear/activation pairs) networks only, got {type(module).__name__}")
+    linears, acts = [], []
+    for i, m in enumerate(mods):
+        if i % 2 == 0:
+            if not isinstance(m, nn.Linear) or m.bias is None:
+                raise NotImplementedError(f"layer {i} must be nn.Linear with bias, got {type(m).__name__}")
+            linears.append(m)
+        else:
+            if type(m) not in _ACT_NAMES:
+                raise NotImplementedError(f"unsupported activation {type(m).__name__} (supported: Tanh, ReLU, Identity)")
+            acts.append(_ACT_NAMES[type(m)])
+    if len(acts) < len(linears):
+        acts.append("identity")
+    hidden = set(acts[:-1]) or {"tanh"}
+    if len(hidden) != 1:
+        raise NotImplementedError(f"hidden activations must all be the same, got {sorted(hidden)}")
+    sizes = [linears[0].in_features] + [l.out_features for l in linears]
+    for a, b in zip(linears[:-1], linears[1:]):
+        if a.out_features != b.in_features:
+            raise ValueError("inconsistent Linear sizes")
+    return sizes, hidden.pop(), acts[-1], linears
+
+
+def flat_params(linears: List[nn.Linear]) -> np.ndarray:
+    with torch.no_grad():
+        return torch.cat([t.detach().reshape(-1).float().cpu() for l in linears for t in (l.weight, l.bias)]).numpy()
+
+
+def write_flat(linears: List[nn.Linear], flat: np.ndarray) -> None:
+    src = torch.from_numpy(np.ascontiguousarray(flat))
+    o = 0
+    with torch.no_grad():
+        for l in linears:
+            for t in (l.weight, l.bias):
+                n = t.numel()
+                t.copy_(src[o:o + n].view_as(t))
+                o += n
+    assert o == src.numel()
+
+
+def adam_hparams(optimizer, linears: List[nn.Linear], what: str):
+    """(lr, beta1, beta2, eps) of a plain torch.optim.Adam over exactly this network's parameters, in order."""
+    if type(optimizer) is not torch.optim.Adam:
+        raise NotImplementedError(f"{what}: the engine implements torch.optim.Adam, got {type(optimizer).__name__}")
+    if len(optimizer.param_groups) != 1:
+        raise NotImplementedError(f"{what}: exactly one param group is supported")
+    g = optimizer.param_groups[0]
+    want = [t for l in linears for t in (l.weight, l.bias)]
+    if len(g["params"]) != len(want) or any(a is not b for a, b in zip(g["params"], want)):
+        raise NotImplementedError(
+            f"{what}: optimizer must hold exactly the network's parameters in order "
+            "(a trainable log_std inside the optimizer is not supported yet)")
+    if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False):
+        raise NotImplementedError(f"{what}: weight_decay / amsgrad / maximize are not supported")
+    return float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"])
+
+
+def read_adam_state(optimizer, linears: List[nn.Linear]):
+    ps = [t for l in linears for t in (l.weight, l.bias)]
+    if not all(p in optimizer.state and "exp_avg" in optimizer.state[p] for p in ps):
+        return None, None, 0
+    m = torch.cat([optimizer.state[p]["exp_avg"].reshape(-1).float() for p in ps]).numpy()
+    v = torch.cat([optimizer.state[p]["exp_avg_sq"].reshape(-1).float() for p in ps]).numpy()
+    steps = {int(float(optimizer.state[p]["step"])) for p in ps}
+    if len(steps) != 1:
+        raise NotImplementedError("parameters of one optimizer have different step counts")
+    return m, v, steps.pop()
+
+
+def write_adam_state(optimizer, linears: List[nn.Linear], m: np.ndarray, v: np.ndarray, step: int) -> None:
+    if step == 0:
+        return
+    mt, vt = torch.from_numpy(m), torch.from_numpy(v)
+    o = 0
+    for l in linears:
+        for p in (l.weight, l.bias):
+            n = p.numel()
+            st = optimizer.state[p]
+            st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
+            st["exp_avg"] = mt[o:o + n].view_as(p).clone()
+            st["exp_avg_sq"] = vt[o:o + n].view_as(p).clone()
+            o += n
+
+
+class OnPolicyTrainerMixin:
+    """Engine management shared by PPO / VPG / TRPO."""
+
+    _engine: Optional[OnPolicyEngine] = None
+    process_group = None
+    distributed = False
+
+    def _describe(self):
+        psizes, pact, pout, self._plin = describe_mlp(self.policy.network)
+        vsizes, vact, vout, self._vlin = describe_mlp(self.value_function.network)
+        if pout != "identity" or vout != "identity":
+            raise NotImplementedError("output activations other than Identity are not supported for on-policy nets")
+        if pact != vact:
+            raise NotImplementedError("policy and value networks must use the same hidden activation")
+        if isinstance(self.policy, GaussianPolicy):
+            dist = "gaussian"
+        elif isinstance(self.policy, CategoricalPolicy):
+            dist = "categorical"
+        else:
+            raise NotImplementedError(f"unsupported policy type {type(self.policy).__name__}")
+        return psizes, vsizes, dist, pact
+
+    def _ensure_engine(self, n_rows: int, n_episodes: int) -> OnPolicyEngine:
+        psizes, vsizes, dist, act = self._describe()
+        e = self._engine
+        if (e is None or e.policy_sizes != psizes or e.value_sizes != vsizes or e.dist != dist
+                or e.max_rows < n_rows or e.max_episodes < n_episodes):
+            if e is not None:
+                e.close()
+            cap_rows = max(n_rows, int(1.25 * n_rows) if e is not None else n_rows)
+            cap_eps = max(n_episodes, 2 * n_episodes if e is not None else n_episodes)
+            e = OnPolicyEngine(psizes, vsizes, dist, cap_rows, cap_eps, hidden_act=act, rewards_f64=True)
+            self._engine = e
+        return e
+
+    def _push_state(self, e: OnPolicyEngine, with_old: bool) -> None:
+        e.set_params(POLICY, flat_params(self._plin))
+        if with_old:
+            e.set_params(OLD_POLICY, flat_params(describe_mlp(self.old_policy.network)[3]))
+        e.set_params(VALUE, flat_params(self._vlin))
+        if e.dist == "gaussian":
+            e.set_log_std(self.policy.log_std.detach().float().numpy())
+        if type(self.policy.optimizer) is torch.optim.Adam:
+            e.set_adam(POLICY, *read_adam_state(self.policy.optimizer, self._plin))
+        e.set_adam(VALUE, *read_adam_state(self.value_function.optimizer, self._vlin))
+
+    def _pull_state(self, e: OnPolicyEngine, with_old: bool, policy_adam: bool = True) -> None:
+        write_flat(self._plin, e.get_params(POLICY))
+        write_flat(self._vlin, e.get_params(VALUE))
+        if with_old:
+            # ref ppo.py:183: old_policy.load_state_dict(policy.state_dict())
+            self.old_policy.load_state_dict(self.policy.state_dict())
+        if policy_adam:
+            write_adam_state(self.policy.optimizer, self._plin, *e.get_adam(POLICY))
+        write_adam_state(self.value_function.optimizer, self._vlin, *e.get_adam(VALUE))
+
+    def _global_rows(self, n_rows: int) -> int:
+        if not self.distributed:
+            return 0
+        import torch.distributed as dist
+        t = torch.tensor([n_rows], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, group=self.process_group)
+        return int(t.item())
+
+    def pack(self, experience):
+        return pack_experience(experience)

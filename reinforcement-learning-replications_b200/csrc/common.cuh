@@ -1,0 +1,48 @@
+// Shared helpers for libb200rl (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "b200rl.h"
+
+namespace b200rl {
+
+void set_error(const char* fmt, ...);
+
+#define B200RL_CUDA(expr)                                                                                  \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) {                                                                               \
+      ::b200rl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);     \
+      return 1;                                                                                            \
+    }                                                                                                      \
+  } while (0)
+
+#define B200RL_REQUIRE(cond, ...)         \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::b200rl::set_error(__VA_ARGS__);   \
+      return 2;                           \
+    }                                     \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int pad4(int x) { return (x + 3) & ~3; }
+
+int device_sm_count();
+
+// global launch counter (bench.py reports gpu_launches from it)
+void count_launch(int n = 1);
+int64_t launches_total();
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace b200rl

@@ -1,0 +1,512 @@
+// On-policy update engine: device-resident batch + flat parameters + Adam state, and the whole per-epoch update
+// (the reference's PPO.train / VPG.train, /root/reference/src/rl_replicas/algorithms/ppo.py:139-223, vpg.py:127-192)
+// as a host-sync-free stream of kernel launches.  See include/b200rl.h for the C ABI.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200rl {
+
+static thread_local std::string g_error;
+static int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+void count_launch(int n) { g_launches += n; }
+int64_t launches_total() { return g_launches; }
+
+int device_sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return sms;
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" const char* b200rl_last_error(void) { return g_error.c_str(); }
+extern "C" int b200rl_version(void) { return B200RL_VERSION; }
+extern "C" int64_t b200rl_launch_count(void) { return launches_total(); }
+
+struct b200rl_onpolicy {
+  b200rl_onpolicy_config cfg;
+  int64_t Pp = 0, Pv = 0;
+  int grid_cap = 0;
+  int obs_dim = 0, act_cols = 0;
+  // batch
+  float *obs = nullptr, *act = nullptr, *last_obs = nullptr;
+  void* rew = nullptr;
+  int64_t* off = nullptr;
+  uint8_t* done = nullptr;
+  int64_t n_rows = 0, n_ep = 0;
+  // derived
+  float *values = nullptr, *last_values = nullptr, *adv_raw = nullptr, *ret = nullptr, *old_logp = nullptr;
+  double* adv_stats = nullptr;
+  void* scan_ws = nullptr;
+  size_t scan_ws_bytes = 0;
+  // parameters / optimiser state
+  float *pol = nullptr, *old_pol = nullptr, *val = nullptr, *log_std = nullptr;
+  float *pol_m = nullptr, *pol_v = nullptr, *val_m = nullptr, *val_v = nullptr;
+  int64_t pol_step = 0, val_step = 0;
+  // workspaces
+  float* partials = nullptr;
+  double* scalar_partials = nullptr;
+  float *pol_grad = nullptr, *val_grad = nullptr;  // [P + N_SCALARS]
+  double* slots = nullptr;                         // [n_slots][N_SCALARS] scalar history
+  int n_slots = 0;
+  int* flags = nullptr;  // 0 stop flag, 1 policy steps applied, 2 value steps applied
+  double* h_slots = nullptr;  // pinned
+  int* h_flags = nullptr;     // pinned
+  double* h_stats3 = nullptr; // pinned
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(b200rl_onpolicy* h, T** p, size_t count) {
+  void* q = nullptr;
+  B200RL_CUDA(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+  B200RL_CUDA(cudaMemset(q, 0, (count ? count : 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+int ensure_slots(b200rl_onpolicy* h, int n) {
+  if (n <= h->n_slots) return 0;
+  if (h->h_slots) cudaFreeHost(h->h_slots);
+  h->h_slots = nullptr;
+  double* d = nullptr;
+  if (dev_alloc(h, &d, (size_t)n * B200RL_N_SCALARS)) return 1;
+  h->slots = d;
+  B200RL_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_slots), (size_t)n * B200RL_N_SCALARS * sizeof(double)));
+  h->n_slots = n;
+  return 0;
+}
+
+struct Net {
+  const b200rl_mlp_desc* mlp;
+  float* params;
+  int64_t P;
+};
+
+// one fused launch over the loaded batch
+int launch_fused(b200rl_onpolicy* h, const b200rl_mlp_desc& mlp, int loss, int dist, const float* params,
+                 const float* obs, int64_t n_rows, int64_t n_global, double clip, bool use_adv, bool use_old,
+                 float* row_out, bool want_scalars, const int* skip, cudaStream_t s) {
+  b200rl_mlp_loss_grad_args a;
+  memset(&a, 0, sizeof(a));
+  a.mlp = mlp;
+  a.loss = loss;
+  a.dist = dist;
+  a.n_rows = n_rows;
+  a.n_global = n_global;
+  a.clip_range = (float)clip;
+  a.params = params;
+  a.obs = obs;
+  if (dist != B200RL_DIST_NONE) {
+    a.actions = h->act;
+    a.log_std = h->log_std;
+  }
+  if (use_adv) {
+    a.adv_raw = h->adv_raw;
+    a.adv_stats = h->adv_stats;
+  }
+  if (use_old) a.old_logp = h->old_logp;
+  if (loss == B200RL_LOSS_MSE) a.target = h->ret;
+  a.row_out = row_out;
+  a.partials = h->partials;
+  a.scalar_partials = want_scalars ? h->scalar_partials : nullptr;
+  a.skip_flag = skip;
+  return b200rl_mlp_loss_grad(&a, s);
+}
+
+}  // namespace
+
+extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_onpolicy** out) {
+  B200RL_REQUIRE(cfg && out, "onpolicy_create: NULL argument");
+  B200RL_REQUIRE(cfg->max_rows > 0 && cfg->max_episodes > 0, "onpolicy_create: capacities must be positive");
+  const int64_t Pp = b200rl_mlp_param_count(&cfg->policy), Pv = b200rl_mlp_param_count(&cfg->value);
+  B200RL_REQUIRE(Pp > 0 && Pv > 0, "onpolicy_create: invalid MLP description");
+  B200RL_REQUIRE(cfg->policy.sizes[0] == cfg->value.sizes[0], "onpolicy_create: policy/value observation widths differ");
+  B200RL_REQUIRE(cfg->value.sizes[cfg->value.n_layers] == 1, "onpolicy_create: value network must have one output");
+  B200RL_REQUIRE(cfg->dist == B200RL_DIST_GAUSSIAN || cfg->dist == B200RL_DIST_CATEGORICAL,
+                 "onpolicy_create: dist must be GAUSSIAN or CATEGORICAL");
+  const int sms = device_sm_count();
+  B200RL_REQUIRE(sms > 0, "onpolicy_create: no CUDA device (%s)", cudaGetErrorString(cudaGetLastError()));
+  b200rl_onpolicy* h = new b200rl_onpolicy();
+  h->cfg = *cfg;
+  h->Pp = Pp;
+  h->Pv = Pv;
+  h->grid_cap = sms;
+  h->obs_dim = cfg->policy.sizes[0];
+  const int A = cfg->policy.sizes[cfg->policy.n_layers];
+  h->act_cols = cfg->dist == B200RL_DIST_GAUSSIAN ? A : 1;
+  const size_t N = (size_t)cfg->max_rows, E = (size_t)cfg->max_episodes;
+  const size_t Pmax = (size_t)(Pp > Pv ? Pp : Pv);
+  int rc = 0;
+  rc |= dev_alloc(h, &h->obs, N * h->obs_dim);
+  rc |= dev_alloc(h, &h->act, N * h->act_cols);
+  rc |= dev_alloc(h, &h->last_obs, E * h->obs_dim);
+  rc |= dev_alloc(h, reinterpret_cast<char**>(&h->rew), N * (cfg->rewards_f64 ? 8 : 4));
+  rc |= dev_alloc(h, &h->off, E + 1);
+  rc |= dev_alloc(h, &h->done, E);
+  rc |= dev_alloc(h, &h->values, N);
+  rc |= dev_alloc(h, &h->last_values, E);
+  rc |= dev_alloc(h, &h->adv_raw, N);
+  rc |= dev_alloc(h, &h->ret, N);
+  rc |= dev_alloc(h, &h->old_logp, N);
+  rc |= dev_alloc(h, &h->adv_stats, 4);
+  h->scan_ws_bytes = b200rl_gae_scan_workspace_bytes(cfg->max_rows);
+  rc |= dev_alloc(h, reinterpret_cast<char**>(&h->scan_ws), h->scan_ws_bytes);
+  rc |= dev_alloc(h, &h->pol, (size_t)Pp);
+  rc |= dev_alloc(h, &h->old_pol, (size_t)Pp);
+  rc |= dev_alloc(h, &h->val, (size_t)Pv);
+  rc |= dev_alloc(h, &h->log_std, 16);
+  rc |= dev_alloc(h, &h->pol_m, (size_t)Pp);
+  rc |= dev_alloc(h, &h->pol_v, (size_t)Pp);
+  rc |= dev_alloc(h, &h->val_m, (size_t)Pv);
+  rc |= dev_alloc(h, &h->val_v, (size_t)Pv);
+  rc |= dev_alloc(h, &h->partials, (size_t)sms * Pmax);
+  rc |= dev_alloc(h, &h->scalar_partials, (size_t)sms * B200RL_N_SCALARS);
+  rc |= dev_alloc(h, &h->pol_grad, (size_t)Pp + B200RL_N_SCALARS);
+  rc |= dev_alloc(h, &h->val_grad, (size_t)Pv + B200RL_N_SCALARS);
+  rc |= dev_alloc(h, &h->flags, 8);
+  if (!rc) rc |= ensure_slots(h, 256);
+  if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), 8 * sizeof(int)) != cudaSuccess) rc = 1;
+  if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_stats3), 4 * sizeof(double)) != cudaSuccess) rc = 1;
+  if (rc) {
+    std::string keep = g_error.empty() ? std::string("onpolicy_create: allocation failed") : g_error;
+    b200rl_onpolicy_destroy(h);
+    g_error = keep;
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" void b200rl_onpolicy_destroy(b200rl_onpolicy* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_slots) cudaFreeHost(h->h_slots);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  if (h->h_stats3) cudaFreeHost(h->h_stats3);
+  delete h;
+}
+
+static float* param_ptr(b200rl_onpolicy* h, int which, int64_t* n) {
+  switch (which) {
+    case 0: *n = h->Pp; return h->pol;
+    case 1: *n = h->Pp; return h->old_pol;
+    case 2: *n = h->Pv; return h->val;
+    default: *n = 0; return nullptr;
+  }
+}
+
+extern "C" int b200rl_onpolicy_set_params(b200rl_onpolicy* h, int which, const float* host_flat, int64_t n,
+                                          void* stream) {
+  B200RL_REQUIRE(h && host_flat, "set_params: NULL argument");
+  int64_t cnt;
+  float* d = param_ptr(h, which, &cnt);
+  B200RL_REQUIRE(d && n == cnt, "set_params: which=%d expects %lld floats, got %lld", which, (long long)cnt, (long long)n);
+  B200RL_CUDA(cudaMemcpyAsync(d, host_flat, (size_t)n * 4, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int b200rl_onpolicy_get_params(b200rl_onpolicy* h, int which, float* host_flat, int64_t n, void* stream) {
+  B200RL_REQUIRE(h && host_flat, "get_params: NULL argument");
+  int64_t cnt;
+  float* d = param_ptr(h, which, &cnt);
+  B200RL_REQUIRE(d && n == cnt, "get_params: which=%d expects %lld floats, got %lld", which, (long long)cnt, (long long)n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200RL_CUDA(cudaMemcpyAsync(host_flat, d, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int b200rl_onpolicy_set_adam(b200rl_onpolicy* h, int which, const float* exp_avg, const float* exp_avg_sq,
+                                        int64_t n, int64_t step, void* stream) {
+  B200RL_REQUIRE(h && (which == 0 || which == 2), "set_adam: which must be 0 (policy) or 2 (value)");
+  const int64_t cnt = which == 0 ? h->Pp : h->Pv;
+  B200RL_REQUIRE(n == cnt && step >= 0, "set_adam: expects %lld floats, got %lld", (long long)cnt, (long long)n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* m = which == 0 ? h->pol_m : h->val_m;
+  float* v = which == 0 ? h->pol_v : h->val_v;
+  if (exp_avg) B200RL_CUDA(cudaMemcpyAsync(m, exp_avg, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  else B200RL_CUDA(cudaMemsetAsync(m, 0, (size_t)n * 4, s));
+  if (exp_avg_sq) B200RL_CUDA(cudaMemcpyAsync(v, exp_avg_sq, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  else B200RL_CUDA(cudaMemsetAsync(v, 0, (size_t)n * 4, s));
+  (which == 0 ? h->pol_step : h->val_step) = step;
+  return 0;
+}
+
+extern "C" int b200rl_onpolicy_get_adam(b200rl_onpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                        int64_t* step, void* stream) {
+  B200RL_REQUIRE(h && (which == 0 || which == 2) && exp_avg && exp_avg_sq && step, "get_adam: bad arguments");
+  const int64_t cnt = which == 0 ? h->Pp : h->Pv;
+  B200RL_REQUIRE(n == cnt, "get_adam: expects %lld floats, got %lld", (long long)cnt, (long long)n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200RL_CUDA(cudaMemcpyAsync(exp_avg, which == 0 ? h->pol_m : h->val_m, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(exp_avg_sq, which == 0 ? h->pol_v : h->val_v, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  *step = which == 0 ? h->pol_step : h->val_step;
+  return 0;
+}
+
+extern "C" int b200rl_onpolicy_set_log_std(b200rl_onpolicy* h, const float* host_log_std, int64_t n, void* stream) {
+  B200RL_REQUIRE(h && host_log_std, "set_log_std: NULL argument");
+  B200RL_REQUIRE(h->cfg.dist == B200RL_DIST_GAUSSIAN && n == h->act_cols, "set_log_std: expects %d floats", h->act_cols);
+  B200RL_CUDA(cudaMemcpyAsync(h->log_std, host_log_std, (size_t)n * 4, cudaMemcpyHostToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int b200rl_onpolicy_load_batch(b200rl_onpolicy* h, const float* obs, const float* actions,
+                                          const void* rewards, const float* last_obs, const int64_t* ep_offsets,
+                                          const uint8_t* ep_done, int64_t n_rows, int64_t n_episodes,
+                                          int src_on_device, void* stream) {
+  B200RL_REQUIRE(h && obs && actions && rewards && last_obs && ep_offsets && ep_done, "load_batch: NULL argument");
+  B200RL_REQUIRE(n_rows >= 1 && n_rows <= h->cfg.max_rows, "load_batch: n_rows %lld exceeds capacity %lld",
+                 (long long)n_rows, (long long)h->cfg.max_rows);
+  B200RL_REQUIRE(n_episodes >= 1 && n_episodes <= h->cfg.max_episodes,
+                 "load_batch: n_episodes %lld exceeds capacity %lld", (long long)n_episodes,
+                 (long long)h->cfg.max_episodes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const cudaMemcpyKind k = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (!src_on_device) {  // host-side validation of the CSR structure (cheap; the scan relies on it)
+    B200RL_REQUIRE(ep_offsets[0] == 0 && ep_offsets[n_episodes] == n_rows,
+                   "load_batch: ep_offsets must start at 0 and end at n_rows");
+    for (int64_t e = 0; e < n_episodes; ++e)
+      B200RL_REQUIRE(ep_offsets[e + 1] > ep_offsets[e], "load_batch: episode %lld is empty", (long long)e);
+  }
+  B200RL_CUDA(cudaMemcpyAsync(h->obs, obs, (size_t)n_rows * h->obs_dim * 4, k, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->act, actions, (size_t)n_rows * h->act_cols * 4, k, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->rew, rewards, (size_t)n_rows * (h->cfg.rewards_f64 ? 8 : 4), k, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->last_obs, last_obs, (size_t)n_episodes * h->obs_dim * 4, k, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->off, ep_offsets, (size_t)(n_episodes + 1) * 8, k, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->done, ep_done, (size_t)n_episodes, k, s));
+  h->n_rows = n_rows;
+  h->n_ep = n_episodes;
+  return 0;
+}
+
+// ---- the shared preamble of PPO / VPG / TRPO train(): value inference -> scan -> (all-reduce of 3 scalars) ----
+static int run_preamble(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
+                        cudaStream_t s) {
+  // utils.py:60-71 compute_values: V(obs_t) for every step and V(last_observation) for every episode
+  if (launch_fused(h, h->cfg.value, B200RL_LOSS_EVAL, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, h->n_rows, 0.0,
+                   false, false, h->values, false, nullptr, s)) return 1;
+  if (launch_fused(h, h->cfg.value, B200RL_LOSS_EVAL, B200RL_DIST_NONE, h->val, h->last_obs, h->n_ep, h->n_ep, 0.0,
+                   false, false, h->last_values, false, nullptr, s)) return 1;
+  if (b200rl_gae_scan(h->rew, h->cfg.rewards_f64, h->values, h->last_values, h->off, h->done, h->n_rows, h->n_ep,
+                      hp->gamma, hp->gae_lambda, h->adv_raw, h->ret, h->adv_stats, h->scan_ws, h->scan_ws_bytes, s))
+    return 1;
+  // normalize_tensor (utils.py:90-92) is over the GLOBAL batch: one 3-scalar all-reduce per update
+  if (ar && ar(user, h->adv_stats, 3, 1, s)) {
+    set_error("allreduce callback failed (advantage statistics)");
+    return 1;
+  }
+  return 0;
+}
+
+static int run_value_loop(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
+                          int64_t n_glob, int slot0, cudaStream_t s) {
+  const int grid = b200rl_mlp_grid(&h->cfg.value, h->n_rows, 1);
+  for (int j = 0; j < hp->num_value_gradients; ++j) {  // ppo.py:186-192
+    double* slot = h->slots + (size_t)(slot0 + j) * B200RL_N_SCALARS;
+    if (launch_fused(h, h->cfg.value, B200RL_LOSS_MSE, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, n_glob, 0.0,
+                     false, false, nullptr, true, nullptr, s)) return 1;
+    if (b200rl_reduce_partials(h->partials, h->scalar_partials, grid, h->Pv, h->val_grad, slot, ar ? 1 : 0, nullptr, s))
+      return 1;
+    if (ar && ar(user, h->val_grad, h->Pv + B200RL_N_SCALARS, 0, s)) {
+      set_error("allreduce callback failed (value gradient)");
+      return 1;
+    }
+    if (b200rl_adam_step(h->val, h->val_grad, h->val_m, h->val_v, h->Pv, h->val_step + j + 1, hp->value_lr,
+                         hp->value_beta1, hp->value_beta2, hp->value_eps, nullptr, 0, (double)n_glob, 0.0, nullptr,
+                         h->flags + 2, ar ? h->val_grad + h->Pv : nullptr, ar ? slot : nullptr, s))
+      return 1;
+  }
+  return 0;
+}
+
+static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
+                      b200rl_update_stats* stats, void* stream, int policy_loss) {
+  B200RL_REQUIRE(h && hp && stats, "update: NULL argument");
+  B200RL_REQUIRE(h->n_rows > 0, "update: no batch loaded");
+  B200RL_REQUIRE(hp->num_policy_gradients >= 0 && hp->num_value_gradients >= 0, "update: negative step count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t launches0 = launches_total();
+  const int64_t n_glob = hp->n_global_rows > 0 ? hp->n_global_rows : h->n_rows;
+  const bool ppo = policy_loss == B200RL_LOSS_PPO_CLIP;
+  const int K = ppo ? hp->num_policy_gradients : 1;
+  const int Kv = hp->num_value_gradients;
+  if (ensure_slots(h, K + Kv + 4)) return 1;
+  B200RL_CUDA(cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), s));
+  B200RL_CUDA(cudaMemsetAsync(h->slots, 0, (size_t)(K + Kv + 4) * B200RL_N_SCALARS * sizeof(double), s));
+
+  if (run_preamble(h, hp, ar, user, s)) return 1;
+
+  const int dist = h->cfg.dist;
+  const int grid_p = b200rl_mlp_grid(&h->cfg.policy, h->n_rows, 1);
+  const int grid_e = b200rl_mlp_grid(&h->cfg.policy, h->n_rows, 0);
+  int* stop = ppo ? h->flags : nullptr;
+  if (ppo) {
+    // ppo.py:241-243: old_policy is frozen for the whole epoch => its log-probs are computed once
+    if (launch_fused(h, h->cfg.policy, B200RL_LOSS_EVAL, dist, h->old_pol, h->obs, h->n_rows, n_glob, 0.0, false,
+                     false, h->old_logp, false, nullptr, s)) return 1;
+  }
+  for (int i = 0; i < K; ++i) {  // ppo.py:173-181 / vpg.py:194-207
+    double* slot = h->slots + (size_t)i * B200RL_N_SCALARS;
+    if (launch_fused(h, h->cfg.policy, policy_loss, dist, h->pol, h->obs, h->n_rows, n_glob, hp->clip_range, true,
+                     ppo, nullptr, true, stop, s)) return 1;
+    if (b200rl_reduce_partials(h->partials, h->scalar_partials, grid_p, h->Pp, h->pol_grad, slot, ar ? 1 : 0, stop, s))
+      return 1;
+    if (ar && ar(user, h->pol_grad, h->Pp + B200RL_N_SCALARS, 0, s)) {
+      set_error("allreduce callback failed (policy gradient)");
+      return 1;
+    }
+    // KL carried by this forward pass = approx KL after the previous update (ppo.py:176-181), checked on device
+    const void* kl = !ppo ? nullptr : (ar ? static_cast<const void*>(h->pol_grad + h->Pp + 1)
+                                          : static_cast<const void*>(slot + 1));
+    if (b200rl_adam_step(h->pol, h->pol_grad, h->pol_m, h->pol_v, h->Pp, h->pol_step + i + 1, hp->policy_lr,
+                         hp->policy_beta1, hp->policy_beta2, hp->policy_eps, kl, ar ? 1 : 0, (double)n_glob,
+                         1.5 * hp->max_kl_divergence, stop, h->flags + 1, ar ? h->pol_grad + h->Pp : nullptr,
+                         ar ? slot : nullptr, s))
+      return 1;
+  }
+  if (ppo) {
+    // KL after the last update (only reached when no early stop fired): forward-only pass, slot K
+    double* slot = h->slots + (size_t)K * B200RL_N_SCALARS;
+    if (launch_fused(h, h->cfg.policy, B200RL_LOSS_EVAL, dist, h->pol, h->obs, h->n_rows, n_glob, 0.0, false, true,
+                     nullptr, true, stop, s)) return 1;
+    if (b200rl_reduce_partials(nullptr, h->scalar_partials, grid_e, h->Pp, nullptr, slot, 0, stop, s)) return 1;
+    if (ar && ar(user, slot, B200RL_N_SCALARS, 1, s)) {
+      set_error("allreduce callback failed (final KL)");
+      return 1;
+    }
+    // ppo.py:183: old_policy.load_state_dict(policy.state_dict())
+    B200RL_CUDA(cudaMemcpyAsync(h->old_pol, h->pol, (size_t)h->Pp * 4, cudaMemcpyDeviceToDevice, s));
+  }
+
+  if (run_value_loop(h, hp, ar, user, n_glob, K + 1, s)) return 1;
+
+  // ---- one device->host read of the statistics ----
+  B200RL_CUDA(cudaMemcpyAsync(h->h_slots, h->slots, (size_t)(K + Kv + 2) * B200RL_N_SCALARS * sizeof(double),
+                              cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->h_stats3, h->adv_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+
+  memset(stats, 0, sizeof(*stats));
+  const double ng = (double)n_glob;
+  const int applied_p = h->h_flags[1], applied_v = h->h_flags[2];
+  const double* s0 = h->h_slots;
+  stats->policy_loss_before = K > 0 ? s0[0] / ng : NAN;
+  stats->entropy_before = K > 0 ? s0[2] / ng : NAN;
+  {
+    const double mean = s0[3] / ng;
+    stats->logp_std_before = K > 0 ? sqrt(fmax(0.0, (s0[4] - ng * mean * mean) / (ng - 1.0))) : NAN;
+  }
+  stats->kl_divergence = ppo ? h->h_slots[(size_t)applied_p * B200RL_N_SCALARS + 1] / ng : NAN;
+  double vsum = 0.0;
+  for (int j = 0; j < Kv; ++j) vsum += h->h_slots[(size_t)(K + 1 + j) * B200RL_N_SCALARS] / ng;
+  stats->value_loss_mean = Kv > 0 ? vsum / Kv : NAN;
+  stats->value_loss_first = Kv > 0 ? h->h_slots[(size_t)(K + 1) * B200RL_N_SCALARS] / ng : NAN;
+  stats->value_loss_last = Kv > 0 ? h->h_slots[(size_t)(K + Kv) * B200RL_N_SCALARS] / ng : NAN;
+  stats->policy_steps_applied = applied_p;
+  stats->value_steps_applied = applied_v;
+  {
+    const double cnt = h->h_stats3[2], mean = h->h_stats3[0] / cnt;
+    stats->adv_mean = mean;
+    stats->adv_std = sqrt((h->h_stats3[1] - cnt * mean * mean) / (cnt - 1.0));
+  }
+  h->pol_step += applied_p;
+  h->val_step += applied_v;
+  stats->kernel_launches = (int32_t)(launches_total() - launches0);
+  return 0;
+}
+
+extern "C" int b200rl_ppo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn allreduce,
+                                 void* user, b200rl_update_stats* stats, void* stream) {
+  return run_update(h, hp, allreduce, user, stats, stream, B200RL_LOSS_PPO_CLIP);
+}
+
+extern "C" int b200rl_vpg_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn allreduce,
+                                 void* user, b200rl_update_stats* stats, void* stream) {
+  return run_update(h, hp, allreduce, user, stats, stream, B200RL_LOSS_VPG);
+}
+
+extern "C" int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr, int64_t* count,
+                                           int32_t* dtype) {
+  B200RL_REQUIRE(h && name && ptr && count && dtype, "device_view: NULL argument");
+  struct V { const char* n; void* p; int64_t c; int32_t d; };
+  const V views[] = {
+      {"values", h->values, h->n_rows, 0},        {"last_values", h->last_values, h->n_ep, 0},
+      {"adv_raw", h->adv_raw, h->n_rows, 0},      {"ret", h->ret, h->n_rows, 0},
+      {"old_logp", h->old_logp, h->n_rows, 0},    {"adv_stats", h->adv_stats, 3, 1},
+      {"policy_grad", h->pol_grad, h->Pp + B200RL_N_SCALARS, 0},
+      {"value_grad", h->val_grad, h->Pv + B200RL_N_SCALARS, 0},
+      {"policy_params", h->pol, h->Pp, 0},        {"old_policy_params", h->old_pol, h->Pp, 0},
+      {"value_params", h->val, h->Pv, 0},         {"obs", h->obs, h->n_rows * h->obs_dim, 0},
+  };
+  for (const V& v : views)
+    if (strcmp(v.n, name) == 0) {
+      *ptr = v.p;
+      *count = v.c;
+      *dtype = v.d;
+      return 0;
+    }
+  set_error("device_view: unknown view '%s'", name);
+  return 2;
+}
+
+// Single stages on the loaded batch, for kernel-level timing (bench.py roofline) and ncu captures.
+extern "C" int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, const b200rl_ppo_hparams* hp,
+                                         void* stream) {
+  B200RL_REQUIRE(h && stage && hp, "run_stage: NULL argument");
+  B200RL_REQUIRE(h->n_rows > 0, "run_stage: no batch loaded");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t n_glob = hp->n_global_rows > 0 ? hp->n_global_rows : h->n_rows;
+  if (strcmp(stage, "values") == 0)
+    return launch_fused(h, h->cfg.value, B200RL_LOSS_EVAL, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, h->n_rows, 0.0,
+                        false, false, h->values, false, nullptr, s);
+  if (strcmp(stage, "preamble") == 0) return run_preamble(h, hp, nullptr, nullptr, s);
+  if (strcmp(stage, "scan") == 0)
+    return b200rl_gae_scan(h->rew, h->cfg.rewards_f64, h->values, h->last_values, h->off, h->done, h->n_rows, h->n_ep,
+                           hp->gamma, hp->gae_lambda, h->adv_raw, h->ret, h->adv_stats, h->scan_ws, h->scan_ws_bytes, s);
+  if (strcmp(stage, "old_logp") == 0)
+    return launch_fused(h, h->cfg.policy, B200RL_LOSS_EVAL, h->cfg.dist, h->old_pol, h->obs, h->n_rows, n_glob, 0.0,
+                        false, false, h->old_logp, false, nullptr, s);
+  if (strcmp(stage, "policy_grad") == 0) {
+    if (launch_fused(h, h->cfg.policy, B200RL_LOSS_PPO_CLIP, h->cfg.dist, h->pol, h->obs, h->n_rows, n_glob,
+                     hp->clip_range, true, true, nullptr, true, nullptr, s)) return 1;
+    return b200rl_reduce_partials(h->partials, h->scalar_partials, b200rl_mlp_grid(&h->cfg.policy, h->n_rows, 1),
+                                  h->Pp, h->pol_grad, h->slots, 0, nullptr, s);
+  }
+  if (strcmp(stage, "policy_grad_kernel") == 0)
+    return launch_fused(h, h->cfg.policy, B200RL_LOSS_PPO_CLIP, h->cfg.dist, h->pol, h->obs, h->n_rows, n_glob,
+                        hp->clip_range, true, true, nullptr, true, nullptr, s);
+  if (strcmp(stage, "value_grad") == 0) {
+    if (launch_fused(h, h->cfg.value, B200RL_LOSS_MSE, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, n_glob, 0.0, false,
+                     false, nullptr, true, nullptr, s)) return 1;
+    return b200rl_reduce_partials(h->partials, h->scalar_partials, b200rl_mlp_grid(&h->cfg.value, h->n_rows, 1), h->Pv,
+                                  h->val_grad, h->slots, 0, nullptr, s);
+  }
+  if (strcmp(stage, "value_grad_kernel") == 0)
+    return launch_fused(h, h->cfg.value, B200RL_LOSS_MSE, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, n_glob, 0.0,
+                        false, false, nullptr, true, nullptr, s);
+  set_error("run_stage: unknown stage '%s'", stage);
+  return 2;
+}

@@ -1,0 +1,195 @@
+"""Python handle of the native on-policy update engine (C ABI: include/b200rl.h).
+
+PyTorch is used for plumbing only: picking the CUDA device / current stream, exposing engine-owned device memory
+as tensors (``view``) and torch.distributed collectives for data-parallel runs.  All arithmetic of the update path
+runs in libb200rl.so's CUDA kernels; there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import DIST, MlpDesc, OnPolicyConfig, PpoHparams, UpdateStats, check
+
+POLICY, OLD_POLICY, VALUE = 0, 1, 2
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so torch can wrap engine-owned device memory without copying."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def current_stream_handle() -> int:
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.B200RLError("no CUDA device: the B200 update engine has no CPU fallback")
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+class OnPolicyEngine:
+    """Device-resident state of one PPO / VPG / TRPO learner."""
+
+    def __init__(self, policy_sizes: Sequence[int], value_sizes: Sequence[int], dist: str, max_rows: int,
+                 max_episodes: int, hidden_act: str = "tanh", rewards_f64: bool = True):
+        self.lib = _lib.load()
+        current_stream_handle()  # fail early and loudly without a GPU
+        cfg = OnPolicyConfig()
+        cfg.policy = MlpDesc.make(policy_sizes, hidden_act, "identity")
+        cfg.value = MlpDesc.make(value_sizes, hidden_act, "identity")
+        cfg.dist = DIST[dist]
+        cfg.rewards_f64 = int(rewards_f64)
+        cfg.max_rows, cfg.max_episodes = int(max_rows), int(max_episodes)
+        self.cfg = cfg
+        self.dist = dist
+        self.policy_sizes, self.value_sizes = list(policy_sizes), list(value_sizes)
+        self.rewards_f64 = rewards_f64
+        self.n_policy = int(self.lib.b200rl_mlp_param_count(cfg.policy))
+        self.n_value = int(self.lib.b200rl_mlp_param_count(cfg.value))
+        self.max_rows, self.max_episodes = int(max_rows), int(max_episodes)
+        h = C.c_void_p()
+        check(self.lib.b200rl_onpolicy_create(C.byref(cfg), C.byref(h)), "onpolicy_create")
+        self.h = h
+        self.n_rows = 0
+        self.n_episodes = 0
+        self._allreduce_cb = None
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rl_onpolicy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters / optimiser state -------------------------------------------------------------------------
+    def _n(self, which):
+        return self.n_value if which == VALUE else self.n_policy
+
+    def set_params(self, which: int, flat: np.ndarray):
+        a = _c(flat, np.float32)
+        self._keep.append(a)
+        check(self.lib.b200rl_onpolicy_set_params(self.h, which, _ptr(a), a.size, current_stream_handle()), "set_params")
+
+    def get_params(self, which: int) -> np.ndarray:
+        out = np.empty(self._n(which), dtype=np.float32)
+        check(self.lib.b200rl_onpolicy_get_params(self.h, which, _ptr(out), out.size, current_stream_handle()), "get_params")
+        return out
+
+    def set_adam(self, which: int, exp_avg: Optional[np.ndarray], exp_avg_sq: Optional[np.ndarray], step: int):
+        m = None if exp_avg is None else _c(exp_avg, np.float32)
+        v = None if exp_avg_sq is None else _c(exp_avg_sq, np.float32)
+        self._keep += [m, v]
+        check(self.lib.b200rl_onpolicy_set_adam(self.h, which, _ptr(m), _ptr(v), self._n(which), int(step),
+                                                current_stream_handle()), "set_adam")
+
+    def get_adam(self, which: int):
+        m = np.empty(self._n(which), dtype=np.float32)
+        v = np.empty(self._n(which), dtype=np.float32)
+        step = C.c_int64()
+        check(self.lib.b200rl_onpolicy_get_adam(self.h, which, _ptr(m), _ptr(v), m.size, C.byref(step),
+                                                current_stream_handle()), "get_adam")
+        return m, v, int(step.value)
+
+    def set_log_std(self, log_std: np.ndarray):
+        a = _c(log_std, np.float32)
+        self._keep.append(a)
+        check(self.lib.b200rl_onpolicy_set_log_std(self.h, _ptr(a), a.size, current_stream_handle()), "set_log_std")
+
+    # ---- batch ----------------------------------------------------------------------------------------------
+    def load_batch(self, batch: Dict[str, np.ndarray]):
+        """Copy a packed HOST batch (see synthetic.py for the layout) to the device."""
+        obs = _c(batch["obs"], np.float32)
+        act = _c(batch["act"], np.float32)
+        rew = _c(batch["rew"], np.float64 if self.rewards_f64 else np.float32)
+        last = _c(batch["last_obs"], np.float32)
+        off = _c(batch["ep_offsets"], np.int64)
+        done = _c(batch["ep_done"], np.uint8)
+        n, e = obs.shape[0], done.shape[0]
+        if obs.ndim != 2 or obs.shape[1] != self.policy_sizes[0]:
+            raise ValueError(f"observations must be [N,{self.policy_sizes[0]}], got {obs.shape}")
+        want_act = (n, self.policy_sizes[-1]) if self.dist == "gaussian" else (n,)
+        if act.shape != want_act:
+            raise ValueError(f"actions must have shape {want_act}, got {act.shape}")
+        if rew.shape != (n,) or last.shape != (e, obs.shape[1]) or off.shape != (e + 1,):
+            raise ValueError("inconsistent packed batch shapes")
+        self._keep += [obs, act, rew, last, off, done]  # keep host buffers alive until the stream has consumed them
+        check(self.lib.b200rl_onpolicy_load_batch(self.h, _ptr(obs), _ptr(act), _ptr(rew), _ptr(last), _ptr(off),
+                                                  _ptr(done), n, e, 0, current_stream_handle()), "load_batch")
+        self.n_rows, self.n_episodes = n, e
+
+    def load_batch_device(self, obs, act, rew, last_obs, ep_offsets, ep_done):
+        """Same from torch CUDA tensors already resident in HBM (device-to-device copies)."""
+        n, e = obs.shape[0], ep_done.shape[0]
+        ts = [obs, act, rew, last_obs, ep_offsets, ep_done]
+        assert all(t.is_cuda and t.is_contiguous() for t in ts)
+        check(self.lib.b200rl_onpolicy_load_batch(self.h, *[C.c_void_p(t.data_ptr()) for t in ts], n, e, 1,
+                                                  current_stream_handle()), "load_batch(device)")
+        self.n_rows, self.n_episodes = n, e
+
+    # ---- update ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def hparams(gamma=0.99, gae_lambda=0.97, clip_range=0.2, max_kl_divergence=0.01, num_policy_gradients=80,
+                num_value_gradients=80, policy_adam=(3e-4, 0.9, 0.999, 1e-8), value_adam=(1e-3, 0.9, 0.999, 1e-8),
+                n_global_rows=0) -> PpoHparams:
+        hp = PpoHparams()
+        hp.gamma, hp.gae_lambda, hp.clip_range, hp.max_kl_divergence = gamma, gae_lambda, clip_range, max_kl_divergence
+        hp.num_policy_gradients, hp.num_value_gradients = int(num_policy_gradients), int(num_value_gradients)
+        hp.policy_lr, hp.policy_beta1, hp.policy_beta2, hp.policy_eps = policy_adam
+        hp.value_lr, hp.value_beta1, hp.value_beta2, hp.value_eps = value_adam
+        hp.n_global_rows = int(n_global_rows)
+        return hp
+
+    def _make_allreduce(self, process_group):
+        import torch
+        import torch.distributed as dist
+
+        def cb(user, buf, count, dtype, stream):
+            try:
+                t = torch.as_tensor(_CudaArray(buf, count, "<f8" if dtype == 1 else "<f4"), device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group)
+                return 0
+            except Exception as exc:  # surfaced by the engine as a failed update
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        return _lib.ALLREDUCE_FN(cb)
+
+    def update(self, hp: PpoHparams, algo: str = "ppo", process_group=None, distributed: bool = False) -> UpdateStats:
+        stats = UpdateStats()
+        cb = None
+        if distributed:
+            self._allreduce_cb = self._make_allreduce(process_group)
+            cb = C.cast(self._allreduce_cb, C.c_void_p)
+        fn = {"ppo": self.lib.b200rl_ppo_update, "vpg": self.lib.b200rl_vpg_update}[algo]
+        check(fn(self.h, C.byref(hp), cb, None, C.byref(stats), current_stream_handle()), f"{algo}_update")
+        self._keep.clear()  # the update synchronised the stream: staged host buffers are no longer in flight
+        return stats
+
+    def run_stage(self, stage: str, hp: PpoHparams):
+        check(self.lib.b200rl_onpolicy_run_stage(self.h, stage.encode(), C.byref(hp), current_stream_handle()),
+              f"run_stage({stage})")
+
+    def view(self, name: str):
+        """Engine-owned device buffer as a torch tensor (zero copy)."""
+        import torch
+        p, n, d = C.c_void_p(), C.c_int64(), C.c_int32()
+        check(self.lib.b200rl_onpolicy_device_view(self.h, name.encode(), C.byref(p), C.byref(n), C.byref(d)), "device_view")
+        return torch.as_tensor(_CudaArray(p.value, int(n.value), "<f8" if d.value == 1 else "<f4"), device="cuda")
