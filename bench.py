@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- PPO update throughput (BASELINE.json metric) on synthetic HalfCheetah-shaped batches.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A "step" = one full PPO.train()-equivalent on one batch: value inference on N+E rows -> GAE/return scan ->
+normalisation -> 80 policy-gradient steps (+ final KL pass) -> old-policy sync -> 80 value steps
+(early stop disabled: max_kl = inf, so the work is fixed).
+Workload at N GPUs: 1024 envs x 1000 steps PER GPU (BASELINE configs[1]; configs[4] at N = 8) -- weak scaling.
+
+  value : transitions/s with the batch already resident in HBM (engine.update only).
+  e2e   : same through the public API, PPO.train_packed(host batch): pinned-host -> device copies of the batch,
+          parameter/optimizer-state upload, the update, and the device -> host read-back of parameters,
+          optimizer state and the logged scalars, all inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+OBS, ACT, HID = 17, 6, 64
+POLICY_SIZES, VALUE_SIZES = [OBS, HID, HID, ACT], [OBS, HID, HID, 1]
+N_POLICY, N_VALUE = 80, 80
+# algorithmic fp32-equivalent FLOPs per row (2*MAC), SURVEY.md section 8: policy fwd 11136 / bwd 20096, value 10496 / 18816
+FLOP_POLICY_STEP = 11136 + 20096
+FLOP_VALUE_STEP = 10496 + 18816
+FLOP_PER_TRANSITION = (N_POLICY + 1) * 11136 + N_POLICY * 20096 + (N_VALUE + 1) * 10496 + N_VALUE * 18816
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def make_nets(seed=0):
+    rng = np.random.default_rng(seed)
+    mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+                     for i, o in zip(sz[:-1], sz[1:])]
+    return mk(POLICY_SIZES), mk(VALUE_SIZES), np.full(ACT, -0.5, np.float32)
+
+
+def make_batch(n_envs, horizon, pl, seed):
+    from rl_replicas_b200 import synthetic
+
+    def mean_fn(o):  # on-policy-like actions: mu_theta0(obs) + sigma * noise
+        h = o
+        for i, (w, b) in enumerate(pl):
+            h = h @ w.T + b
+            if i < len(pl) - 1:
+                h = np.tanh(h)
+        return h
+
+    return synthetic.fixed_batch(n_envs, horizon, OBS, ACT, seed=seed, frac_not_done=0.1, mean_fn=mean_fn)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_evt.wait(0.2)
+
+    def summary(self):
+        self.stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_run(steps, warmup, n_envs=64, horizon=1000):
+    """The reference's CPU path for this workload.  The reference itself is Python-on-torch and does not travel to
+    the GPU box, so the arm is oracle/torch_port.py: the same torch CPU calls (F.linear/tanh, distributions, autograd,
+    torch.optim.Adam, scipy lfilter) on all host threads torch will use.  Bounded sample of the same workload:
+    n_envs x horizon transitions, the same 80 + 80 full-batch steps (throughput is size-independent to first order)."""
+    import torch
+    from oracle import onpolicy as O, torch_port as T
+    pl, vl, log_std = make_nets()
+    b = make_batch(n_envs, horizon, pl, seed=0)
+    n = n_envs * horizon
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        T.ppo_train(b, pl, vl, "gaussian", log_std, max_kl=float("inf"), n_policy=N_POLICY, n_value=N_VALUE)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    best = float(np.mean(times))
+    return dict(value=n / best, unit="transitions/s", cores=int(torch.get_num_threads()), kind="port",
+                host_cpus=os.cpu_count(),
+                sample=f"{n_envs} envs x {horizon} steps = {n} transitions, {N_POLICY}+{N_VALUE} full-batch steps, "
+                       f"torch-CPU port of the reference (oracle/torch_port.py), mean of {len(times)} run(s)"), best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, sec = cpu_reference_run(args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "ppo_update_transitions_per_sec", "value": cb["value"],
+            "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, envs=1024, horizon=1000):
+    return {"workload": f"PPO synthetic HalfCheetah-shaped obs({OBS}) act({ACT}), {envs} envs x {horizon} steps per GPU"
+                        f" ({envs * n_gpus} envs total), MLP(64,64) Gaussian policy + value, {N_POLICY}+{N_VALUE} "
+                        f"full-batch Adam steps, max_kl=inf",
+            "envs_per_gpu": envs, "horizon": horizon, "parallelism": f"dp{n_gpus} (shard by environment)",
+            "l2": "L2 flushed (256 MiB write) before every timed step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=1024)
+    ap.add_argument("--horizon", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from oracle import onpolicy as O  # only for the cpu_baseline leg and to flatten the initial nets
+    from rl_replicas_b200 import _lib
+    from test_gpu_ppo import build as build_algo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or not distributed, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    lib = _lib.load()
+    pk = peaks()
+
+    pl, vl, log_std = make_nets()
+    E, T = args.envs, args.horizon
+    n_local = E * T
+    batch = make_batch(E, T, pl, seed=rank)
+    # pinned host staging for the e2e leg
+    pinned = {}
+    for k, v in batch.items():
+        t = torch.from_numpy(np.ascontiguousarray(v if k != "ep_done" else v.astype(np.uint8)))
+        pinned[k] = t.pin_memory().numpy()
+    h2d = sum(pinned[k].nbytes for k in pinned) + 2 * (5702 * 4 * 3 + 5377 * 4 * 3) // 2 + 5702 * 4 + ACT * 4
+    d2h = (5702 + 5377) * 4 * 3 + 13 * 8
+
+    ppo = build_algo(POLICY_SIZES, VALUE_SIZES, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std,
+                     num_policy_gradients=N_POLICY, num_value_gradients=N_VALUE, max_kl_divergence=float("inf"),
+                     distributed=distributed)
+    ppo.metrics_manager = None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush, outside the timed events
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            total += ev0.elapsed_time(ev1)
+        barrier()
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps  # ms per step, max over ranks
+
+    # ---------------- e2e: public API with host buffers ----------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = lib.b200rl_launch_count()
+    ms_e2e = timed(lambda: ppo.train_packed(pinned), args.steps, args.warmup)
+    launches_per_step = (lib.b200rl_launch_count() - l0) // (args.steps + args.warmup)
+
+    # ---------------- value: batch resident in HBM ----------------
+    engine = ppo._engine
+    hp = ppo._hparams(engine, n_local * world if distributed else 0)
+
+    def device_step():
+        engine.update(hp, "ppo", None, distributed)
+
+    ms_dev = timed(device_step, args.steps, args.warmup)
+    clocks = sampler.summary() if sampler else None
+
+    # ---------------- kernel-level rooflines (rank 0, N = 1 semantics: per-GPU kernels) ----------------
+    def stage_ms(stage, reps):
+        engine.run_stage(stage, hp)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            engine.run_stage(stage, hp)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps
+
+    ms_pol = stage_ms("policy_grad_kernel", 10)
+    ms_val = stage_ms("value_grad_kernel", 10)
+    scan_reps = 20
+    engine.run_stage("values", hp)
+    ms_scan_pair = stage_ms("scan", scan_reps)  # scan kernel + 1-CTA finalize + memset node
+    tf_pol = FLOP_POLICY_STEP * n_local / (ms_pol * 1e-3) / 1e12
+    tf_val = FLOP_VALUE_STEP * n_local / (ms_val * 1e-3) / 1e12
+    scan_bytes = (8 + 4 + 4 + 4) * n_local  # f64 rewards + values in, adv + ret out
+    gbs_scan = scan_bytes / (ms_scan_pair * 1e-3) / 1e9
+
+    if rank == 0:
+        total_transitions = n_local * world
+        value = total_transitions / (ms_dev * 1e-3)
+        e2e = total_transitions / (ms_e2e * 1e-3)
+        line = {
+            "metric": "ppo_update_transitions_per_sec", "value": value, "unit": "transitions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world, E, T),
+            "e2e": {"value": e2e, "unit": "transitions/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": {"kernel": "mlp_fused_kernel<64,true> (policy fwd+loss+bwd, one launch per policy step)",
+                         "bound": "tensor", "achieved": tf_pol, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                         "frac": tf_pol / pk["tf_sust"], "traffic": None,
+                         "note": f"fp32-equivalent algorithmic FLOPs ({FLOP_POLICY_STEP}/row) over the CUDA-event "
+                                 f"launch time; peak = bf16 sustained GEMM ({pk['src']})",
+                         "ms_per_launch": ms_pol},
+            "roofline_value_kernel": {"bound": "tensor", "achieved": tf_val, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                                      "frac": tf_val / pk["tf_sust"], "ms_per_launch": ms_val},
+            "roofline_scan": {"kernel": "gae_scan_kernel<double> (+finalize)", "bound": "hbm", "achieved": gbs_scan,
+                              "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_scan / pk["hbm"], "traffic": None,
+                              "bytes_per_transition": 20, "ms_per_launch": ms_scan_pair,
+                              "note": "16.4 MB problem: launch-latency bound at this size (SURVEY 7.3-3)"},
+            "update_flops_per_transition": FLOP_PER_TRANSITION,
+            "update_tflops_fp32_equiv": FLOP_PER_TRANSITION * total_transitions / (ms_dev * 1e-3) / 1e12,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_reference_run(1, 0)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,3 +114,25 @@ def test_vpg_first_gradient():
     r = O.policy_loss_and_grad(policy, kind, log_std, b["obs"], b["act"], adv, None, "vpg")
     assert rel_err(r["grad"], g["grad0"]) < TOL
     assert abs(r["loss"] - g["metric:policy/loss"]) < 1e-6
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_torch_port_matches_reference(case):
+    """oracle/torch_port.py (the CPU-baseline arm) issues the reference's own torch calls: it must track the
+    reference's outputs to float32 round-off over the whole update."""
+    import torch
+    from oracle import torch_port as T
+    g = load_golden(case)
+    policy, value, kind, log_std = _setup(g)
+    hp = dict(max_kl=float("inf")) if "inf" in str(g["hp_json"]) else {}
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)  # the fixtures were generated single-threaded
+    try:
+        out = T.ppo_train(batch_of(g), policy, value, kind, log_std, **hp)
+    finally:
+        torch.set_num_threads(nt)
+    assert out["policy_steps"] == len(g["kl_trace"])
+    assert rel_err(out["policy_flat"], g["policy_flat_final"]) < 1e-5
+    assert rel_err(out["value_flat"], g["value_flat_final"]) < 1e-5
+    assert rel_err(out["value_losses"], g["value_losses"]) < 1e-5
+    assert rel_err(out["ret"], g["ret"]) < 1e-6 and rel_err(out["adv"], g["adv"]) < 1e-5
