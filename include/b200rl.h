@@ -206,6 +206,15 @@ int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr
 /* Whole path through HOST buffers (what `e2e` in bench.py times): H2D batch + parameters/Adam state, update, D2H. */
 int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, const b200rl_ppo_hparams* hp, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Diagnostics (not on the product path): issue a chain of tcgen05.mma kind::tf32 instructions on a caller-supplied
+ * shared-memory image and return the raw TMEM contents [128 lanes, read_cols]; tests use it to pin the descriptor
+ * and TMEM layouts the tensor-core kernels rely on.  mmas: array of {u64 adesc, u64 bdesc, u32 idesc, u32 dcol,
+ * u32 accumulate, u32 pad}, descriptor start addresses relative to the 1024-byte-aligned image base.
+ * ------------------------------------------------------------------------------------------------------------ */
+int b200rl_tc_probe(const uint32_t* image_dev, int image_words, const void* mmas_dev, int n_mma, int read_cols,
+                    float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,7 @@ SIGNATURES = {
                                     C.POINTER(UpdateStats), C.c_void_p]),
     "b200rl_onpolicy_device_view": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                               C.POINTER(C.c_int32)]),
+    "b200rl_tc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200rl_onpolicy_run_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(PpoHparams), C.c_void_p]),
 }
 
