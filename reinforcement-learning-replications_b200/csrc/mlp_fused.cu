@@ -16,6 +16,7 @@
 //     are written once as partials[cta][P]; b200rl_reduce_partials sums them in a fixed order.
 //   * HBM reads per row: obs (4*O) + actions (4*A) + adv_raw (4) + old_logp (4) [policy] or target (4) [value].
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -452,6 +453,18 @@ static int fused_grid(const MlpLayout& lay, int64_t n_rows) {
   return (int)(tiles < sms ? (tiles < 1 ? 1 : tiles) : sms);
 }
 
+// tensor-core path (mlp_tc.cu)
+bool tc_shape_ok(const b200rl_mlp_desc& d);
+int tc_grid(int64_t n_rows);
+int launch_mlp_tc(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s);
+
+// B200RL_DISABLE_TC=1 forces the fp32 CUDA-core kernel (A/B parity runs); read on every call so tests can flip it.
+static bool use_tc(const b200rl_mlp_desc& d) {
+  const char* e = getenv("B200RL_DISABLE_TC");
+  if (e != nullptr && e[0] == '1') return false;
+  return tc_shape_ok(d);
+}
+
 }  // namespace b200rl
 
 using namespace b200rl;
@@ -468,6 +481,7 @@ extern "C" int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp) {
 
 extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward) {
   if (!mlp) return -1;
+  if (use_tc(*mlp)) return tc_grid(n_rows);
   MlpLayout lay;
   if (build_layout(*mlp, with_backward != 0, &lay)) return -1;
   return fused_grid(lay, n_rows);
@@ -499,6 +513,7 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
       B200RL_REQUIRE(a->old_logp, "mlp_loss_grad: PPO/TRPO loss needs old_logp");
   }
   if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
+  if (use_tc(a->mlp)) return launch_mlp_tc(a, a->n_global > 0 ? a->n_global : a->n_rows, s);
   const size_t smem_bytes = (size_t)k.lay.total_floats * sizeof(float);
   B200RL_REQUIRE(smem_bytes <= 227 * 1024,
                  "mlp_loss_grad: network needs %zu bytes of shared memory (> 227 KiB); too large for the fused kernel",
