@@ -274,7 +274,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": {"kernel": "mlp_fused_kernel<64,true> (policy fwd+loss+bwd, one launch per policy step)",
+            "roofline": {"kernel": "mlp_tc_kernel<true> (tcgen05 policy fwd+loss+bwd, one launch per policy step)",
                          "bound": "tensor", "achieved": tf_pol, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": tf_pol / pk["tf_sust"], "traffic": None,
                          "note": f"fp32-equivalent algorithmic FLOPs ({FLOP_POLICY_STEP}/row) over the CUDA-event "

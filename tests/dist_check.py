@@ -1,0 +1,70 @@
+"""Data-parallel parity check, run under torchrun on N GPUs (NCCL):
+   torchrun --nproc-per-node N tests/dist_check.py
+Every rank builds the same global batch, trains on its contiguous block of episodes with distributed=True, and the
+result must match a single-GPU run on the whole batch (1e-5 of max|ref|): the sharded engine computes the same global
+mean / std / KL and applies the same reduced gradient on every rank."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from oracle import onpolicy as O  # noqa: E402
+from rl_replicas_b200 import synthetic  # noqa: E402
+from test_gpu_ppo import build, flat  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rng = np.random.default_rng(0)
+    ps, vs = [17, 64, 64, 6], [17, 64, 64, 1]
+    mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+                     for i, o in zip(sz[:-1], sz[1:])]
+    pl, vl = mk(ps), mk(vs)
+    log_std = np.full(6, -0.5, np.float32)
+    full = synthetic.ragged_batch(40000, 17, 6, False, seed=3, min_len=50, max_len=400,
+                                  mean_fn=lambda o: O.mlp_forward(pl, o)[0])
+    hp = dict(num_policy_gradients=6, num_value_gradients=6)
+    ok = True
+    for max_kl in (float("inf"), 0.002):  # second setting triggers the device-side early stop on every rank
+        dp = build(ps, vs, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std, distributed=True,
+                   max_kl_divergence=max_kl, **hp)
+        dp.train_packed(synthetic.shard_batch(full, rank, world))
+        p_dp, v_dp = flat(dp.policy.network).copy(), flat(dp.value_function.network).copy()
+        st = dp.last_update_stats
+        # all ranks must hold bit-identical parameters
+        t = torch.from_numpy(np.concatenate([p_dp, v_dp])).cuda()
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+        if rank == 0:
+            ref = build(ps, vs, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std,
+                        max_kl_divergence=max_kl, **hp)
+            ref.train_packed(full)
+            rs = ref.last_update_stats
+            ep = np.abs(p_dp - flat(ref.policy.network)).max() / np.abs(flat(ref.policy.network)).max()
+            ev = np.abs(v_dp - flat(ref.value_function.network)).max() / np.abs(flat(ref.value_function.network)).max()
+            good = (same and ep < 1e-5 and ev < 1e-5 and st.policy_steps_applied == rs.policy_steps_applied
+                    and abs(st.kl_divergence - rs.kl_divergence) < 1e-4 * abs(rs.kl_divergence) + 1e-8
+                    and abs(st.value_loss_mean - rs.value_loss_mean) < 1e-5 * rs.value_loss_mean
+                    and abs(st.adv_std - rs.adv_std) < 1e-9 * rs.adv_std)
+            print(f"max_kl={max_kl}: world={world} ranks_identical={same} policy_err={ep:.2e} value_err={ev:.2e} "
+                  f"steps {st.policy_steps_applied}/{rs.policy_steps_applied} kl {st.kl_divergence:.6g}/{rs.kl_divergence:.6g} "
+                  f"vloss {st.value_loss_mean:.6g}/{rs.value_loss_mean:.6g} -> {'OK' if good else 'FAIL'}")
+            ok = ok and good
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if ok else "FAIL")
+        sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
