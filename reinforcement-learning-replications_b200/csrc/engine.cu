@@ -156,9 +156,9 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
   const size_t N = (size_t)cfg->max_rows, E = (size_t)cfg->max_episodes;
   const size_t Pmax = (size_t)(Pp > Pv ? Pp : Pv);
   int rc = 0;
-  rc |= dev_alloc(h, &h->obs, N * h->obs_dim);
+  rc |= dev_alloc(h, &h->obs, N * h->obs_dim + 64);  // + slack: the tc kernel stages whole 16-byte chunks
   rc |= dev_alloc(h, &h->act, N * h->act_cols);
-  rc |= dev_alloc(h, &h->last_obs, E * h->obs_dim);
+  rc |= dev_alloc(h, &h->last_obs, E * h->obs_dim + 64);
   rc |= dev_alloc(h, reinterpret_cast<char**>(&h->rew), N * (cfg->rewards_f64 ? 8 : 4));
   rc |= dev_alloc(h, &h->off, E + 1);
   rc |= dev_alloc(h, &h->done, E);

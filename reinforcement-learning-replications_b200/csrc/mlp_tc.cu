@@ -51,7 +51,8 @@ constexpr uint32_t SM_OPERANDS_END = SM_W3 + 3 * W3_BUF;
 constexpr uint32_t SM_BIAS = SM_OPERANDS_END;       // b1[64] b2[64] b3[16] floats
 constexpr uint32_t SM_DIST = SM_BIAS + 1024;        // var[16], log_scale[16] floats
 constexpr uint32_t SM_DB3 = SM_DIST + 256;          // [4 warps][16] floats
-constexpr uint32_t SM_TOTAL = SM_DB3 + 512;
+constexpr uint32_t SM_STAGE = SM_DB3 + 512;         // fp32 staging of the NEXT tile's observations [128][n_in<=32]
+constexpr uint32_t SM_TOTAL = SM_STAGE + 128 * 32 * 4;
 constexpr uint32_t TC_SMEM_BYTES = SM_TOTAL + 1024;  // + alignment slack
 
 // tensor-memory column map
@@ -119,6 +120,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // the six split products, smallest terms first: (m,m) (h,l) (l,h) (h,m) (m,h) (h,h)
@@ -294,36 +310,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
 
     // tanh layer epilogue: Z (TMEM) + bias -> tanh -> fp32 copy back to TMEM (for tanh') + bf16 splits to smem
     auto act_epilogue = [&](uint32_t tm_col, const float* bias, uint32_t dst_buf) {
-      uint32_t v[32];
-      tmem_ld32(tmem + lane_addr + tm_col + c0, v);
-      tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(tanhf(__uint_as_float(v[j]) + bias[c0 + j]));
-      if (BACKWARD) tmem_st32(tmem + lane_addr + tm_col + c0, v);
+      for (int sub = 0; sub < 2; ++sub) {  // 16 columns at a time keeps the live register set small
+        const int cs = c0 + 16 * sub;
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_addr + tm_col + cs, v);
+        tmem_wait_ld();
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        float x[8];
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(tanhf(__uint_as_float(v[j]) + bias[cs + j]));
+        if (BACKWARD) tmem_st16(tmem + lane_addr + tm_col + cs, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * ch + j]);
-        store_chunk3(sm, dst_buf, ACT_BUF, r, (c0 >> 3) + ch, x);
+        for (int ch = 0; ch < 2; ++ch) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * ch + j]);
+          store_chunk3(sm, dst_buf, ACT_BUF, r, (cs >> 3) + ch, x);
+        }
       }
       if (BACKWARD) tmem_wait_st();
     };
     // backward epilogue: dZ = dH * (1 - H^2), bf16 splits over the activation buffer (in place)
     auto dz_epilogue = [&](uint32_t tm_dh, uint32_t tm_h, uint32_t dst_buf) {
-      uint32_t g[32], h[32];
-      tmem_ld32(tmem + lane_addr + tm_dh + c0, g);
-      tmem_ld32(tmem + lane_addr + tm_h + c0, h);
-      tmem_wait_ld();
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        float x[8];
+      for (int sub = 0; sub < 2; ++sub) {
+        const int cs = c0 + 16 * sub;
+        uint32_t g[16], h[16];
+        tmem_ld16(tmem + lane_addr + tm_dh + cs, g);
+        tmem_ld16(tmem + lane_addr + tm_h + cs, h);
+        tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float hv = __uint_as_float(h[8 * ch + j]);
-          x[j] = __uint_as_float(g[8 * ch + j]) * (1.f - hv * hv);
+        for (int ch = 0; ch < 2; ++ch) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float hv = __uint_as_float(h[8 * ch + j]);
+            x[j] = __uint_as_float(g[8 * ch + j]) * (1.f - hv * hv);
+          }
+          store_chunk3(sm, dst_buf, ACT_BUF, r, (cs >> 3) + ch, x);
         }
-        store_chunk3(sm, dst_buf, ACT_BUF, r, (c0 >> 3) + ch, x);
       }
     };
     auto stage_done = [&]() {  // publish smem writes to the tensor core, hand over to the issuer, wait for its MMAs
@@ -335,22 +359,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
       tc_fence_after_sync();
     };
 
+    float pf_act[15], pf_adv = 0.f, pf_old = 0.f, pf_tgt = 0.f;
+#pragma unroll
+    for (int a = 0; a < 15; ++a) pf_act[a] = 0.f;
+    const float* s_stage = reinterpret_cast<const float*>(sm + SM_STAGE);
+    // stage one tile's observations (contiguous rows_here*n_in floats, 16-byte aligned) with cp.async; warps 4..7
+    auto stage_obs = [&](long long t) {
+      if (half == 1 && t < num_tiles) {
+        const long long r0 = t * TC_ROWS;
+        const long long rows_here = (p.n_rows - r0) < TC_ROWS ? (p.n_rows - r0) : TC_ROWS;
+        const int n16 = (int)((rows_here * n_in * 4 + 15) / 16);  // the obs buffer is padded to 16 bytes by the engine
+        const char* g = reinterpret_cast<const char*>(p.obs + r0 * n_in);
+        for (int i = tid - 128; i < n16; i += 128) cp_async16(base + SM_STAGE + 16 * i, g + 16 * (size_t)i);
+      }
+      cp_async_commit_wait_all();
+    };
+    stage_obs(blockIdx.x);
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long row = tile * TC_ROWS + r;
       const bool valid = row < p.n_rows;
 
-      // ---- observations: one row per thread of warps 0..3 -> cols 0..31 of XD (three splits) ----
+      // ---- observations: staged as fp32 by cp.async (previous tile / prologue); one row per thread of warps 0..3
+      //      converts its row to the three bf16 splits in cols 0..31 of XD ----
       if (half == 0) {
-        const float* src = p.obs + row * n_in;
+        const float* src = s_stage + r * n_in;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = 8 * ch + j;
-            x[j] = (valid && c < n_in) ? __ldg(src + c) : 0.f;
+            x[j] = (valid && c < n_in) ? src[c] : 0.f;
           }
           store_chunk3(sm, SM_XD, ACT_BUF, r, ch, x);
+        }
+        // loss inputs of this row: issue the loads now, consume them three stages later
+        if (valid) {
+          if (p.dist == B200RL_DIST_GAUSSIAN) {
+#pragma unroll
+            for (int a = 0; a < 15; ++a)
+              if (a < A_out) pf_act[a] = __ldg(p.actions + row * A_out + a);
+          } else if (p.dist == B200RL_DIST_CATEGORICAL) {
+            pf_act[0] = __ldg(p.actions + row);
+          }
+          if (p.loss != B200RL_LOSS_EVAL && p.adv_raw != nullptr) pf_adv = __ldg(p.adv_raw + row);
+          if (p.old_logp != nullptr) pf_old = __ldg(p.old_logp + row);
+          if (p.loss == B200RL_LOSS_MSE) pf_tgt = __ldg(p.target + row);
         }
       }
       stage_done();                                   // F1
@@ -358,6 +414,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
       stage_done();                                   // F2
       act_epilogue(TM_Z2, s_bias + 64, SM_H2);
       stage_done();                                   // F3
+
+      // warps 4..7 have no loss work: they fetch the next tile's observations into the staging buffer meanwhile
+      stage_obs(tile + gridDim.x);
 
       // ---- distribution / loss epilogue (one thread per row: warps 0..3) ----
       if (half == 0) {
@@ -376,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
             const float vout = out[0];
             if (p.row_out) p.row_out[row] = vout;
             if (p.loss == B200RL_LOSS_MSE) {  // ppo.py:282-287
-              const float diff = vout - __ldg(p.target + row);
+              const float diff = vout - pf_tgt;
               term = diff * diff;
               dout[0] = (2.f * diff) * p.inv_n;
             }
@@ -387,12 +446,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
 #pragma unroll
             for (int a = 0; a < 16; ++a) dlp[a] = 0.f;
             if (p.dist == B200RL_DIST_GAUSSIAN) {
-              const float* act = p.actions + row * A_out;
 #pragma unroll
               for (int a = 0; a < 15; ++a)
                 if (a < A_out) {
                   const float var = s_dist[a], lsc = s_dist[16 + a];
-                  const float d = __ldg(act + a) - out[a];
+                  const float d = pf_act[a] - out[a];
                   lp += -(d * d) / (2.f * var) - lsc - TC_LOG_SQRT_2PI;  // torch Normal.log_prob
                   ent += TC_ENT_CONST + lsc;                             // torch Normal.entropy
                   dlp[a] = d / var;
@@ -407,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
               for (int a = 0; a < 15; ++a)
                 if (a < A_out) se += expf(out[a] - m);
               const float lse = m + logf(se);
-              const int ai = (int)__ldg(p.actions + row);  // value.long()
+              const int ai = (int)pf_act[0];  // value.long()
 #pragma unroll
               for (int a = 0; a < 15; ++a)
                 if (a < A_out) {
@@ -421,10 +479,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
             if (p.row_out) p.row_out[row] = lp;
             float adv = 0.f, oldlp = 0.f;
             if (p.loss != B200RL_LOSS_EVAL) {
-              adv = __ldg(p.adv_raw + row);
+              adv = pf_adv;
               if (p.adv_stats != nullptr) adv = (adv - adv_mean) / adv_std;  // utils.py:91
             }
-            if (p.old_logp != nullptr) oldlp = __ldg(p.old_logp + row);
+            if (p.old_logp != nullptr) oldlp = pf_old;
             if (p.loss == B200RL_LOSS_PPO_CLIP) {  // ppo.py:245-255
               const float ratio = expf(lp - oldlp);
               const float s1 = ratio * adv;
