@@ -255,12 +255,46 @@ def main():
     ms_val = stage_ms("value_grad_kernel", 10)
     scan_reps = 20
     engine.run_stage("values", hp)
-    ms_scan_pair = stage_ms("scan", scan_reps)  # scan kernel + 1-CTA finalize + memset node
+    ms_scan_pair = stage_ms("scan", scan_reps)
     tf_pol = FLOP_POLICY_STEP * n_local / (ms_pol * 1e-3) / 1e12
     tf_val = FLOP_VALUE_STEP * n_local / (ms_val * 1e-3) / 1e12
     scan_bytes = (8 + 4 + 4 + 4) * n_local  # f64 rewards + values in, adv + ret out
     gbs_scan = scan_bytes / (ms_scan_pair * 1e-3) / 1e9
 
+    # the same scan kernel on a shape whose traffic (1.3 GB) cannot live in the 126 MB L2: the HBM-bandwidth figure
+    def scan_large():
+        import ctypes as C
+        E2, T2 = 65536, 1000
+        n2 = E2 * T2
+        rew = torch.randn(n2, dtype=torch.float64, device="cuda")
+        val = torch.randn(n2, dtype=torch.float32, device="cuda")
+        lv = torch.randn(E2, dtype=torch.float32, device="cuda")
+        off = torch.arange(E2 + 1, dtype=torch.int64, device="cuda") * T2
+        done = (torch.rand(E2, device="cuda") < 0.9).to(torch.uint8)
+        adv, ret = torch.empty(n2, dtype=torch.float32, device="cuda"), torch.empty(n2, dtype=torch.float32, device="cuda")
+        st = torch.zeros(3, dtype=torch.float64, device="cuda")
+        wsb = lib.b200rl_gae_scan_workspace_bytes(n2)
+        ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        strm = int(torch.cuda.current_stream().cuda_stream)
+
+        def go():
+            _lib.check(lib.b200rl_gae_scan(p(rew), 1, p(val), p(lv), p(off), p(done), n2, E2, 0.99, 0.97, p(adv), p(ret),
+                                           p(st), p(ws), wsb, strm), "gae_scan")
+        for _ in range(3):
+            go()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(10):
+            go()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 10
+        return n2, ms, 20.0 * n2 / (ms * 1e-3) / 1e9
+
+    if rank == 0:
+        n_big, ms_big, gbs_big = scan_large()
     if rank == 0:
         total_transitions = n_local * world
         value = total_transitions / (ms_dev * 1e-3)
@@ -282,10 +316,14 @@ def main():
                          "ms_per_launch": ms_pol},
             "roofline_value_kernel": {"bound": "tensor", "achieved": tf_val, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                                       "frac": tf_val / pk["tf_sust"], "ms_per_launch": ms_val},
-            "roofline_scan": {"kernel": "gae_scan_kernel<double> (+finalize)", "bound": "hbm", "achieved": gbs_scan,
+            "roofline_scan": {"kernel": "gae_scan_kernel<double> (single launch: scan + statistics)", "bound": "hbm", "achieved": gbs_scan,
                               "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_scan / pk["hbm"], "traffic": None,
                               "bytes_per_transition": 20, "ms_per_launch": ms_scan_pair,
                               "note": "16.4 MB problem: launch-latency bound at this size (SURVEY 7.3-3)"},
+            "roofline_scan_large": {"kernel": "gae_scan_kernel<double>", "bound": "hbm", "achieved": gbs_big,
+                                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_big / pk["hbm"], "traffic": None,
+                                    "transitions": n_big, "bytes_per_transition": 20, "ms_per_launch": ms_big,
+                                    "note": "65536 episodes x 1000 steps: 1.31 GB of algorithmic traffic (> L2)"},
             "update_flops_per_transition": FLOP_PER_TRANSITION,
             "update_tflops_fp32_equiv": FLOP_PER_TRANSITION * total_transitions / (ms_dev * 1e-3) / 1e12,
             "clocks": clocks,

@@ -67,7 +67,8 @@ int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backwar
  *   ep_done     [n_ep]  1 = the episode ended (terminated or truncated) => no bootstrap (utils.py:81-82)
  *   adv_raw, ret [n]    outputs (float32 casts of the float64 recurrences, ppo.py:151,160)
  *   stats       [3]     float64: sum(adv_raw), sum(adv_raw^2), n   (for normalize_tensor, utils.py:90-92)
- *   workspace           b200rl_gae_scan_workspace_bytes(n) bytes of device memory
+ *   workspace           b200rl_gae_scan_workspace_bytes(n) bytes of device memory, ZEROED ONCE by the caller at
+ *                       allocation (cudaMemset); every launch leaves it ready for the next one (no per-call memset)
  * ------------------------------------------------------------------------------------------------------------ */
 size_t b200rl_gae_scan_workspace_bytes(int64_t n);
 int b200rl_gae_scan(const void* rewards, int rewards_f64, const float* values, const float* last_values,

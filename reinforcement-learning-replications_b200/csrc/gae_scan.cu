@@ -33,10 +33,15 @@ struct __align__(16) ScanTileState {
 };
 static_assert(sizeof(ScanTileState) == 64, "tile state is one 64-byte record");
 
+// Workspace header.  The workspace is zeroed ONCE (at allocation); after that every launch cleans up after itself:
+// tile status words carry the launch epoch (a stale word from an earlier launch reads as "not ready"), and the last
+// CTA to finish resets the ticket / done counters and bumps the epoch.  => one kernel launch per scan, no memset.
 struct ScanHeader {
   int ticket;
+  int done;
+  int epoch;
   int error;
-  int pad[14];
+  int pad[12];
 };
 
 struct Aff {
@@ -60,6 +65,7 @@ struct ScanArgs {
   ScanHeader* hdr;
   ScanTileState* tiles;
   double2* partial;
+  double* stats;
   int num_tiles;
 };
 
@@ -126,17 +132,52 @@ __device__ __forceinline__ Aff warp_suffix_exclusive(Aff& incl, int lane) {
   return ex;
 }
 
+// Warp-cooperative 32-ary search: max e in [0, n_ep) with off[e] <= target (requires off[0] <= target < off[n_ep]).
+// ~log32(n_ep) rounds of one coalesced probe per lane instead of log2(n_ep) dependent loads per thread.
+__device__ __forceinline__ long long warp_find_episode(const long long* __restrict__ off, long long n_ep,
+                                                       long long target, int lane) {
+  long long lo = 0, hi = n_ep;  // invariant: off[lo] <= target < off[hi]
+  while (hi - lo > 1) {
+    const long long step = (hi - lo + 31) / 32;
+    const long long idx = lo + (long long)lane * step;
+    const bool ok = (idx < hi) && (__ldg(off + idx) <= target);  // monotone in lane; lane 0 is always true
+    const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
+    lo = lo + (long long)(cnt - 1) * step;
+    hi = (lo + step < hi) ? lo + step : hi;
+  }
+  return lo;
+}
+
 template <typename RewT>
-__global__ void __launch_bounds__(SCAN_THREADS) gae_scan_kernel(const ScanArgs p) {
-  __shared__ int s_tile;
+__global__ void __launch_bounds__(SCAN_THREADS, 4) gae_scan_kernel(const ScanArgs p) {
+  __shared__ int s_tile, s_epoch, s_last;
+  __shared__ long long s_e0, s_e1;
   __shared__ Aff s_wret[SCAN_THREADS / 32], s_wadv[SCAN_THREADS / 32];
   __shared__ double s_carry[2];
   __shared__ double s_red[2][SCAN_THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = p.num_tiles - 1 - atomicAdd(&p.hdr->ticket, 1);
+  if (warp == 0) {
+    int t = 0;
+    if (lane == 0) {
+      s_epoch = *reinterpret_cast<volatile int*>(&p.hdr->epoch);  // constant for the whole launch
+      t = p.num_tiles - 1 - atomicAdd(&p.hdr->ticket, 1);
+      s_tile = t;
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    // episodes that overlap this tile: found once per CTA, cooperatively
+    const long long t0 = (long long)t * SCAN_TILE;
+    const long long t1 = (t0 + SCAN_TILE - 1 < p.n - 1) ? t0 + SCAN_TILE - 1 : p.n - 1;
+    const long long e0 = warp_find_episode(p.off, p.n_ep, t0, lane);
+    const long long e1 = warp_find_episode(p.off, p.n_ep, t1, lane);
+    if (lane == 0) {
+      s_e0 = e0;
+      s_e1 = e1;
+    }
+  }
   __syncthreads();
   const int tile = s_tile;
+  const int st_agg = s_epoch * 4 + 1, st_incl = s_epoch * 4 + 2;  // status words of THIS launch
   const long long n = p.n;
   const long long i0 = (long long)tile * SCAN_TILE + (long long)tid * SCAN_ITEMS;
   const bool full = (i0 + SCAN_ITEMS <= n);
@@ -159,7 +200,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) gae_scan_kernel(const ScanArgs p
   // ---- which episode does item i0 belong to?  e = max{e : off[e] <= i0} ----
   long long e = 0, next_off = 0;
   if (i0 < n) {
-    long long lo = 0, hi = p.n_ep;
+    long long lo = s_e0, hi = s_e1 + 1;  // only the episodes that overlap this tile
     while (hi - lo > 1) {
       const long long mid = (lo + hi) >> 1;
       if (__ldg(p.off + mid) <= i0) lo = mid; else hi = mid;
@@ -229,7 +270,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) gae_scan_kernel(const ScanArgs p
     }
     ScanTileState* me = p.tiles + tile;
     me->a_ret = agg_r.a; me->b_ret = agg_r.b; me->a_adv = agg_a.a; me->b_adv = agg_a.b;
-    st_release(&me->status, 1);
+    st_release(&me->status, st_agg);
 
     Aff acc_r{1.0, 0.0}, acc_a{1.0, 0.0};
     for (int j = tile + 1; j < p.num_tiles; ++j) {
@@ -237,15 +278,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) gae_scan_kernel(const ScanArgs p
       const ScanTileState* t = p.tiles + j;
       int st = 0;
       long long spins = 0;
-      while ((st = ld_acquire(&t->status)) == 0) {
+      while ((st = ld_acquire(&t->status)) != st_agg && st != st_incl) {
         if (++spins > (1ll << 22)) break;  // bounded: never hang the GPU; flag and bail out
         __nanosleep(32);
       }
-      if (st == 0) {
+      if (st != st_agg && st != st_incl) {
         p.hdr->error = 1;
         break;
       }
-      if (st == 2) {
+      if (st == st_incl) {
         acc_r = Aff{0.0, acc_r.b + acc_r.a * __ldcg(&t->y_ret)};
         acc_a = Aff{0.0, acc_a.b + acc_a.a * __ldcg(&t->y_adv)};
         break;
@@ -258,7 +299,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) gae_scan_kernel(const ScanArgs p
     s_carry[1] = acc_a.b;
     me->y_ret = agg_r.b + agg_r.a * acc_r.b;
     me->y_adv = agg_a.b + agg_a.a * acc_a.b;
-    st_release(&me->status, 2);
+    st_release(&me->status, st_incl);
   }
   __syncthreads();
 
@@ -317,34 +358,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) gae_scan_kernel(const ScanArgs p
       t2 += s_red[1][w];
     }
     p.partial[tile] = make_double2(t1, t2);
+    __threadfence();
+    s_last = (atomicAdd(&p.hdr->done, 1) == p.num_tiles - 1) ? 1 : 0;
   }
-}
-
-// one CTA: fixed-order sum of the per-tile statistics -> stats[0..2] = (sum, sum of squares, n)
-__global__ void __launch_bounds__(256) gae_scan_finalize_kernel(const double2* partial, int num_tiles, long long n,
-                                                                double* stats, const ScanHeader* hdr) {
-  __shared__ double s1[256], s2[256];
-  double a = 0.0, b = 0.0;
-  for (int i = threadIdx.x; i < num_tiles; i += 256) {
-    const double2 x = partial[i];
-    a += x.x;
-    b += x.y;
-  }
-  s1[threadIdx.x] = a;
-  s2[threadIdx.x] = b;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      s1[threadIdx.x] += s1[threadIdx.x + o];
-      s2[threadIdx.x] += s2[threadIdx.x + o];
+  if (!s_last) return;
+
+  // ---- last CTA: fixed-order sum of the per-tile statistics -> stats = (sum, sum of squares, n); reset the header ----
+  __threadfence();
+  __shared__ double f1[SCAN_THREADS], f2[SCAN_THREADS];
+  double fa = 0.0, fb = 0.0;
+  for (int i = tid; i < p.num_tiles; i += SCAN_THREADS) {
+    const double2 x = __ldcg(p.partial + i);
+    fa += x.x;
+    fb += x.y;
+  }
+  f1[tid] = fa;
+  f2[tid] = fb;
+  __syncthreads();
+  for (int o = SCAN_THREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) {
+      f1[tid] += f1[tid + o];
+      f2[tid] += f2[tid + o];
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const bool bad = hdr->error != 0;
-    stats[0] = bad ? __longlong_as_double(0x7ff8000000000000ll) : s1[0];
-    stats[1] = bad ? __longlong_as_double(0x7ff8000000000000ll) : s2[0];
-    stats[2] = (double)n;
+  if (tid == 0) {
+    const bool bad = p.hdr->error != 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    p.stats[0] = bad ? nan : f1[0];
+    p.stats[1] = bad ? nan : f2[0];
+    p.stats[2] = (double)n;
+    p.hdr->ticket = 0;
+    p.hdr->done = 0;
+    p.hdr->error = 0;
+    p.hdr->epoch = (s_epoch + 1) & 0x0fffffff;
   }
 }
 
@@ -395,14 +443,12 @@ extern "C" int b200rl_gae_scan(const void* rewards, int rewards_f64, const float
   a.tiles = reinterpret_cast<ScanTileState*>(static_cast<char*>(workspace) + sizeof(ScanHeader));
   a.partial = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.tiles) + (size_t)tiles * sizeof(ScanTileState));
   a.num_tiles = tiles;
-  B200RL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(ScanHeader) + (size_t)tiles * sizeof(ScanTileState), s));
+  a.stats = stats;
   if (rewards_f64)
     gae_scan_kernel<double><<<tiles, SCAN_THREADS, 0, s>>>(a);
   else
     gae_scan_kernel<float><<<tiles, SCAN_THREADS, 0, s>>>(a);
   B200RL_CUDA(cudaGetLastError());
-  gae_scan_finalize_kernel<<<1, 256, 0, s>>>(a.partial, tiles, n, stats, a.hdr);
-  B200RL_CUDA(cudaGetLastError());
-  count_launch(2);
+  count_launch(1);
   return 0;
 }

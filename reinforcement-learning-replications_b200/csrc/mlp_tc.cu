@@ -137,31 +137,53 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// the six split products, smallest terms first: (m,m) (h,l) (l,h) (h,m) (m,h) (h,h)
-template <class FA, class FB>
-__device__ __forceinline__ void issue6(uint32_t d_tmem, uint32_t idesc, int ksteps, bool accumulate_first, FA fa,
-                                       FB fb) {
+// One operand of a split product: 32-bit halves of the descriptor of split 0 / k-step 0, the low-word advance per
+// split (buffer stride >> 4) and per k-step (bytes >> 4).  All fields are warp-uniform.
+struct OpDesc {
+  uint32_t lo, hi, split_step, k_step;
+};
+__device__ __forceinline__ OpDesc op_kmajor(uint32_t addr, uint32_t split_bytes) {  // K along the 128-byte rows
+  const uint64_t d = make_smem_desc_sw128(addr, 16, 1024);
+  return OpDesc{(uint32_t)d, (uint32_t)(d >> 32), split_bytes >> 4, 32u >> 4};
+}
+__device__ __forceinline__ OpDesc op_mnmajor(uint32_t addr, uint32_t rows, uint32_t split_bytes) {  // K along rows
+  const uint64_t d = make_smem_desc_sw128(addr, rows * 128, 1024);
+  return OpDesc{(uint32_t)d, (uint32_t)(d >> 32), split_bytes >> 4, 2048u >> 4};
+}
+
+// the six split products, smallest terms first: (m,m) (h,l) (l,h) (h,m) (m,h) (h,h); k-loop kept rolled (code size)
+__device__ __forceinline__ void issue6(uint32_t d_tmem, uint32_t idesc, int ksteps, bool accumulate_first,
+                                       const OpDesc a, const OpDesc b) {
   constexpr int TI[6] = {1, 0, 2, 0, 1, 0};
   constexpr int TJ[6] = {1, 2, 0, 1, 0, 0};
   uint32_t acc = accumulate_first ? 1u : 0u;
 #pragma unroll
-  for (int t = 0; t < 6; ++t)
+  for (int t = 0; t < 6; ++t) {
+    uint32_t alo = a.lo + TI[t] * a.split_step, blo = b.lo + TJ[t] * b.split_step;
+#pragma unroll 1
     for (int k = 0; k < ksteps; ++k) {
-      umma_f16(d_tmem, fa(TI[t], k), fb(TJ[t], k), idesc, acc);
+      umma_f16_elect2(d_tmem, alo, a.hi, blo, b.hi, idesc, acc);
       acc = 1u;
+      alo += a.k_step;
+      blo += b.k_step;
     }
+  }
 }
-// A (three splits) times an operand that is exact in bf16 (the ones column): three products
-template <class FA, class FB>
-__device__ __forceinline__ void issue3(uint32_t d_tmem, uint32_t idesc, int ksteps, bool accumulate_first, FA fa,
-                                       FB fb) {
+// A (three splits) times an operand that is exact in bf16 (the ones column, split 0 only): three products
+__device__ __forceinline__ void issue3(uint32_t d_tmem, uint32_t idesc, int ksteps, bool accumulate_first,
+                                       const OpDesc a, const OpDesc b) {
   uint32_t acc = accumulate_first ? 1u : 0u;
 #pragma unroll
-  for (int s = 2; s >= 0; --s)
+  for (int sp = 2; sp >= 0; --sp) {
+    uint32_t alo = a.lo + sp * a.split_step, blo = b.lo;
+#pragma unroll 1
     for (int k = 0; k < ksteps; ++k) {
-      umma_f16(d_tmem, fa(s, k), fb(0, k), idesc, acc);
+      umma_f16_elect2(d_tmem, alo, a.hi, blo, b.hi, idesc, acc);
       acc = 1u;
+      alo += a.k_step;
+      blo += b.k_step;
     }
+  }
 }
 
 template <bool BACKWARD>
@@ -236,54 +258,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
     const uint32_t I_128_64_KK = make_idesc_bf16(128, 64, 0, 0), I_128_16_KK = make_idesc_bf16(128, 16, 0, 0);
     const uint32_t I_128_64_KM = make_idesc_bf16(128, 64, 0, 1), I_64_64_MM = make_idesc_bf16(64, 64, 1, 1);
     const uint32_t I_64_32_MM = make_idesc_bf16(64, 32, 1, 1), I_64_16_MM = make_idesc_bf16(64, 16, 1, 1);
-    auto dK = [&](uint32_t buf, int kstep) { return make_smem_desc_sw128(base + buf + kstep * 32, 16, 1024); };
-    auto dMN = [&](uint32_t buf, uint32_t rows, int kstep, uint32_t col_bytes) {
-      return make_smem_desc_sw128(base + buf + kstep * 2048 + col_bytes, rows * 128, 1024);
-    };
+    // warp-uniform copies (ptxas keeps them in uniform registers: no per-instruction R2UR)
+    const uint32_t ub = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t ut = __shfl_sync(0xffffffffu, tmem, 0);
+    const OpDesc XD_K = op_kmajor(ub + SM_XD, ACT_BUF), H1_K = op_kmajor(ub + SM_H1, ACT_BUF),
+                 H2_K = op_kmajor(ub + SM_H2, ACT_BUF), W1_K = op_kmajor(ub + SM_W1, W_BUF),
+                 W2_K = op_kmajor(ub + SM_W2, W_BUF), W3_K = op_kmajor(ub + SM_W3, W3_BUF);
+    const OpDesc XD_K2 = op_kmajor(ub + SM_XD + 64, ACT_BUF);  // cols 32..47 (dOut) as a K-major A operand
+    const OpDesc H1_M = op_mnmajor(ub + SM_H1, 128, ACT_BUF), H2_M = op_mnmajor(ub + SM_H2, 128, ACT_BUF),
+                 XD_M0 = op_mnmajor(ub + SM_XD, 128, ACT_BUF),        // X    (cols 0..31)
+                 XD_M32 = op_mnmajor(ub + SM_XD + 64, 128, ACT_BUF),  // dOut (cols 32..47, col 47 = ones)
+                 W2_M = op_mnmajor(ub + SM_W2, 64, W_BUF), W3_M = op_mnmajor(ub + SM_W3, 16, W3_BUF);
     bool first = true;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+#pragma unroll 1
       for (int s = 0; s < STAGES; ++s) {
         __syncthreads();  // operands of stage s are in shared memory (and the previous stage's MMAs have retired)
         tc_fence_after_sync();
-        if (lane == 0) {
-          if (s == 0) {  // Z1 = X W1^T
-            issue6(tmem + TM_Z1, I_128_64_KK, 2, false, [&](int a, int k) { return dK(SM_XD + a * ACT_BUF, k); },
-                   [&](int b, int k) { return dK(SM_W1 + b * W_BUF, k); });
-          } else if (s == 1) {  // Z2 = H1 W2^T
-            issue6(tmem + TM_Z2, I_128_64_KK, 4, false, [&](int a, int k) { return dK(SM_H1 + a * ACT_BUF, k); },
-                   [&](int b, int k) { return dK(SM_W2 + b * W_BUF, k); });
-          } else if (s == 2) {  // OUT = H2 W3^T
-            issue6(tmem + TM_OUT, I_128_16_KK, 4, false, [&](int a, int k) { return dK(SM_H2 + a * ACT_BUF, k); },
-                   [&](int b, int k) { return dK(SM_W3 + b * W3_BUF, k); });
-          } else if (s == 3) {
-            // dW3^T[i][o] += sum_r H2[r][i] dOut[r][o]   (both read MN-major: the reduction runs over rows)
-            issue6(tmem + TM_DW3, I_64_16_MM, 8, !first,
-                   [&](int a, int k) { return dMN(SM_H2 + a * ACT_BUF, 128, k, 0); },
-                   [&](int b, int k) { return dMN(SM_XD + b * ACT_BUF, 128, k, 64); });
-            // dH2 = dOut W3   (A: XD cols 32..47 = k-step 2; B: W3 read MN-major, K = output index)
-            issue6(tmem + TM_DH2, I_128_64_KM, 1, false, [&](int a, int) { return dK(SM_XD + a * ACT_BUF, 2); },
-                   [&](int b, int) { return dMN(SM_W3 + b * W3_BUF, 16, 0, 0); });
-          } else if (s == 4) {
-            // dW2[o][i] += sum_r dZ2[r][o] H1[r][i] ; db2[o] += sum_r dZ2[r][o] * 1 ; dH1 = dZ2 W2
-            issue6(tmem + TM_DW2, I_64_64_MM, 8, !first,
-                   [&](int a, int k) { return dMN(SM_H2 + a * ACT_BUF, 128, k, 0); },
-                   [&](int b, int k) { return dMN(SM_H1 + b * ACT_BUF, 128, k, 0); });
-            issue3(tmem + TM_DB2, I_64_16_MM, 8, !first,
-                   [&](int a, int k) { return dMN(SM_H2 + a * ACT_BUF, 128, k, 0); },
-                   [&](int, int k) { return dMN(SM_XD, 128, k, 64); });
-            issue6(tmem + TM_DH1, I_128_64_KM, 4, false, [&](int a, int k) { return dK(SM_H2 + a * ACT_BUF, k); },
-                   [&](int b, int k) { return dMN(SM_W2 + b * W_BUF, 64, k, 0); });
-          } else {
-            // dW1[o][i] += sum_r dZ1[r][o] X[r][i] ; db1[o] += sum_r dZ1[r][o]
-            issue6(tmem + TM_DW1, I_64_32_MM, 8, !first,
-                   [&](int a, int k) { return dMN(SM_H1 + a * ACT_BUF, 128, k, 0); },
-                   [&](int b, int k) { return dMN(SM_XD + b * ACT_BUF, 128, k, 0); });
-            issue3(tmem + TM_DB1, I_64_16_MM, 8, !first,
-                   [&](int a, int k) { return dMN(SM_H1 + a * ACT_BUF, 128, k, 0); },
-                   [&](int, int k) { return dMN(SM_XD, 128, k, 64); });
-          }
-          umma_commit(bar);
+        if (s == 0) {  // Z1 = X W1^T
+          issue6(ut + TM_Z1, I_128_64_KK, 2, false, XD_K, W1_K);
+        } else if (s == 1) {  // Z2 = H1 W2^T
+          issue6(ut + TM_Z2, I_128_64_KK, 4, false, H1_K, W2_K);
+        } else if (s == 2) {  // OUT = H2 W3^T
+          issue6(ut + TM_OUT, I_128_16_KK, 4, false, H2_K, W3_K);
+        } else if (s == 3) {
+          // dW3^T[i][o] += sum_r H2[r][i] dOut[r][o]   (both read MN-major: the reduction runs over rows)
+          issue6(ut + TM_DW3, I_64_16_MM, 8, !first, H2_M, XD_M32);
+          // dH2 = dOut W3   (A: XD cols 32..47; B: W3 read MN-major, K = output index)
+          issue6(ut + TM_DH2, I_128_64_KM, 1, false, XD_K2, W3_M);
+        } else if (s == 4) {
+          // dW2[o][i] += sum_r dZ2[r][o] H1[r][i] ; db2[o] += sum_r dZ2[r][o] * 1 ; dH1 = dZ2 W2
+          issue6(ut + TM_DW2, I_64_64_MM, 8, !first, H2_M, H1_M);
+          issue3(ut + TM_DB2, I_64_16_MM, 8, !first, H2_M, XD_M32);
+          issue6(ut + TM_DH1, I_128_64_KM, 4, false, H2_K, W2_M);
+        } else {
+          // dW1[o][i] += sum_r dZ1[r][o] X[r][i] ; db1[o] += sum_r dZ1[r][o]
+          issue6(ut + TM_DW1, I_64_32_MM, 8, !first, H1_M, XD_M0);
+          issue3(ut + TM_DB1, I_64_16_MM, 8, !first, H1_M, XD_M32);
         }
+        umma_commit_elect(bar);
         __syncwarp();
       }
       first = false;

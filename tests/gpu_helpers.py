@@ -31,7 +31,7 @@ def gae_scan(rew, values, last_values, ep_offsets, ep_done, gamma=0.99, lam=0.97
     ret = torch.empty(max(n, 1), dtype=torch.float32, device="cuda")
     stats = torch.zeros(3, dtype=torch.float64, device="cuda")
     wsb = lib.b200rl_gae_scan_workspace_bytes(n)
-    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")  # zeroed once at allocation (ABI contract)
     check(lib.b200rl_gae_scan(p(d_rew), int(f64), p(d_v), p(d_lv), p(d_off), p(d_done), n, e, gamma, lam, p(adv), p(ret),
                               p(stats), p(ws), wsb, stream()), "gae_scan")
     torch.cuda.synchronize()
