@@ -36,8 +36,14 @@ enum b200rl_loss {
   B200RL_LOSS_PPO_CLIP = 1,       /* -mean(min(r A, clamp(r,1-c,1+c) A))        ref: algorithms/ppo.py:237-257 */
   B200RL_LOSS_VPG = 2,            /* -mean(logp A)                               ref: algorithms/vpg.py:194-207 */
   B200RL_LOSS_TRPO_SURROGATE = 3, /* -mean(r A)                                  ref: algorithms/trpo.py:154-165 */
-  B200RL_LOSS_MSE = 4             /* mean((out - target)^2)                      ref: algorithms/ppo.py:282-287 */
+  B200RL_LOSS_MSE = 4,            /* mean((out - target)^2)                      ref: algorithms/ppo.py:282-287 */
+  B200RL_LOSS_FVP = 5             /* Fisher-vector product J^T M J v / N of mean KL(old || new) at theta_old:
+                                     forward pass with tangents (J v), metric M of the distribution, then the ordinary
+                                     backward pass (J^T); replaces the double backprop of
+                                     optimizers/conjugate_gradient_optimizer.py:133-167 (trpo.py:167-175) */
 };
+#define B200RL_FLAG_FORWARD_ONLY 1 /* evaluate the loss terms of `loss` but run no backward pass (line search) */
+#define B200RL_FLAG_NO_TC 2        /* force the fp32 CUDA-core kernel */
 
 /* MLP description (ref: networks/mlp.py:15-31). */
 typedef struct {
@@ -53,7 +59,9 @@ int b200rl_version(void);
 int64_t b200rl_launch_count(void);
 /* number of float32 parameters of the MLP (sum of out*in + out); -1 if the description is invalid */
 int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp);
-/* CTAs the fused MLP kernels use for n_rows rows on the current device (= rows of `partials`); -1 on error */
+/* CTAs the fused MLP kernels use for n_rows rows on the current device (= rows of `partials`); -1 on error.
+ * with_backward: 0 forward only, 1 forward + backward, 2 Fisher-vector product, 3 forward only on the fp32 kernel
+ * (launches that set out_full / old_out / B200RL_FLAG_NO_TC). */
 int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -103,8 +111,13 @@ typedef struct {
   float* partials;         /* [grid, P] per-CTA partial gradients (losses other than EVAL) */
   double* scalar_partials; /* [grid, B200RL_N_SCALARS] per-CTA partial sums:
                               0 sum(loss terms)  1 sum(old_logp - logp)  2 sum(entropy)  3 sum(logp)  4 sum(logp^2)
-                              5 rows processed   6,7 reserved */
+                              5 rows processed   6 sum(KL(old || new)) when old_out is given   7 reserved */
   const int32_t* skip_flag; /* optional device flag: non-zero => the launch is a no-op (early stop) */
+  float* out_full;         /* optional [n_rows, sizes[L]]: raw network outputs (means / logits) are written here */
+  const float* old_out;    /* optional [n_rows, sizes[L]]: outputs of the old policy -> true KL(old || new) per row,
+                              kl_divergence(old_dist, dist) of trpo.py:167-175 (Gaussian: same log_std for both) */
+  const float* direction;  /* [P] the vector v of B200RL_LOSS_FVP, same flat layout as params */
+  int32_t flags;           /* B200RL_FLAG_* */
 } b200rl_mlp_loss_grad_args;
 
 int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* args, void* stream);
@@ -198,6 +211,35 @@ int b200rl_ppo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_a
 /* The reference's VPG.train (algorithms/vpg.py:127-192): one policy step on -mean(logp A), then value steps. */
 int b200rl_vpg_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn allreduce, void* user,
                       b200rl_update_stats* stats, void* stream);
+
+/* The reference's TRPO.train (algorithms/trpo.py:130-226): surrogate gradient, ConjugateGradientOptimizer.step
+ * (optimizers/conjugate_gradient_optimizer.py:59-98: n_cg Fisher-vector products + CG, step size, backtracking line
+ * search, reject/restore), old-policy sync, value steps.  Single GPU (an all-reduce per FVP is not implemented). */
+typedef struct {
+  double max_constraint;          /* delta, default 0.01 */
+  int32_t n_conjugate_gradients;  /* default 10 */
+  int32_t max_backtracks;         /* default 15 */
+  double backtrack_ratio;         /* default 0.8 */
+  double hvp_damping_coefficient; /* default 1e-5 */
+} b200rl_trpo_hparams;
+
+typedef struct {
+  double step_size;           /* sqrt(2 delta / (x^T H x + 1e-8)) */
+  double xhx;
+  double loss_before;         /* surrogate at theta_old */
+  double new_loss, kl;        /* at the accepted (or last tried) parameters */
+  int32_t accepted_index;     /* index k of the accepted ratio backtrack_ratio^k; -1 = none accepted */
+  int32_t rejected;           /* 1 = line-search condition violated, parameters restored */
+  int32_t cg_converged;       /* 1 = residual fell below 1e-10 before n_cg iterations */
+  int32_t fvp_launches;
+} b200rl_trpo_stats;
+
+int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, const b200rl_trpo_hparams* cg,
+                       b200rl_update_stats* stats, b200rl_trpo_stats* trpo_stats, void* stream);
+/* One Fisher-vector product on the loaded batch at the current policy parameters: out = F v + damping * v (host
+ * vectors of policy-parameter length); for tests against the reference's double-backprop Hessian-vector product. */
+int b200rl_onpolicy_fvp(b200rl_onpolicy* h, const float* host_v, float* host_out, int64_t n, double damping,
+                        void* stream);
 
 /* Device views for tests / profiling (pointers stay owned by the engine):
  * name: "values","last_values","adv_raw","ret","old_logp","adv_stats","policy_grad","value_grad",

@@ -369,3 +369,99 @@ def ppo_train(batch: Dict[str, np.ndarray], policy: Layers, value: Layers, dist_
     out.update(value_flat=flat_v, value_losses=np.asarray(vlosses),
                value_loss_mean=float(np.mean(vlosses)) if vlosses else float("nan"))
     return out
+
+
+# --------------------------------------------------------------------------
+# TRPO (ref: algorithms/trpo.py:130-240, optimizers/conjugate_gradient_optimizer.py:59-250)
+# --------------------------------------------------------------------------
+def dist_kl(kind: str, out_old, out_new, log_std) -> np.ndarray:
+    """kl_divergence(old_dist, dist) per row (ref: trpo.py:167-175)."""
+    if kind == "gaussian":
+        return gaussian_kl(out_old, log_std, out_new, log_std)
+    return categorical_kl(out_old, out_new)
+
+
+def fisher_vector_product(layers: Layers, dist_kind: str, log_std, obs, v_flat, damping: float = 1e-5,
+                          hidden_act: str = "tanh") -> np.ndarray:
+    """(F + damping I) v with F = (1/N) J^T M J, the Hessian of mean KL(old || new) at theta = theta_old.
+    The reference obtains the same product by double backprop (conjugate_gradient_optimizer.py:133-167); at
+    theta_old the two are identical.  J v by forward-mode tangents, J^T by mlp_backward."""
+    sizes = layer_sizes(layers)
+    vl = unflatten_layers(np.asarray(v_flat, dtype=F32), sizes)
+    out, acts = mlp_forward(layers, obs, hidden_act, "identity")
+    n = obs.shape[0]
+    t = np.zeros((n, sizes[0]), dtype=F32)
+    L = len(layers)
+    for l, ((w, _), (vw, vb)) in enumerate(zip(layers, vl)):
+        zt = t @ w.T + acts[l] @ vw.T + vb
+        kind = "identity" if l == L - 1 else hidden_act
+        t = (zt * _act_prime_from_output(acts[l + 1], kind)).astype(F32)
+    if dist_kind == "gaussian":
+        scale = np.exp(log_std.astype(F32))
+        u = t / (scale * scale)
+    else:
+        p = np.exp(log_softmax(out))
+        u = p * (t - (p * t).sum(axis=-1, keepdims=True))
+    grads = mlp_backward(layers, acts, (u / F32(n)).astype(F32), hidden_act, "identity")
+    return (flatten_layers(grads) + F32(damping) * np.asarray(v_flat, dtype=F32)).astype(F32)
+
+
+def conjugate_gradient(hvp, b: np.ndarray, n_iters: int = 10, residual_tol: float = 1e-10) -> np.ndarray:
+    """ref: conjugate_gradient_optimizer.py:169-202 (float32 vectors)."""
+    x = np.zeros_like(b)
+    r, p = b.copy(), b.copy()
+    rdotr = F32(r @ r)
+    for _ in range(n_iters):
+        z = hvp(p)
+        v = F32(rdotr / F32(p @ z))
+        x = (x + v * p).astype(F32)
+        r = (r - v * z).astype(F32)
+        newrdotr = F32(r @ r)
+        mu = F32(newrdotr / rdotr)
+        p = (r + mu * p).astype(F32)
+        rdotr = newrdotr
+        if rdotr < residual_tol:
+            break
+    return x
+
+
+def trpo_policy_step(layers: Layers, dist_kind: str, log_std, obs, act, adv, max_constraint=0.01, n_cg=10,
+                     max_backtracks=15, backtrack_ratio=0.8, damping=1e-5, hidden_act: str = "tanh"):
+    """ConjugateGradientOptimizer.step restated (ref: conjugate_gradient_optimizer.py:59-98, 204-250)."""
+    sizes = layer_sizes(layers)
+    out_old = mlp_forward(layers, obs, hidden_act)[0]
+    old_logp = Dist(dist_kind, out_old, log_std).log_prob(act)
+    g = policy_loss_and_grad(layers, dist_kind, log_std, obs, act, adv, old_logp, "trpo", hidden_act=hidden_act)
+    hvp = lambda v: fisher_vector_product(layers, dist_kind, log_std, obs, v, damping, hidden_act)
+    x = conjugate_gradient(hvp, g["grad"], n_cg)
+    x[np.isnan(x)] = 0
+    xhx = F32(x @ hvp(x))
+    step_size = F32(np.sqrt(F32(2.0 * max_constraint) * (F32(1.0) / (xhx + F32(1e-8)))))
+    if np.isnan(step_size):
+        step_size = F32(1.0)
+    descent = (step_size * x).astype(F32)
+    prev = flatten_layers(layers)
+    loss_before = F32(g["loss"])
+
+    def evaluate(flat):
+        lay = unflatten_layers(flat, sizes)
+        o = mlp_forward(lay, obs, hidden_act)[0]
+        lp = Dist(dist_kind, o, log_std).log_prob(act)
+        loss = F32(-np.mean((np.exp(lp - old_logp) * adv).astype(np.float64)))
+        kl = F32(np.mean(dist_kl(dist_kind, out_old, o, log_std).astype(np.float64)))
+        return loss, kl
+
+    accepted, new_loss, kl, flat = -1, None, None, prev
+    for k in range(max_backtracks):
+        flat = (prev - F32(backtrack_ratio ** k) * descent).astype(F32)
+        new_loss, kl = evaluate(flat)
+        if new_loss < loss_before and kl <= max_constraint:
+            accepted = k
+            break
+    rejected = bool(np.isnan(new_loss) or np.isnan(kl) or new_loss >= loss_before or kl >= max_constraint)
+    if rejected:
+        flat = prev
+    return dict(grad=g["grad"], x=x, step_size=float(step_size), xhx=float(xhx), descent=descent, policy_flat=flat,
+                accepted=accepted, rejected=rejected, loss_before=float(loss_before), new_loss=float(new_loss),
+                kl=float(kl), entropy=float(np.mean(g["entropy"], dtype=np.float64)),
+                logp_std=float(np.std(g["logp"].astype(np.float64), ddof=1)))

@@ -14,7 +14,8 @@ MAX_LAYERS = 4
 N_SCALARS = 8
 ACT = {"identity": 0, "tanh": 1, "relu": 2}
 DIST = {"none": 0, "gaussian": 1, "categorical": 2}
-LOSS = {"eval": 0, "ppo_clip": 1, "vpg": 2, "trpo_surrogate": 3, "mse": 4}
+LOSS = {"eval": 0, "ppo_clip": 1, "vpg": 2, "trpo_surrogate": 3, "mse": 4, "fvp": 5}
+FLAG_FORWARD_ONLY, FLAG_NO_TC = 1, 2
 
 
 class MlpDesc(C.Structure):
@@ -38,7 +39,8 @@ class LossGradArgs(C.Structure):
                 ("n_global", C.c_int64), ("clip_range", C.c_float), ("params", C.c_void_p), ("obs", C.c_void_p),
                 ("actions", C.c_void_p), ("log_std", C.c_void_p), ("adv_raw", C.c_void_p), ("adv_stats", C.c_void_p),
                 ("old_logp", C.c_void_p), ("target", C.c_void_p), ("row_out", C.c_void_p), ("partials", C.c_void_p),
-                ("scalar_partials", C.c_void_p), ("skip_flag", C.c_void_p)]
+                ("scalar_partials", C.c_void_p), ("skip_flag", C.c_void_p), ("out_full", C.c_void_p),
+                ("old_out", C.c_void_p), ("direction", C.c_void_p), ("flags", C.c_int32)]
 
 
 class OnPolicyConfig(C.Structure):
@@ -61,6 +63,17 @@ class UpdateStats(C.Structure):
                 ("value_steps_applied", C.c_int32), ("kernel_launches", C.c_int32), ("reserved", C.c_int32),
                 ("adv_mean", C.c_double), ("adv_std", C.c_double), ("value_loss_first", C.c_double),
                 ("value_loss_last", C.c_double)]
+
+
+class TrpoHparams(C.Structure):
+    _fields_ = [("max_constraint", C.c_double), ("n_conjugate_gradients", C.c_int32), ("max_backtracks", C.c_int32),
+                ("backtrack_ratio", C.c_double), ("hvp_damping_coefficient", C.c_double)]
+
+
+class TrpoStats(C.Structure):
+    _fields_ = [("step_size", C.c_double), ("xhx", C.c_double), ("loss_before", C.c_double), ("new_loss", C.c_double),
+                ("kl", C.c_double), ("accepted_index", C.c_int32), ("rejected", C.c_int32), ("cg_converged", C.c_int32),
+                ("fvp_launches", C.c_int32)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
@@ -96,6 +109,9 @@ SIGNATURES = {
                                     C.POINTER(UpdateStats), C.c_void_p]),
     "b200rl_vpg_update": (C.c_int, [C.c_void_p, C.POINTER(PpoHparams), C.c_void_p, C.c_void_p,
                                     C.POINTER(UpdateStats), C.c_void_p]),
+    "b200rl_trpo_update": (C.c_int, [C.c_void_p, C.POINTER(PpoHparams), C.POINTER(TrpoHparams), C.POINTER(UpdateStats),
+                                     C.POINTER(TrpoStats), C.c_void_p]),
+    "b200rl_onpolicy_fvp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     "b200rl_onpolicy_device_view": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                               C.POINTER(C.c_int32)]),
     "b200rl_tc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -39,6 +39,19 @@ int device_sm_count();
 void count_launch(int n = 1);
 int64_t launches_total();
 
+// TRPO vector kernels (trpo.cu)
+int trpo_cg_init(const float* g, float* x, float* r, float* pv, int n, double* sc, int* flags, cudaStream_t s);
+int trpo_cg_update(const float* z_raw, float damping, float* x, float* r, float* pv, int n, double* sc, int* flags,
+                   cudaStream_t s);
+int trpo_nan_to_zero(float* x, int n, cudaStream_t s);
+int trpo_step_size(const float* x, const float* hx_raw, float damping, float delta, float* descent, const float* params,
+                   float* prev, int n, double* sc, cudaStream_t s);
+int trpo_ls_set_params(float* params, const float* prev, const float* descent, float ratio, int n, const int* flags,
+                       cudaStream_t s);
+int trpo_ls_check(const double* slot, double n_rows, float delta, double* sc, int* flags, int index, cudaStream_t s);
+int trpo_ls_final(float* params, const float* prev, int n, float delta, const double* sc, int* flags, cudaStream_t s);
+int trpo_set_scalar(double* dst, const double* slot, int k, double inv, cudaStream_t s);
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

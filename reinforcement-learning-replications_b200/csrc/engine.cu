@@ -68,6 +68,14 @@ struct b200rl_onpolicy {
   double* h_slots = nullptr;  // pinned
   int* h_flags = nullptr;     // pinned
   double* h_stats3 = nullptr; // pinned
+  // TRPO (allocated on first use)
+  int out_cols = 0;
+  float* old_out = nullptr;  // [max_rows, out_cols] outputs of the old policy
+  float *cg_x = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_z = nullptr, *cg_prev = nullptr, *cg_descent = nullptr;
+  double* cg_sc = nullptr;   // 8 doubles, see trpo.cu
+  int* cg_flags = nullptr;   // 4 ints
+  double* h_cg_sc = nullptr; // pinned
+  int* h_cg_flags = nullptr; // pinned
   std::vector<void*> allocs;
 };
 
@@ -199,6 +207,8 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
 extern "C" void b200rl_onpolicy_destroy(b200rl_onpolicy* h) {
   if (!h) return;
   for (void* p : h->allocs) cudaFree(p);
+  if (h->h_cg_sc) cudaFreeHost(h->h_cg_sc);
+  if (h->h_cg_flags) cudaFreeHost(h->h_cg_flags);
   if (h->h_slots) cudaFreeHost(h->h_slots);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   if (h->h_stats3) cudaFreeHost(h->h_stats3);
@@ -448,6 +458,193 @@ extern "C" int b200rl_vpg_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* h
   return run_update(h, hp, allreduce, user, stats, stream, B200RL_LOSS_VPG);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TRPO
+// ------------------------------------------------------------------------------------------------------------------
+static int ensure_trpo(b200rl_onpolicy* h) {
+  if (h->cg_x) return 0;
+  h->out_cols = h->cfg.policy.sizes[h->cfg.policy.n_layers];
+  int rc = 0;
+  rc |= dev_alloc(h, &h->old_out, (size_t)h->cfg.max_rows * h->out_cols);
+  rc |= dev_alloc(h, &h->cg_x, (size_t)h->Pp);
+  rc |= dev_alloc(h, &h->cg_r, (size_t)h->Pp);
+  rc |= dev_alloc(h, &h->cg_p, (size_t)h->Pp);
+  rc |= dev_alloc(h, &h->cg_z, (size_t)h->Pp + B200RL_N_SCALARS);
+  rc |= dev_alloc(h, &h->cg_prev, (size_t)h->Pp);
+  rc |= dev_alloc(h, &h->cg_descent, (size_t)h->Pp);
+  rc |= dev_alloc(h, &h->cg_sc, 8);
+  rc |= dev_alloc(h, &h->cg_flags, 4);
+  if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_cg_sc), 8 * sizeof(double)) != cudaSuccess) rc = 1;
+  if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_cg_flags), 4 * sizeof(int)) != cudaSuccess) rc = 1;
+  if (rc && g_error.empty()) set_error("trpo: allocation failed");
+  return rc;
+}
+
+// out[P] = F v (without damping): one B200RL_LOSS_FVP launch + fixed-order reduction of the partials
+static int launch_fvp(b200rl_onpolicy* h, const float* direction, float* out, int64_t n_glob, cudaStream_t s) {
+  b200rl_mlp_loss_grad_args a;
+  memset(&a, 0, sizeof(a));
+  a.mlp = h->cfg.policy;
+  a.loss = B200RL_LOSS_FVP;
+  a.dist = h->cfg.dist;
+  a.n_rows = h->n_rows;
+  a.n_global = n_glob;
+  a.params = h->pol;
+  a.obs = h->obs;
+  a.log_std = h->log_std;
+  a.direction = direction;
+  a.partials = h->partials;
+  if (b200rl_mlp_loss_grad(&a, s)) return 1;
+  return b200rl_reduce_partials(h->partials, nullptr, b200rl_mlp_grid(&h->cfg.policy, h->n_rows, 2), h->Pp, out,
+                                nullptr, 0, nullptr, s);
+}
+
+extern "C" int b200rl_onpolicy_fvp(b200rl_onpolicy* h, const float* host_v, float* host_out, int64_t n, double damping,
+                                   void* stream) {
+  B200RL_REQUIRE(h && host_v && host_out && n == h->Pp, "fvp: bad arguments");
+  B200RL_REQUIRE(h->n_rows > 0, "fvp: no batch loaded");
+  if (ensure_trpo(h)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200RL_CUDA(cudaMemcpyAsync(h->cg_p, host_v, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  if (launch_fvp(h, h->cg_p, h->cg_z, h->n_rows, s)) return 1;
+  B200RL_CUDA(cudaMemcpyAsync(host_out, h->cg_z, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  for (int64_t i = 0; i < n; ++i) host_out[i] += (float)damping * host_v[i];  // H -> H + damping I (cg optimizer :165)
+  return 0;
+}
+
+extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, const b200rl_trpo_hparams* cg,
+                                  b200rl_update_stats* stats, b200rl_trpo_stats* ts, void* stream) {
+  B200RL_REQUIRE(h && hp && cg && stats && ts, "trpo_update: NULL argument");
+  B200RL_REQUIRE(h->n_rows > 0, "trpo_update: no batch loaded");
+  B200RL_REQUIRE(cg->n_conjugate_gradients >= 1 && cg->max_backtracks >= 1, "trpo_update: bad CG parameters");
+  if (ensure_trpo(h)) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t launches0 = launches_total();
+  const int64_t n = h->n_rows;
+  const int Kv = hp->num_value_gradients, nb = cg->max_backtracks;
+  const int n_slots = 1 + nb + Kv + 2;
+  if (ensure_slots(h, n_slots)) return 1;
+  B200RL_CUDA(cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), s));
+  B200RL_CUDA(cudaMemsetAsync(h->slots, 0, (size_t)n_slots * B200RL_N_SCALARS * sizeof(double), s));
+  B200RL_CUDA(cudaMemsetAsync(h->cg_sc, 0, 8 * sizeof(double), s));
+  if (run_preamble(h, hp, nullptr, nullptr, s)) return 1;
+  const int dist = h->cfg.dist;
+  const int P = (int)h->Pp;
+  const float delta = (float)cg->max_constraint, damping = (float)cg->hvp_damping_coefficient;
+
+  b200rl_mlp_loss_grad_args a;
+  // (1) old policy: log-probs and raw outputs (trpo.py:158-159, 171); frozen for the whole step
+  memset(&a, 0, sizeof(a));
+  a.mlp = h->cfg.policy;
+  a.loss = B200RL_LOSS_EVAL;
+  a.dist = dist;
+  a.n_rows = n;
+  a.n_global = n;
+  a.params = h->old_pol;
+  a.obs = h->obs;
+  a.actions = h->act;
+  a.log_std = h->log_std;
+  a.row_out = h->old_logp;
+  a.out_full = h->old_out;
+  if (b200rl_mlp_loss_grad(&a, s)) return 1;
+  // (2) surrogate loss and its gradient at theta (trpo.py:228-239); slot 0 also carries the logged statistics
+  if (launch_fused(h, h->cfg.policy, B200RL_LOSS_TRPO_SURROGATE, dist, h->pol, h->obs, n, n, 0.0, true, true, nullptr,
+                   true, nullptr, s)) return 1;
+  if (b200rl_reduce_partials(h->partials, h->scalar_partials, b200rl_mlp_grid(&h->cfg.policy, n, 1), h->Pp, h->pol_grad,
+                             h->slots, 0, nullptr, s)) return 1;
+  if (trpo_set_scalar(h->cg_sc + 1, h->slots, 0, 1.0 / (double)n, s)) return 1;  // loss_before
+  // (3) conjugate gradient: x ~ H^-1 g
+  if (trpo_cg_init(h->pol_grad, h->cg_x, h->cg_r, h->cg_p, P, h->cg_sc, h->cg_flags, s)) return 1;
+  int fvps = 0;
+  for (int it = 0; it < cg->n_conjugate_gradients; ++it) {
+    if (launch_fvp(h, h->cg_p, h->cg_z, n, s)) return 1;
+    ++fvps;
+    if (trpo_cg_update(h->cg_z, damping, h->cg_x, h->cg_r, h->cg_p, P, h->cg_sc, h->cg_flags, s)) return 1;
+  }
+  // (4) step size and descent step
+  if (trpo_nan_to_zero(h->cg_x, P, s)) return 1;
+  if (launch_fvp(h, h->cg_x, h->cg_z, n, s)) return 1;
+  ++fvps;
+  if (trpo_step_size(h->cg_x, h->cg_z, damping, delta, h->cg_descent, h->pol, h->cg_prev, P, h->cg_sc, s)) return 1;
+  // (5) backtracking line search (device-side accept flag: later iterations become no-ops)
+  const int grid_f = b200rl_mlp_grid(&h->cfg.policy, n, 3);
+  for (int k = 0; k < nb; ++k) {
+    const float ratio = (float)pow(cg->backtrack_ratio, (double)k);
+    double* slot = h->slots + (size_t)(1 + k) * B200RL_N_SCALARS;
+    if (trpo_ls_set_params(h->pol, h->cg_prev, h->cg_descent, ratio, P, h->cg_flags, s)) return 1;
+    memset(&a, 0, sizeof(a));
+    a.mlp = h->cfg.policy;
+    a.loss = B200RL_LOSS_TRPO_SURROGATE;
+    a.flags = B200RL_FLAG_FORWARD_ONLY | B200RL_FLAG_NO_TC;
+    a.dist = dist;
+    a.n_rows = n;
+    a.n_global = n;
+    a.params = h->pol;
+    a.obs = h->obs;
+    a.actions = h->act;
+    a.log_std = h->log_std;
+    a.adv_raw = h->adv_raw;
+    a.adv_stats = h->adv_stats;
+    a.old_logp = h->old_logp;
+    a.old_out = h->old_out;
+    a.scalar_partials = h->scalar_partials;
+    a.skip_flag = h->cg_flags + 1;
+    if (b200rl_mlp_loss_grad(&a, s)) return 1;
+    if (b200rl_reduce_partials(nullptr, h->scalar_partials, grid_f, h->Pp, nullptr, slot, 0, h->cg_flags + 1, s)) return 1;
+    if (trpo_ls_check(slot, (double)n, delta, h->cg_sc, h->cg_flags, k, s)) return 1;
+  }
+  if (trpo_ls_final(h->pol, h->cg_prev, P, delta, h->cg_sc, h->cg_flags, s)) return 1;
+  // (6) trpo.py:192 old_policy.load_state_dict(policy.state_dict()); then the value steps (:195-201)
+  B200RL_CUDA(cudaMemcpyAsync(h->old_pol, h->pol, (size_t)h->Pp * 4, cudaMemcpyDeviceToDevice, s));
+  const int vslot0 = 1 + nb;
+  if (run_value_loop(h, hp, nullptr, nullptr, n, vslot0, s)) return 1;
+
+  B200RL_CUDA(cudaMemcpyAsync(h->h_slots, h->slots, (size_t)n_slots * B200RL_N_SCALARS * sizeof(double),
+                              cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->h_stats3, h->adv_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->h_cg_sc, h->cg_sc, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->h_cg_flags, h->cg_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+
+  memset(stats, 0, sizeof(*stats));
+  memset(ts, 0, sizeof(*ts));
+  const double ng = (double)n;
+  const double* s0 = h->h_slots;
+  stats->policy_loss_before = s0[0] / ng;
+  stats->entropy_before = s0[2] / ng;
+  {
+    const double mean = s0[3] / ng;
+    stats->logp_std_before = sqrt(fmax(0.0, (s0[4] - ng * mean * mean) / (ng - 1.0)));
+  }
+  stats->kl_divergence = h->h_cg_sc[4];
+  double vsum = 0.0;
+  for (int j = 0; j < Kv; ++j) vsum += h->h_slots[(size_t)(vslot0 + j) * B200RL_N_SCALARS] / ng;
+  stats->value_loss_mean = Kv > 0 ? vsum / Kv : NAN;
+  stats->value_loss_first = Kv > 0 ? h->h_slots[(size_t)vslot0 * B200RL_N_SCALARS] / ng : NAN;
+  stats->value_loss_last = Kv > 0 ? h->h_slots[(size_t)(vslot0 + Kv - 1) * B200RL_N_SCALARS] / ng : NAN;
+  stats->policy_steps_applied = h->h_cg_flags[2] ? 0 : 1;
+  stats->value_steps_applied = h->h_flags[2];
+  {
+    const double cnt = h->h_stats3[2], mean = h->h_stats3[0] / cnt;
+    stats->adv_mean = mean;
+    stats->adv_std = sqrt((h->h_stats3[1] - cnt * mean * mean) / (cnt - 1.0));
+  }
+  h->val_step += h->h_flags[2];
+  stats->kernel_launches = (int32_t)(launches_total() - launches0);
+  ts->step_size = h->h_cg_sc[2];
+  ts->xhx = h->h_cg_sc[5];
+  ts->loss_before = h->h_cg_sc[1];
+  ts->new_loss = h->h_cg_sc[3];
+  ts->kl = h->h_cg_sc[4];
+  ts->accepted_index = (int32_t)h->h_cg_sc[6];
+  ts->rejected = h->h_cg_flags[2];
+  ts->cg_converged = h->h_cg_flags[0];
+  ts->fvp_launches = fvps;
+  return 0;
+}
+
 extern "C" int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr, int64_t* count,
                                            int32_t* dtype) {
   B200RL_REQUIRE(h && name && ptr && count && dtype, "device_view: NULL argument");
@@ -460,6 +657,7 @@ extern "C" int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name,
       {"value_grad", h->val_grad, h->Pv + B200RL_N_SCALARS, 0},
       {"policy_params", h->pol, h->Pp, 0},        {"old_policy_params", h->old_pol, h->Pp, 0},
       {"value_params", h->val, h->Pv, 0},         {"obs", h->obs, h->n_rows * h->obs_dim, 0},
+      {"cg_x", h->cg_x, h->cg_x ? h->Pp : 0, 0},  {"cg_descent", h->cg_descent, h->cg_descent ? h->Pp : 0, 0},
   };
   for (const V& v : views)
     if (strcmp(v.n, name) == 0) {

@@ -46,10 +46,14 @@ struct MlpLayout {
   int s_dz[2];          // dZ row-major ping-pong [TM][ldz]
   int ldz;
   int s_dist;           // per-action constants (Gaussian): var[A], log_scale[A]
+  // Fisher-vector product only: direction weights V^T [n_in][ld[l+1]], direction bias, tangents (feature-major)
+  int s_vt[MAXL], s_vb[MAXL];
+  int s_tt[MAXL + 1];   // tangent of activation l, feature-major [n[l]][TM]
+  int s_trm;            // tangent of the output, row-major [TM][ld[L]]
   int total_floats;
 };
 
-static int build_layout_tm(const b200rl_mlp_desc& d, bool backward, int TM, MlpLayout* out) {
+static int build_layout_tm(const b200rl_mlp_desc& d, bool backward, bool fvp, int TM, MlpLayout* out) {
   B200RL_REQUIRE(d.n_layers >= 1 && d.n_layers <= MAXL, "mlp: n_layers %d out of range 1..%d", d.n_layers, MAXL);
   MlpLayout L{};
   L.tm = TM;
@@ -92,15 +96,23 @@ static int build_layout_tm(const b200rl_mlp_desc& d, bool backward, int TM, MlpL
     L.s_dz[1] = take(TM * L.ldz);
   }
   L.s_dist = take(2 * L.ld[L.L]);
+  if (fvp) {
+    for (int l = 0; l < L.L; ++l) {
+      L.s_vt[l] = take(L.n[l] * L.ld[l + 1]);
+      L.s_vb[l] = take(L.ld[l + 1]);
+    }
+    for (int l = 1; l <= L.L; ++l) L.s_tt[l] = take(L.ld[l] * TM);
+    L.s_trm = take(TM * L.ld[L.L]);
+  }
   L.total_floats = s;
   *out = L;
   return 0;
 }
 
 // largest tile height whose shared-memory footprint fits
-int build_layout(const b200rl_mlp_desc& d, bool backward, MlpLayout* out) {
+int build_layout(const b200rl_mlp_desc& d, bool backward, MlpLayout* out, bool fvp = false) {
   for (int tm = TM_MAX; tm >= 16; tm >>= 1) {
-    if (build_layout_tm(d, backward, tm, out)) return 2;
+    if (build_layout_tm(d, backward, fvp, tm, out)) return 2;
     if ((size_t)out->total_floats * sizeof(float) <= 227 * 1024) return 0;
   }
   return 0;  // caller reports the size
@@ -124,6 +136,9 @@ struct FusedArgs {
   float* partials;
   double* scalar_partials;
   const int* skip_flag;
+  float* out_full;
+  const float* old_out;
+  const float* direction;
 };
 
 __device__ __forceinline__ float apply_act(float z, int kind) {
@@ -137,10 +152,13 @@ __device__ __forceinline__ float act_prime_from_output(float a, int kind) {
   return 1.f;
 }
 
-// C[m][n] = sum_k A[k*lda + m] * B[k*ldb + n], m < 4*M4, n < 4*N4; 4x4 register tile per thread.
+// C[m][n] = sum_k A[k*lda + m] * B[k*ldb + n] (+ sum_k A2[k*lda2 + m] * B2[k*ldb2 + n]), m < 4*M4, n < 4*N4;
+// 4x4 register tile per thread.
 template <class Epi>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                          int K, int M4, int N4, Epi epi) {
+                                          int K, int M4, int N4, Epi epi, const float* __restrict__ A2 = nullptr,
+                                          int lda2 = 0, const float* __restrict__ B2 = nullptr, int ldb2 = 0,
+                                          int K2 = 0) {
   const int ntiles = M4 * N4;
   for (int t = threadIdx.x; t < ntiles; t += MLP_THREADS) {
     const int mi = t % M4, ni = t / M4;
@@ -162,12 +180,31 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
+    if (K2 > 0) {
+      const float* a2 = A2 + 4 * mi;
+      const float* b2 = B2 + 4 * ni;
+#pragma unroll 4
+      for (int k = 0; k < K2; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(a2 + (size_t)k * lda2);
+        const float4 bv = *reinterpret_cast<const float4*>(b2 + (size_t)k * ldb2);
+        const float ar[4] = {av.x, av.y, av.z, av.w};
+        const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
     epi(4 * mi, 4 * ni, acc);
   }
 }
 
-template <int TM, bool BACKWARD>
+// MODE 0: forward only (EVAL / line search), 1: forward + backward, 2: Fisher-vector product (forward with tangents,
+// metric, backward)
+template <int TM, int MODE>
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedArgs p) {
+  constexpr bool BACKWARD = MODE != 0;
+  constexpr bool FVP = MODE == 2;
   extern __shared__ __align__(16) float smem[];
   const MlpLayout& Y = p.lay;
   const int tid = threadIdx.x;
@@ -198,6 +235,24 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
     for (int o = tid; o < Y.ld[l + 1]; o += MLP_THREADS)
       smem[Y.s_bias[l] + o] = o < nout ? __ldg(p.params + Y.b_off[l] + o) : 0.f;
   }
+  if (FVP) {
+    for (int l = 0; l < L; ++l) {
+      const int nin = Y.n[l], nout = Y.n[l + 1];
+      float* vt = smem + Y.s_vt[l];
+      for (int idx = tid; idx < nin * Y.ld[l + 1]; idx += MLP_THREADS) vt[idx] = 0.f;
+    }
+    __syncthreads();
+    for (int l = 0; l < L; ++l) {
+      const int nin = Y.n[l], nout = Y.n[l + 1];
+      float* vt = smem + Y.s_vt[l];
+      for (int idx = tid; idx < nin * nout; idx += MLP_THREADS) {
+        const int o = idx / nin, i = idx - o * nin;
+        vt[i * Y.ld[l + 1] + o] = __ldg(p.direction + Y.w_off[l] + idx);
+      }
+      for (int o = tid; o < Y.ld[l + 1]; o += MLP_THREADS)
+        smem[Y.s_vb[l] + o] = o < nout ? __ldg(p.direction + Y.b_off[l] + o) : 0.f;
+    }
+  }
   if (BACKWARD)
     for (int i = tid; i < Y.P; i += MLP_THREADS) smem[Y.s_dw + i] = 0.f;
   const int A_out = Y.n[L];
@@ -225,7 +280,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
   }
   __syncthreads();
 
-  double sc[6] = {0, 0, 0, 0, 0, 0};  // loss terms, old_logp - logp, entropy, logp, logp^2, rows
+  double sc[7] = {0, 0, 0, 0, 0, 0, 0};  // loss terms, old_logp - logp, entropy, logp, logp^2, rows, KL(old||new)
   const long long num_tiles = (p.n_rows + TM - 1) / TM;
   const int n0 = Y.n[0], ld0 = Y.ld[0];
 
@@ -273,6 +328,31 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
                   }
                 });
       __syncthreads();
+      if (FVP) {
+        // tangent (J v) propagation: T_{l+1} = act'(H_{l+1}) * (T_l W^T + X_l V^T + v_b);  T_0 = 0
+        const float* vb = smem + Y.s_vb[l];
+        float* tt = smem + Y.s_tt[l + 1];
+        float* trm = smem + Y.s_trm;
+        const bool last = (l == L - 1);
+        tile_gemm(smem + Y.s_xt[l], TM, smem + Y.s_vt[l], ldo, Y.n[l], TM / 4, ldo / 4,
+                  [&](int m0, int c0, float (&acc)[4][4]) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const int c = c0 + j;
+                      if (c < nout) {
+                        float t[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                          t[i] = (acc[i][j] + vb[c]) * act_prime_from_output(orm[(m0 + i) * ldo + c], kind);
+                          if (last) trm[(m0 + i) * ldo + c] = t[i];
+                        }
+                        *reinterpret_cast<float4*>(tt + c * TM + m0) = make_float4(t[0], t[1], t[2], t[3]);
+                      }
+                    }
+                  },
+                  l > 0 ? smem + Y.s_tt[l] : nullptr, TM, smem + Y.s_wt[l], ldo, l > 0 ? Y.n[l] : 0);
+        __syncthreads();
+      }
     }
 
     // ---- distribution / loss epilogue: one thread per row ----
@@ -284,7 +364,33 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
       float* dzrm = BACKWARD ? smem + Y.s_dz[L & 1] + r * Y.ldz : nullptr;
       float* dzt = smem + Y.s_xt[L];
       float lp = 0.f, ent = 0.f;
-      if (valid) {
+      if (valid && FVP) {
+        // metric of the distribution applied to the output tangent: u = M (J v); dOut = u / N.
+        // Gaussian with fixed std: M = diag(1/var).  Categorical: M = diag(p) - p p^T.
+        const float* t = smem + Y.s_trm + r * Y.ld[L];
+        if (p.dist == B200RL_DIST_GAUSSIAN) {
+          const float* var = smem + Y.s_dist;
+          for (int a = 0; a < A_out; ++a) {
+            const float g = (t[a] / var[a]) * p.inv_n;
+            dzrm[a] = g;
+            dzt[a * TM + r] = g;
+          }
+        } else {
+          float m = out[0];
+          for (int a = 1; a < A_out; ++a) m = fmaxf(m, out[a]);
+          float se = 0.f;
+          for (int a = 0; a < A_out; ++a) se += expf(out[a] - m);
+          const float lse = m + logf(se);
+          float pt = 0.f;
+          for (int a = 0; a < A_out; ++a) pt += expf(out[a] - lse) * t[a];
+          for (int a = 0; a < A_out; ++a) {
+            const float g = expf(out[a] - lse) * (t[a] - pt) * p.inv_n;
+            dzrm[a] = g;
+            dzt[a * TM + r] = g;
+          }
+        }
+        sc[5] += 1.0;
+      } else if (valid) {
         float coef = 0.f, term = 0.f;
         if (p.dist == B200RL_DIST_NONE) {
           const float vout = out[0];
@@ -329,6 +435,36 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
             }
           }
           if (p.row_out) p.row_out[row] = lp;
+          if (p.out_full)
+            for (int a = 0; a < A_out; ++a) p.out_full[row * A_out + a] = out[a];
+          if (p.old_out) {  // kl_divergence(old_dist, dist), trpo.py:167-175
+            const float* oo = p.old_out + row * A_out;
+            float kl = 0.f;
+            if (p.dist == B200RL_DIST_GAUSSIAN) {  // same std: 0.5 * ((mu_old - mu) / std)^2 summed
+              const float* var = smem + Y.s_dist;
+              for (int a = 0; a < A_out; ++a) {
+                const float d = __ldg(oo + a) - out[a];
+                kl += 0.5f * ((d * d) / var[a]);
+              }
+            } else {
+              float mo = __ldg(oo), mn = out[0];
+              for (int a = 1; a < A_out; ++a) {
+                mo = fmaxf(mo, __ldg(oo + a));
+                mn = fmaxf(mn, out[a]);
+              }
+              float so = 0.f, sn = 0.f;
+              for (int a = 0; a < A_out; ++a) {
+                so += expf(__ldg(oo + a) - mo);
+                sn += expf(out[a] - mn);
+              }
+              const float lo = mo + logf(so), ln = mn + logf(sn);
+              for (int a = 0; a < A_out; ++a) {
+                const float lpo = __ldg(oo + a) - lo;
+                kl += expf(lpo) * (lpo - (out[a] - ln));
+              }
+            }
+            sc[6] += (double)kl;
+          }
           float adv = 0.f, oldlp = 0.f;
           if (p.loss != B200RL_LOSS_EVAL) {
             adv = __ldg(p.adv_raw + row);
@@ -429,17 +565,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
     for (int i = tid; i < Y.P; i += MLP_THREADS) dst[i] = smem[Y.s_dw + i];
   }
   if (p.scalar_partials != nullptr) {
-    __shared__ double s_sc[6][MLP_THREADS / 32];
+    __shared__ double s_sc[7][MLP_THREADS / 32];
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 7; ++k) {
       const double v = warp_sum(sc[k]);
       if (lane == 0) s_sc[k][warp] = v;
     }
     __syncthreads();
     if (tid < B200RL_N_SCALARS) {
       double t = 0.0;
-      if (tid < 6)
+      if (tid < 7)
         for (int w = 0; w < MLP_THREADS / 32; ++w) t += s_sc[tid][w];
       p.scalar_partials[(size_t)blockIdx.x * B200RL_N_SCALARS + tid] = t;
     }
@@ -479,41 +615,49 @@ extern "C" int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp) {
   return p;
 }
 
+// with_backward: 0 forward only, 1 forward + backward, 2 Fisher-vector product, 3 forward only on the fp32 kernel
+// (launches that use out_full / old_out / B200RL_FLAG_NO_TC)
 extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward) {
   if (!mlp) return -1;
-  if (use_tc(*mlp)) return tc_grid(n_rows);
+  if (with_backward < 2 && use_tc(*mlp)) return tc_grid(n_rows);
   MlpLayout lay;
-  if (build_layout(*mlp, with_backward != 0, &lay)) return -1;
+  if (build_layout(*mlp, with_backward == 1 || with_backward == 2, &lay, with_backward == 2)) return -1;
   return fused_grid(lay, n_rows);
 }
 
 extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   B200RL_REQUIRE(a != nullptr, "mlp_loss_grad: NULL args");
-  const bool backward = a->loss != B200RL_LOSS_EVAL;
+  const bool fvp = a->loss == B200RL_LOSS_FVP;
+  const bool forward_only = (a->flags & B200RL_FLAG_FORWARD_ONLY) != 0 || a->loss == B200RL_LOSS_EVAL;
+  const bool backward = !forward_only;
+  B200RL_REQUIRE(!(fvp && forward_only), "mlp_loss_grad: FVP cannot be forward-only");
   FusedArgs k{};
-  if (build_layout(a->mlp, backward, &k.lay)) return 2;
+  if (build_layout(a->mlp, backward, &k.lay, fvp)) return 2;
   const int L = k.lay.L;
   B200RL_REQUIRE(a->n_rows >= 0, "mlp_loss_grad: negative n_rows");
   B200RL_REQUIRE(a->params && a->obs, "mlp_loss_grad: params/obs is NULL");
-  B200RL_REQUIRE(a->loss >= B200RL_LOSS_EVAL && a->loss <= B200RL_LOSS_MSE, "mlp_loss_grad: bad loss %d", a->loss);
+  B200RL_REQUIRE(a->loss >= B200RL_LOSS_EVAL && a->loss <= B200RL_LOSS_FVP, "mlp_loss_grad: bad loss %d", a->loss);
   if (a->dist == B200RL_DIST_NONE) {
     B200RL_REQUIRE(a->loss == B200RL_LOSS_EVAL || a->loss == B200RL_LOSS_MSE,
                    "mlp_loss_grad: dist NONE supports only EVAL / MSE");
     B200RL_REQUIRE(k.lay.n[L] == 1, "mlp_loss_grad: value head must have one output, got %d", k.lay.n[L]);
     B200RL_REQUIRE(a->loss != B200RL_LOSS_MSE || a->target, "mlp_loss_grad: MSE needs target");
+    B200RL_REQUIRE(!a->out_full && !a->old_out, "mlp_loss_grad: out_full / old_out need a distribution");
   } else {
     B200RL_REQUIRE(a->dist == B200RL_DIST_GAUSSIAN || a->dist == B200RL_DIST_CATEGORICAL, "mlp_loss_grad: bad dist");
     B200RL_REQUIRE(a->loss != B200RL_LOSS_MSE, "mlp_loss_grad: MSE needs dist NONE");
-    B200RL_REQUIRE(a->actions, "mlp_loss_grad: actions is NULL");
+    B200RL_REQUIRE(fvp || a->actions, "mlp_loss_grad: actions is NULL");
     B200RL_REQUIRE(k.lay.n[L] <= 16, "mlp_loss_grad: at most 16 action dimensions, got %d", k.lay.n[L]);
     B200RL_REQUIRE(a->dist != B200RL_DIST_GAUSSIAN || a->log_std, "mlp_loss_grad: Gaussian needs log_std");
-    if (a->loss != B200RL_LOSS_EVAL) B200RL_REQUIRE(a->adv_raw, "mlp_loss_grad: policy loss needs adv_raw");
+    if (a->loss != B200RL_LOSS_EVAL && !fvp) B200RL_REQUIRE(a->adv_raw, "mlp_loss_grad: policy loss needs adv_raw");
     if (a->loss == B200RL_LOSS_PPO_CLIP || a->loss == B200RL_LOSS_TRPO_SURROGATE)
       B200RL_REQUIRE(a->old_logp, "mlp_loss_grad: PPO/TRPO loss needs old_logp");
+    if (fvp) B200RL_REQUIRE(a->direction, "mlp_loss_grad: FVP needs the direction vector");
   }
   if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
-  if (use_tc(a->mlp)) return launch_mlp_tc(a, a->n_global > 0 ? a->n_global : a->n_rows, s);
+  const bool needs_fp32 = fvp || a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC);
+  if (!needs_fp32 && use_tc(a->mlp)) return launch_mlp_tc(a, a->n_global > 0 ? a->n_global : a->n_rows, s);
   const size_t smem_bytes = (size_t)k.lay.total_floats * sizeof(float);
   B200RL_REQUIRE(smem_bytes <= 227 * 1024,
                  "mlp_loss_grad: network needs %zu bytes of shared memory (> 227 KiB); too large for the fused kernel",
@@ -537,21 +681,28 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
   k.partials = a->partials;
   k.scalar_partials = a->scalar_partials;
   k.skip_flag = a->skip_flag;
+  k.out_full = a->out_full;
+  k.old_out = a->old_out;
+  k.direction = a->direction;
   const int grid = fused_grid(k.lay, a->n_rows);
   B200RL_REQUIRE(grid > 0, "mlp_loss_grad: no CUDA device");
-#define B200RL_LAUNCH_FUSED(TMV, BWD)                                                                        \
-  do {                                                                                                      \
-    B200RL_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<TMV, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)smem_bytes));                                                     \
-    mlp_fused_kernel<TMV, BWD><<<grid, MLP_THREADS, smem_bytes, s>>>(k);                                    \
+  const int mode = fvp ? 2 : (backward ? 1 : 0);
+#define B200RL_LAUNCH_FUSED(TMV, MODEV)                                                                       \
+  do {                                                                                                         \
+    B200RL_CUDA(cudaFuncSetAttribute(mlp_fused_kernel<TMV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem_bytes));                                                        \
+    mlp_fused_kernel<TMV, MODEV><<<grid, MLP_THREADS, smem_bytes, s>>>(k);                                     \
   } while (0)
-  if (k.lay.tm == 64) {
-    if (backward) B200RL_LAUNCH_FUSED(64, true); else B200RL_LAUNCH_FUSED(64, false);
-  } else if (k.lay.tm == 32) {
-    if (backward) B200RL_LAUNCH_FUSED(32, true); else B200RL_LAUNCH_FUSED(32, false);
-  } else {
-    if (backward) B200RL_LAUNCH_FUSED(16, true); else B200RL_LAUNCH_FUSED(16, false);
-  }
+#define B200RL_LAUNCH_TM(TMV)                      \
+  do {                                             \
+    if (mode == 2) B200RL_LAUNCH_FUSED(TMV, 2);    \
+    else if (mode == 1) B200RL_LAUNCH_FUSED(TMV, 1); \
+    else B200RL_LAUNCH_FUSED(TMV, 0);              \
+  } while (0)
+  if (k.lay.tm == 64) B200RL_LAUNCH_TM(64);
+  else if (k.lay.tm == 32) B200RL_LAUNCH_TM(32);
+  else B200RL_LAUNCH_TM(16);
+#undef B200RL_LAUNCH_TM
 #undef B200RL_LAUNCH_FUSED
   B200RL_CUDA(cudaGetLastError());
   count_launch(1);

@@ -12,7 +12,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import DIST, MlpDesc, OnPolicyConfig, PpoHparams, UpdateStats, check
+from ._lib import DIST, MlpDesc, OnPolicyConfig, PpoHparams, TrpoHparams, TrpoStats, UpdateStats, check
 
 POLICY, OLD_POLICY, VALUE = 0, 1, 2
 
@@ -182,6 +182,27 @@ class OnPolicyEngine:
         check(fn(self.h, C.byref(hp), cb, None, C.byref(stats), current_stream_handle()), f"{algo}_update")
         self._keep.clear()  # the update synchronised the stream: staged host buffers are no longer in flight
         return stats
+
+    def trpo_update(self, hp: PpoHparams, max_constraint=0.01, n_conjugate_gradients=10, max_backtracks=15,
+                    backtrack_ratio=0.8, hvp_damping_coefficient=1e-5):
+        """The reference's TRPO.train on the loaded batch; returns (UpdateStats, TrpoStats)."""
+        cg = TrpoHparams()
+        cg.max_constraint, cg.n_conjugate_gradients = float(max_constraint), int(n_conjugate_gradients)
+        cg.max_backtracks, cg.backtrack_ratio = int(max_backtracks), float(backtrack_ratio)
+        cg.hvp_damping_coefficient = float(hvp_damping_coefficient)
+        stats, ts = UpdateStats(), TrpoStats()
+        check(self.lib.b200rl_trpo_update(self.h, C.byref(hp), C.byref(cg), C.byref(stats), C.byref(ts),
+                                          current_stream_handle()), "trpo_update")
+        self._keep.clear()
+        return stats, ts
+
+    def fvp(self, v: np.ndarray, damping: float = 1e-5) -> np.ndarray:
+        """(F + damping I) v at the current policy parameters on the loaded batch (one fused FVP launch)."""
+        v = _c(v, np.float32)
+        out = np.empty_like(v)
+        check(self.lib.b200rl_onpolicy_fvp(self.h, _ptr(v), _ptr(out), v.size, float(damping), current_stream_handle()),
+              "fvp")
+        return out
 
     def run_stage(self, stage: str, hp: PpoHparams):
         check(self.lib.b200rl_onpolicy_run_stage(self.h, stage.encode(), C.byref(hp), current_stream_handle()),

@@ -47,7 +47,8 @@ _stub_gymnasium()
 sys.path.insert(0, "/root/reference/src")
 import rl_replicas.algorithms.ppo as ref_ppo_mod  # noqa: E402
 import rl_replicas.algorithms.vpg as ref_vpg_mod  # noqa: E402
-from rl_replicas.algorithms import PPO, VPG  # noqa: E402
+from rl_replicas.algorithms import PPO, TRPO, VPG  # noqa: E402
+from rl_replicas.optimizers import ConjugateGradientOptimizer  # noqa: E402
 from rl_replicas.experience import Experience  # noqa: E402
 from rl_replicas.networks import MLP  # noqa: E402
 from rl_replicas.policies import CategoricalPolicy, GaussianPolicy  # noqa: E402
@@ -231,6 +232,78 @@ def run_vpg_case(name, batch_fn, obs_dim, act_dim, discrete):
     print(name, "done")
 
 
+def run_trpo_case(name, batch_fn, obs_dim, act_dim, discrete):
+    """TRPO.train with the reference's ConjugateGradientOptimizer; records g, one Hessian-vector product of a fixed
+    probe vector, the CG solution, the descent step and the outcome of the line search."""
+    set_seed_for_libraries(0)
+    pnet, vnet = MLP([obs_dim, 64, 64, act_dim]), MLP([obs_dim, 64, 64, 1])
+    opt = ConjugateGradientOptimizer(pnet.parameters())
+    if discrete:
+        policy, log_std = CategoricalPolicy(pnet, opt), None
+    else:
+        log_std = torch.nn.Parameter(-0.5 * torch.ones(act_dim))
+        policy = GaussianPolicy(pnet, opt, log_std)
+    vf = ValueFunction(vnet, torch.optim.Adam(vnet.parameters(), lr=1e-3))
+    with torch.no_grad():
+        batch = batch_fn(lambda o: policy.network(torch.from_numpy(o)).numpy())
+    exp = Experience(**synthetic.to_experience_lists(batch, discrete))
+    trpo = TRPO(policy, vf, None, None, num_value_gradients=5)
+    trpo.metrics_manager = Recorder()
+    trpo.current_total_steps = 0
+    out = dict(batch)
+    out["policy_flat0"], out["value_flat0"] = flat(policy.network), flat(vf.network)
+    if log_std is not None:
+        out["log_std"] = log_std.detach().numpy().copy()
+    out["policy_sizes"] = np.asarray([obs_dim, 64, 64, act_dim])
+    out["value_sizes"] = np.asarray([obs_dim, 64, 64, 1])
+    cap = {}
+    rng = np.random.default_rng(11)
+    probe = rng.standard_normal(out["policy_flat0"].size).astype(np.float32)
+    out["hvp_probe"] = probe
+    orig_build, orig_cg, orig_ls = opt._build_hessian_vector_product, opt._conjugate_gradient, opt._backtracking_line_search
+
+    def build_wrap(fn, params):
+        hvp = orig_build(fn, params)
+        if "hvp_of_probe" not in cap:
+            cap["hvp_of_probe"] = hvp(torch.from_numpy(probe)).detach().numpy().copy()
+        return hvp
+
+    def cg_wrap(hvp, b, residual_tol=1e-10):
+        cap["grad0"] = b.detach().numpy().copy()
+        x = orig_cg(hvp, b, residual_tol)
+        cap["cg_x"] = x.detach().numpy().copy()
+        return x
+
+    def ls_wrap(params, descent_step, loss_fn, kl_fn):
+        cap["descent"] = torch.as_tensor(descent_step).detach().numpy().copy()
+        orig_ls(params, descent_step, loss_fn, kl_fn)
+        with torch.no_grad():
+            cap["final_loss"] = float(loss_fn())
+            cap["final_kl"] = float(kl_fn())
+
+    opt._build_hessian_vector_product, opt._conjugate_gradient, opt._backtracking_line_search = build_wrap, cg_wrap, ls_wrap
+    import rl_replicas.algorithms.trpo as ref_trpo_mod
+    orig_norm = ref_trpo_mod.normalize_tensor
+
+    def norm_wrap(t):
+        r = orig_norm(t)
+        cap["adv"] = r.numpy().copy()
+        return r
+
+    ref_trpo_mod.normalize_tensor = norm_wrap
+    try:
+        trpo.train(exp)
+    finally:
+        ref_trpo_mod.normalize_tensor = orig_norm
+    out.update(cap)
+    out["policy_flat_final"], out["value_flat_final"] = flat(policy.network), flat(vf.network)
+    for k, val in trpo.metrics_manager.scalars.items():
+        out["metric:" + k] = val
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    moved = np.abs(out["policy_flat_final"] - out["policy_flat0"]).max()
+    print(name, "N=", batch["obs"].shape[0], "moved", moved, "final kl", cap["final_kl"], "loss", cap["final_loss"])
+
+
 def scan_kats():
     """Known-answer tests of the two scan helpers, taken from the reference functions themselves."""
     out = {}
@@ -264,5 +337,9 @@ if __name__ == "__main__":
     run_ppo_case("ppo_gaussian_ragged_earlystop",
                  lambda mf: synthetic.ragged_batch(1500, 17, 6, False, seed=1, min_len=1, max_len=120, mean_fn=mf),
                  17, 6, False)
+    run_trpo_case("trpo_gaussian_small",
+                  lambda mf: synthetic.fixed_batch(8, 150, 27, 8, seed=4, frac_not_done=0.3, mean_fn=mf), 27, 8, False)
+    run_trpo_case("trpo_categorical_small",
+                  lambda mf: synthetic.ragged_batch(1000, 4, 3, True, seed=5, min_len=5, max_len=80), 4, 3, True)
     run_vpg_case("vpg_gaussian_small",
                  lambda mf: synthetic.fixed_batch(4, 150, 17, 6, seed=2, frac_not_done=0.5, mean_fn=mf), 17, 6, False)

@@ -136,3 +136,27 @@ def test_torch_port_matches_reference(case):
     assert rel_err(out["value_flat"], g["value_flat_final"]) < 1e-5
     assert rel_err(out["value_losses"], g["value_losses"]) < 1e-5
     assert rel_err(out["ret"], g["ret"]) < 1e-6 and rel_err(out["adv"], g["adv"]) < 1e-5
+
+
+TRPO_CASES = ["trpo_gaussian_small", "trpo_categorical_small"]
+
+
+@pytest.mark.parametrize("case", TRPO_CASES)
+def test_trpo_pieces_match_reference(case):
+    """Analytic Fisher-vector product == the reference's double-backprop Hessian-vector product at theta_old; CG
+    solution, descent step and the line-search outcome match the reference's ConjugateGradientOptimizer."""
+    g = load_golden(case)
+    policy, value, kind, log_std = _setup(g)
+    b = batch_of(g)
+    hv = O.fisher_vector_product(policy, kind, log_std, b["obs"], g["hvp_probe"], 1e-5)
+    assert rel_err(hv, g["hvp_of_probe"]) < 1e-5
+    out = O.trpo_policy_step(policy, kind, log_std, b["obs"], b["act"], g["adv"])
+    assert rel_err(out["grad"], g["grad0"]) < TOL
+    # CG amplifies round-off over 10 iterations (SURVEY 7.3-9): documented looser bounds
+    assert rel_err(out["x"], g["cg_x"]) < 2e-3
+    assert rel_err(out["descent"], g["descent"]) < 2e-3
+    assert rel_err(out["policy_flat"], g["policy_flat_final"]) < 2e-3
+    assert not out["rejected"]
+    assert abs(out["kl"] - g["final_kl"]) < 2e-2 * g["final_kl"]
+    assert abs(out["new_loss"] - g["final_loss"]) < 2e-2 * abs(g["final_loss"])
+    assert abs(out["loss_before"] - g["metric:policy/loss"]) < 1e-6
