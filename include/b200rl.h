@@ -250,6 +250,50 @@ int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr
 int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, const b200rl_ppo_hparams* hp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Off-policy update engine (DDPG / TD3): the reference's `train(replay_buffer, num_train_steps, minibatch_size)`
+ * (algorithms/td3.py:214-358, algorithms/ddpg.py:195-293) on device.  Networks: 0 policy, 1 Q1, 2 Q2, 3 target
+ * policy, 4 target Q1, 5 target Q2 (2 and 5 absent when n_q = 1).  Minibatch sampling (numpy RNG) and the
+ * target-smoothing noise (torch CPU RNG) stay on the host so the reference's random streams are reproduced; ALL
+ * minibatches of one train() call are handed over at once.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct b200rl_offpolicy b200rl_offpolicy;
+
+typedef struct {
+  b200rl_mlp_desc policy;  /* [obs, hidden..., act]      (ref: policies/deterministic_policy.py) */
+  b200rl_mlp_desc q;       /* [obs + act, hidden..., 1]  (ref: q_function.py:20-32) */
+  int32_t n_q;             /* 1 = DDPG, 2 = TD3 */
+  int32_t max_minibatch;   /* capacity: rows per minibatch */
+  int32_t max_steps;       /* capacity: train steps per call */
+  int32_t reserved;
+} b200rl_offpolicy_config;
+
+typedef struct {
+  double gamma, polyak_rho;
+  double target_noise_scale, target_noise_clip, action_limit; /* td3.py:328-332 */
+  int32_t policy_delay;      /* td3.py:244 (DDPG: 1) */
+  int32_t use_target_noise;  /* 1 = TD3 target smoothing, 0 = DDPG */
+  double policy_lr, policy_beta1, policy_beta2, policy_eps;
+  double q1_lr, q2_lr, q_beta1, q_beta2, q_eps;
+} b200rl_offpolicy_hparams;
+
+int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200rl_offpolicy** out);
+void b200rl_offpolicy_destroy(b200rl_offpolicy* h);
+int b200rl_offpolicy_set_params(b200rl_offpolicy* h, int which, const float* host_flat, int64_t n, void* stream);
+int b200rl_offpolicy_get_params(b200rl_offpolicy* h, int which, float* host_flat, int64_t n, void* stream);
+/* which: 0 policy, 1 Q1, 2 Q2 optimizers */
+int b200rl_offpolicy_set_adam(b200rl_offpolicy* h, int which, const float* exp_avg, const float* exp_avg_sq, int64_t n,
+                              int64_t step, void* stream);
+int b200rl_offpolicy_get_adam(b200rl_offpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              int64_t* step, void* stream);
+/* HOST buffers: obs/next_obs [S,B,O], act [S,B,A], rew/done [S,B] float32 (done as 0/1), noise [S,B,A] raw N(0,1)
+ * draws (NULL for DDPG).  Outputs (host): q1_values/q2_values [S,B] (the logged pre-update Q-values), q1_losses /
+ * q2_losses [S], policy_losses [*n_policy_updates].  One upload, S steps without host synchronisation, one read-back. */
+int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S, int32_t B,
+                           const float* obs, const float* act, const float* rew, const float* next_obs,
+                           const float* done, const float* noise, float* q1_values, float* q2_values, float* q1_losses,
+                           float* q2_losses, float* policy_losses, int32_t* n_policy_updates, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Diagnostics (not on the product path): issue a chain of tcgen05.mma kind::tf32 instructions on a caller-supplied
  * shared-memory image and return the raw TMEM contents [128 lanes, read_cols]; tests use it to pin the descriptor
  * and TMEM layouts the tensor-core kernels rely on.  mmas: array of {u64 adesc, u64 bdesc, u32 idesc, u32 dcol,

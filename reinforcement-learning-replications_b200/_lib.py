@@ -76,6 +76,19 @@ class TrpoStats(C.Structure):
                 ("fvp_launches", C.c_int32)]
 
 
+class OffPolicyConfig(C.Structure):
+    _fields_ = [("policy", MlpDesc), ("q", MlpDesc), ("n_q", C.c_int32), ("max_minibatch", C.c_int32),
+                ("max_steps", C.c_int32), ("reserved", C.c_int32)]
+
+
+class OffPolicyHparams(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("polyak_rho", C.c_double), ("target_noise_scale", C.c_double),
+                ("target_noise_clip", C.c_double), ("action_limit", C.c_double), ("policy_delay", C.c_int32),
+                ("use_target_noise", C.c_int32), ("policy_lr", C.c_double), ("policy_beta1", C.c_double),
+                ("policy_beta2", C.c_double), ("policy_eps", C.c_double), ("q1_lr", C.c_double), ("q2_lr", C.c_double),
+                ("q_beta1", C.c_double), ("q_beta2", C.c_double), ("q_eps", C.c_double)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
 
 # name -> (restype, argtypes); must list every symbol include/b200rl.h declares (tests/test_abi.py checks)
@@ -114,6 +127,15 @@ SIGNATURES = {
     "b200rl_onpolicy_fvp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     "b200rl_onpolicy_device_view": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                               C.POINTER(C.c_int32)]),
+    "b200rl_offpolicy_create": (C.c_int, [C.POINTER(OffPolicyConfig), C.POINTER(C.c_void_p)]),
+    "b200rl_offpolicy_destroy": (None, [C.c_void_p]),
+    "b200rl_offpolicy_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200rl_offpolicy_get_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "b200rl_offpolicy_set_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "b200rl_offpolicy_get_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.POINTER(C.c_int64), C.c_void_p]),
+    "b200rl_offpolicy_train": (C.c_int, [C.c_void_p, C.POINTER(OffPolicyHparams), C.c_int32, C.c_int32] +
+                               [C.c_void_p] * 11 + [C.POINTER(C.c_int32), C.c_void_p]),
     "b200rl_tc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200rl_onpolicy_run_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(PpoHparams), C.c_void_p]),
 }

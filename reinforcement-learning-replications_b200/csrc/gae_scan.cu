@@ -157,23 +157,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) gae_scan_kernel(const ScanArg
   __shared__ double s_red[2][SCAN_THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (warp == 0) {
-    int t = 0;
-    if (lane == 0) {
-      s_epoch = *reinterpret_cast<volatile int*>(&p.hdr->epoch);  // constant for the whole launch
-      t = p.num_tiles - 1 - atomicAdd(&p.hdr->ticket, 1);
-      s_tile = t;
-    }
-    t = __shfl_sync(0xffffffffu, t, 0);
-    // episodes that overlap this tile: found once per CTA, cooperatively
-    const long long t0 = (long long)t * SCAN_TILE;
-    const long long t1 = (t0 + SCAN_TILE - 1 < p.n - 1) ? t0 + SCAN_TILE - 1 : p.n - 1;
-    const long long e0 = warp_find_episode(p.off, p.n_ep, t0, lane);
-    const long long e1 = warp_find_episode(p.off, p.n_ep, t1, lane);
-    if (lane == 0) {
-      s_e0 = e0;
-      s_e1 = e1;
-    }
+  if (tid == 0) {
+    s_epoch = *reinterpret_cast<volatile int*>(&p.hdr->epoch);  // constant for the whole launch
+    s_tile = p.num_tiles - 1 - atomicAdd(&p.hdr->ticket, 1);
   }
   __syncthreads();
   const int tile = s_tile;
@@ -182,7 +168,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) gae_scan_kernel(const ScanArg
   const long long i0 = (long long)tile * SCAN_TILE + (long long)tid * SCAN_ITEMS;
   const bool full = (i0 + SCAN_ITEMS <= n);
 
-  // ---- loads (vectorised when the thread's 8 items are all in range) ----
+  // ---- loads first (vectorised when the thread's 8 items are all in range): their DRAM latency overlaps the
+  //      episode search below ----
   double r[SCAN_ITEMS];
   float v[SCAN_ITEMS + 1];
   load_rewards<RewT>(static_cast<const RewT*>(p.rew), i0, full, n, r);
@@ -196,6 +183,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) gae_scan_kernel(const ScanArg
     for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (i0 + j < n) ? p.values[i0 + j] : 0.f;
   }
   v[SCAN_ITEMS] = (i0 + SCAN_ITEMS < n) ? __ldg(p.values + i0 + SCAN_ITEMS) : 0.f;
+
+  // ---- episodes that overlap this tile: found once per CTA, cooperatively by warp 0 ----
+  if (warp == 0) {
+    const long long t0 = (long long)tile * SCAN_TILE;
+    const long long t1 = (t0 + SCAN_TILE - 1 < n - 1) ? t0 + SCAN_TILE - 1 : n - 1;
+    const long long e0 = warp_find_episode(p.off, p.n_ep, t0, lane);
+    const long long e1 = warp_find_episode(p.off, p.n_ep, t1, lane);
+    if (lane == 0) {
+      s_e0 = e0;
+      s_e1 = e1;
+    }
+  }
+  __syncthreads();
 
   // ---- which episode does item i0 belong to?  e = max{e : off[e] <= i0} ----
   long long e = 0, next_off = 0;

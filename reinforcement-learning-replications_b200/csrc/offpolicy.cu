@@ -1,0 +1,544 @@
+// Off-policy update engine: DDPG / TD3 train() on device-resident minibatches.
+//
+// Replaces (reference: /root/reference/src/rl_replicas/): algorithms/td3.py:214-358 (train, train_policy,
+// compute_targets, train_q_function), algorithms/ddpg.py:195-293, q_function.py:20-32, policies/
+// deterministic_policy.py:23-32, utils.py:47-57 (polyak_average), and the torch.optim.Adam steps inside them.
+//
+// Regime: minibatch B ~ 100-256 rows, 256-wide ReLU MLPs (~70k parameters each): ~0.5 GFLOP per train step, i.e.
+// launch-latency bound, not throughput bound.  The design therefore minimises host involvement:
+// ALL `num_train_steps` minibatches (and the target-smoothing noise) are uploaded once, every step runs as a fixed
+// sequence of small fp32 kernels with no host synchronisation, and losses / Q-values are read back once at the end.
+// GEMMs are one generic 64x64x16 shared-memory-tiled fp32 kernel in three operand arrangements (forward NT, dX NN,
+// dW TN) with the activation derivative fused into the operand load, so activations are never rewritten.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int GT = 64;   // output tile
+constexpr int GK = 16;   // k tile
+constexpr int GTHREADS = 256;
+
+__device__ __forceinline__ float op_act(float z, int kind) {
+  if (kind == B200RL_ACT_TANH) return tanhf(z);
+  if (kind == B200RL_ACT_RELU) return fmaxf(z, 0.f);
+  return z;
+}
+__device__ __forceinline__ float op_act_prime(float y, int kind) {  // derivative from the activation OUTPUT
+  if (kind == B200RL_ACT_TANH) return 1.f - y * y;
+  if (kind == B200RL_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// MODE 0 (NT): C[M,N] = act(A[M,K] * B[N,K]^T + bias[N])              forward: A = X, B = W [out,in]
+// MODE 1 (NN): C[M,N] = (A (.) act'(Y))[M,K] * B[K,N]                  dX = dZ * W,   A = dY, Y = layer output
+// MODE 2 (TN): C[M,N] = (A (.) act'(Y))[K,M]^T * B[K,N]                dW = dZ^T * X, A = dY [rows, out]
+// All matrices row-major with explicit leading dimensions.  Y (same shape / ld as A) may be NULL (no derivative).
+struct GemmArgs {
+  const float* A; int lda;
+  const float* B; int ldb;
+  float* C; int ldc;
+  const float* bias;
+  const float* Y; int ldy; int act;  // MODE 0: output activation; MODE 1/2: activation whose derivative gates A
+  int M, N, K;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(GTHREADS) gemm_kernel(const GemmArgs g) {
+  __shared__ float As[GK][GT + 4], Bs[GK][GT + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < g.K; k0 += GK) {
+    // stage A^T-style: As[k][m], Bs[k][n]
+    for (int idx = tid; idx < GK * GT; idx += GTHREADS) {
+      int k, m;
+      if (MODE == 2) { k = idx / GT; m = idx % GT; } else { m = idx / GK; k = idx % GK; }
+      const int gm = m0 + m, gk = k0 + k;
+      float a = 0.f;
+      if (gm < g.M && gk < g.K) {
+        if (MODE == 2) {
+          a = g.A[(size_t)gk * g.lda + gm];
+          if (g.Y) a *= op_act_prime(g.Y[(size_t)gk * g.ldy + gm], g.act);
+        } else {
+          a = g.A[(size_t)gm * g.lda + gk];
+          if (MODE == 1 && g.Y) a *= op_act_prime(g.Y[(size_t)gm * g.ldy + gk], g.act);
+        }
+      }
+      As[k][m] = a;
+    }
+    for (int idx = tid; idx < GK * GT; idx += GTHREADS) {
+      int k, n;
+      if (MODE == 0) { n = idx / GK; k = idx % GK; } else { k = idx / GT; n = idx % GT; }
+      const int gn = n0 + n, gk = k0 + k;
+      float b = 0.f;
+      if (gn < g.N && gk < g.K) b = (MODE == 0) ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn];
+      Bs[k][n] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][tm]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tn]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + tm + i, gn = n0 + tn + j;
+      if (gm < g.M && gn < g.N) {
+        float v = acc[i][j];
+        if (MODE == 0) v = op_act(v + (g.bias ? g.bias[gn] : 0.f), g.act);
+        g.C[(size_t)gm * g.ldc + gn] = v;
+      }
+    }
+}
+
+// db[n] = sum_rows dY[r][n] * act'(Y[r][n])
+__global__ void colsum_kernel(const float* dY, int ldd, const float* Y, int ldy, int act, int rows, int N, float* out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    float d = dY[(size_t)r * ldd + n];
+    if (Y) d *= op_act_prime(Y[(size_t)r * ldy + n], act);
+    s += d;
+  }
+  out[n] = s;
+}
+
+// X[r] = [obs[r] | act[r]]  (q_function.py:30 torch.cat([observation, action], -1))
+__global__ void concat_kernel(const float* obs, int O, const float* act, int lda, int A, int rows, float* X) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = O + A;
+  if (idx >= rows * W) return;
+  const int r = idx / W, c = idx % W;
+  X[idx] = c < O ? obs[(size_t)r * O + c] : act[(size_t)r * lda + (c - O)];
+}
+
+// TD3 target action (td3.py:326-332): a' = clamp(pi_targ(s') + clamp(sigma * eps, -c, c), -limit, limit); DDPG: a' = pi_targ(s')
+__global__ void target_action_kernel(float* a, const float* eps, int n, float sigma, float clipv, float limit, int noisy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!noisy) return;
+  float e = sigma * eps[i];
+  e = fminf(fmaxf(e, -clipv), clipv);
+  a[i] = fminf(fmaxf(a[i] + e, -limit), limit);
+}
+
+// y = r + gamma * (1 - d) * min(q1t, q2t)   (td3.py:337-339; ddpg.py:280: single target Q)
+__global__ void td_target_kernel(const float* rew, const float* done, const float* q1t, const float* q2t, float gamma,
+                                 int n, float* y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float q = q2t ? fminf(q1t[i], q2t[i]) : q1t[i];
+  y[i] = rew[i] + gamma * (1.f - done[i]) * q;
+}
+
+// One CTA: loss = mean((q - y)^2), dq = 2 (q - y) / B   (F.mse_loss + backward);  or policy: loss = -mean(q), dq = -1/B
+__global__ void __launch_bounds__(1024) q_loss_kernel(const float* q, const float* y, int n, float* dq, float* loss_out,
+                                                      float* q_copy) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const float inv = 1.0f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float qi = q[i];
+    if (q_copy) q_copy[i] = qi;
+    if (y) {
+      const float d = qi - y[i];
+      acc += (double)d * (double)d;
+      dq[i] = (2.f * d) * inv;
+    } else {
+      acc -= (double)qi;
+      dq[i] = -inv;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *loss_out = (float)(t / (double)n);
+  }
+}
+
+// target <- rho * target + (1 - rho) * param   (utils.py:47-57: f32 tensors tensor(rho), tensor(1 - rho))
+__global__ void polyak_kernel(float* target, const float* param, float rho, float one_minus_rho, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) target[i] = rho * target[i] + one_minus_rho * param[i];
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+// ---------------------------------------------------------------------------------------------------------------
+struct NetBuf {
+  b200rl_mlp_desc d;
+  int64_t P = 0;
+  float* params = nullptr;
+  float *m = nullptr, *v = nullptr;  // Adam state (trainable nets only)
+  float* grad = nullptr;
+  int64_t step = 0;
+  int w_off[B200RL_MAX_LAYERS], b_off[B200RL_MAX_LAYERS];
+};
+
+struct b200rl_offpolicy {
+  b200rl_offpolicy_config cfg;
+  NetBuf net[6];  // 0 pi, 1 Q1, 2 Q2, 3 pi_targ, 4 Q1_targ, 5 Q2_targ
+  int O = 0, A = 0, maxw = 0;
+  // staged minibatches [S,B,*]
+  float *obs = nullptr, *act = nullptr, *rew = nullptr, *nobs = nullptr, *done = nullptr, *eps = nullptr;
+  // per-step workspace
+  float* acts[3][B200RL_MAX_LAYERS + 1];  // three activation stacks [B, width]: 0 scratch/target, 1 Q, 2 policy
+  float *x_cat = nullptr, *x_cat2 = nullptr, *qt1 = nullptr, *qt2 = nullptr, *y = nullptr, *dq = nullptr;
+  float *dbuf0 = nullptr, *dbuf1 = nullptr;  // gradient ping-pong [B, maxw]
+  // outputs
+  float *out_q1 = nullptr, *out_q2 = nullptr, *out_l1 = nullptr, *out_l2 = nullptr, *out_lp = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int oalloc(b200rl_offpolicy* h, T** p, size_t count) {
+  void* q = nullptr;
+  B200RL_CUDA(cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+  B200RL_CUDA(cudaMemset(q, 0, (count ? count : 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+template <int MODE>
+int gemm(const GemmArgs& g, cudaStream_t s) {
+  dim3 grid((g.N + GT - 1) / GT, (g.M + GT - 1) / GT);
+  gemm_kernel<MODE><<<grid, GTHREADS, 0, s>>>(g);
+  B200RL_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+// forward through one network: acts[0] = input [rows, n0] (ld = n0); acts[l+1] = layer outputs
+int net_forward(const NetBuf& nb, float* const* acts, int rows, cudaStream_t s) {
+  const int L = nb.d.n_layers;
+  for (int l = 0; l < L; ++l) {
+    GemmArgs g{};
+    g.A = acts[l]; g.lda = nb.d.sizes[l];
+    g.B = nb.params + nb.w_off[l]; g.ldb = nb.d.sizes[l];
+    g.C = acts[l + 1]; g.ldc = nb.d.sizes[l + 1];
+    g.bias = nb.params + nb.b_off[l];
+    g.act = (l == L - 1) ? nb.d.out_act : nb.d.hidden_act;
+    g.M = rows; g.N = nb.d.sizes[l + 1]; g.K = nb.d.sizes[l];
+    if (gemm<0>(g, s)) return 1;
+  }
+  return 0;
+}
+
+// backward: dOut = gradient w.r.t. the network OUTPUT (after the output activation) [rows, nL] with ld ld_dout.
+// want_param_grads: write nb.grad (flat).  dx_out (optional): gradient w.r.t. the input [rows, n0].
+int net_backward(b200rl_offpolicy* h, const NetBuf& nb, float* const* acts, const float* dOut, int ld_dout, int rows,
+                 bool want_param_grads, float* dx_out, cudaStream_t s) {
+  const int L = nb.d.n_layers;
+  const float* dY = dOut;
+  int ldd = ld_dout;
+  float* pp[2] = {h->dbuf0, h->dbuf1};
+  for (int l = L - 1; l >= 0; --l) {
+    const int nout = nb.d.sizes[l + 1], nin = nb.d.sizes[l];
+    const int act = (l == L - 1) ? nb.d.out_act : nb.d.hidden_act;
+    const float* Y = acts[l + 1];
+    if (want_param_grads) {
+      GemmArgs g{};  // dW[nout, nin] = (dY . act'(Y))^T [nout, rows] * X[rows, nin]
+      g.A = dY; g.lda = ldd; g.Y = Y; g.ldy = nout; g.act = act;
+      g.B = acts[l]; g.ldb = nin;
+      g.C = nb.grad + nb.w_off[l]; g.ldc = nin;
+      g.M = nout; g.N = nin; g.K = rows;
+      if (gemm<2>(g, s)) return 1;
+      colsum_kernel<<<(nout + 127) / 128, 128, 0, s>>>(dY, ldd, Y, nout, act, rows, nout, nb.grad + nb.b_off[l]);
+      B200RL_CUDA(cudaGetLastError());
+      count_launch(1);
+    }
+    if (l > 0 || dx_out) {
+      float* dst = (l == 0) ? dx_out : pp[l & 1];
+      GemmArgs g{};  // dX[rows, nin] = (dY . act'(Y))[rows, nout] * W[nout, nin]
+      g.A = dY; g.lda = ldd; g.Y = Y; g.ldy = nout; g.act = act;
+      g.B = nb.params + nb.w_off[l]; g.ldb = nin;
+      g.C = dst; g.ldc = nin;
+      g.M = rows; g.N = nin; g.K = nout;
+      if (gemm<1>(g, s)) return 1;
+      dY = dst;
+      ldd = nin;
+    }
+  }
+  return 0;
+}
+
+int adam_net(NetBuf& nb, double lr, double b1, double b2, double eps, cudaStream_t s) {
+  nb.step += 1;
+  return b200rl_adam_step(nb.params, nb.grad, nb.m, nb.v, nb.P, nb.step, lr, b1, b2, eps, nullptr, 0, 1.0, 0.0, nullptr,
+                          nullptr, nullptr, nullptr, s);
+}
+
+}  // namespace
+
+extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200rl_offpolicy** out) {
+  B200RL_REQUIRE(cfg && out, "offpolicy_create: NULL argument");
+  B200RL_REQUIRE(cfg->n_q == 1 || cfg->n_q == 2, "offpolicy_create: n_q must be 1 (DDPG) or 2 (TD3)");
+  B200RL_REQUIRE(cfg->max_minibatch >= 1 && cfg->max_minibatch <= 65536 && cfg->max_steps >= 1,
+                 "offpolicy_create: bad capacities");
+  const int64_t Pp = b200rl_mlp_param_count(&cfg->policy), Pq = b200rl_mlp_param_count(&cfg->q);
+  B200RL_REQUIRE(Pp > 0 && Pq > 0, "offpolicy_create: invalid MLP description");
+  const int O = cfg->policy.sizes[0], A = cfg->policy.sizes[cfg->policy.n_layers];
+  B200RL_REQUIRE(cfg->q.sizes[0] == O + A && cfg->q.sizes[cfg->q.n_layers] == 1,
+                 "offpolicy_create: Q network must map [obs %d + act %d] -> 1", O, A);
+  B200RL_REQUIRE(device_sm_count() > 0, "offpolicy_create: no CUDA device");
+  b200rl_offpolicy* h = new b200rl_offpolicy();
+  h->cfg = *cfg;
+  h->O = O;
+  h->A = A;
+  int rc = 0;
+  int maxw = O + A;
+  for (int i = 0; i < 6; ++i) {
+    NetBuf& nb = h->net[i];
+    nb.d = (i == 0 || i == 3) ? cfg->policy : cfg->q;
+    nb.P = (i == 0 || i == 3) ? Pp : Pq;
+    int off = 0;
+    for (int l = 0; l < nb.d.n_layers; ++l) {
+      nb.w_off[l] = off;
+      off += nb.d.sizes[l + 1] * nb.d.sizes[l];
+      nb.b_off[l] = off;
+      off += nb.d.sizes[l + 1];
+      maxw = nb.d.sizes[l + 1] > maxw ? nb.d.sizes[l + 1] : maxw;
+    }
+    if (cfg->n_q == 1 && (i == 2 || i == 5)) continue;
+    rc |= oalloc(h, &nb.params, (size_t)nb.P);
+    if (i < 3) {
+      rc |= oalloc(h, &nb.m, (size_t)nb.P);
+      rc |= oalloc(h, &nb.v, (size_t)nb.P);
+      rc |= oalloc(h, &nb.grad, (size_t)nb.P);
+    }
+  }
+  h->maxw = maxw;
+  const size_t B = (size_t)cfg->max_minibatch, S = (size_t)cfg->max_steps;
+  rc |= oalloc(h, &h->obs, S * B * O);
+  rc |= oalloc(h, &h->act, S * B * A);
+  rc |= oalloc(h, &h->rew, S * B);
+  rc |= oalloc(h, &h->nobs, S * B * O);
+  rc |= oalloc(h, &h->done, S * B);
+  rc |= oalloc(h, &h->eps, S * B * A);
+  for (int k = 0; k < 3; ++k)
+    for (int l = 0; l <= B200RL_MAX_LAYERS; ++l) rc |= oalloc(h, &h->acts[k][l], B * (size_t)maxw);
+  rc |= oalloc(h, &h->x_cat, B * (size_t)(O + A));
+  rc |= oalloc(h, &h->x_cat2, B * (size_t)(O + A));
+  rc |= oalloc(h, &h->qt1, B);
+  rc |= oalloc(h, &h->qt2, B);
+  rc |= oalloc(h, &h->y, B);
+  rc |= oalloc(h, &h->dq, B);
+  rc |= oalloc(h, &h->dbuf0, B * (size_t)maxw);
+  rc |= oalloc(h, &h->dbuf1, B * (size_t)maxw);
+  rc |= oalloc(h, &h->out_q1, S * B);
+  rc |= oalloc(h, &h->out_q2, S * B);
+  rc |= oalloc(h, &h->out_l1, S);
+  rc |= oalloc(h, &h->out_l2, S);
+  rc |= oalloc(h, &h->out_lp, S);
+  if (rc) {
+    b200rl_offpolicy_destroy(h);
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" void b200rl_offpolicy_destroy(b200rl_offpolicy* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+extern "C" int b200rl_offpolicy_set_params(b200rl_offpolicy* h, int which, const float* host_flat, int64_t n,
+                                           void* stream) {
+  B200RL_REQUIRE(h && host_flat && which >= 0 && which < 6 && h->net[which].params, "offpolicy_set_params: bad net");
+  B200RL_REQUIRE(n == h->net[which].P, "offpolicy_set_params: expects %lld floats", (long long)h->net[which].P);
+  B200RL_CUDA(cudaMemcpyAsync(h->net[which].params, host_flat, (size_t)n * 4, cudaMemcpyHostToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int b200rl_offpolicy_get_params(b200rl_offpolicy* h, int which, float* host_flat, int64_t n, void* stream) {
+  B200RL_REQUIRE(h && host_flat && which >= 0 && which < 6 && h->net[which].params, "offpolicy_get_params: bad net");
+  B200RL_REQUIRE(n == h->net[which].P, "offpolicy_get_params: expects %lld floats", (long long)h->net[which].P);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200RL_CUDA(cudaMemcpyAsync(host_flat, h->net[which].params, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int b200rl_offpolicy_set_adam(b200rl_offpolicy* h, int which, const float* exp_avg, const float* exp_avg_sq,
+                                         int64_t n, int64_t step, void* stream) {
+  B200RL_REQUIRE(h && which >= 0 && which < 3 && h->net[which].m, "offpolicy_set_adam: bad net");
+  NetBuf& nb = h->net[which];
+  B200RL_REQUIRE(n == nb.P && step >= 0, "offpolicy_set_adam: expects %lld floats", (long long)nb.P);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (exp_avg) B200RL_CUDA(cudaMemcpyAsync(nb.m, exp_avg, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  else B200RL_CUDA(cudaMemsetAsync(nb.m, 0, (size_t)n * 4, s));
+  if (exp_avg_sq) B200RL_CUDA(cudaMemcpyAsync(nb.v, exp_avg_sq, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  else B200RL_CUDA(cudaMemsetAsync(nb.v, 0, (size_t)n * 4, s));
+  nb.step = step;
+  return 0;
+}
+
+extern "C" int b200rl_offpolicy_get_adam(b200rl_offpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                         int64_t* step, void* stream) {
+  B200RL_REQUIRE(h && which >= 0 && which < 3 && h->net[which].m && exp_avg && exp_avg_sq && step,
+                 "offpolicy_get_adam: bad arguments");
+  NetBuf& nb = h->net[which];
+  B200RL_REQUIRE(n == nb.P, "offpolicy_get_adam: expects %lld floats", (long long)nb.P);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200RL_CUDA(cudaMemcpyAsync(exp_avg, nb.m, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(exp_avg_sq, nb.v, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  *step = nb.step;
+  return 0;
+}
+
+extern "C" int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S, int32_t B,
+                                      const float* obs, const float* act, const float* rew, const float* next_obs,
+                                      const float* done, const float* noise, float* q1_values, float* q2_values,
+                                      float* q1_losses, float* q2_losses, float* policy_losses,
+                                      int32_t* n_policy_updates, void* stream) {
+  B200RL_REQUIRE(h && hp && obs && act && rew && next_obs && done && q1_values && q1_losses && policy_losses &&
+                     n_policy_updates, "offpolicy_train: NULL argument");
+  B200RL_REQUIRE(S >= 0 && S <= h->cfg.max_steps && B >= 1 && B <= h->cfg.max_minibatch,
+                 "offpolicy_train: S=%d B=%d exceed the capacities", S, B);
+  const bool td3 = h->cfg.n_q == 2;
+  B200RL_REQUIRE(!td3 || (q2_values && q2_losses), "offpolicy_train: TD3 needs the Q2 outputs");
+  B200RL_REQUIRE(!hp->use_target_noise || noise, "offpolicy_train: target noise requested but no noise given");
+  B200RL_REQUIRE(hp->policy_delay >= 1, "offpolicy_train: policy_delay must be >= 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int O = h->O, A = h->A;
+  const size_t SB = (size_t)S * B;
+  *n_policy_updates = 0;
+  if (S == 0) return 0;
+  // one host -> device upload of every minibatch of this train() call
+  B200RL_CUDA(cudaMemcpyAsync(h->obs, obs, SB * O * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->act, act, SB * A * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->rew, rew, SB * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->nobs, next_obs, SB * O * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->done, done, SB * 4, cudaMemcpyHostToDevice, s));
+  if (hp->use_target_noise) B200RL_CUDA(cudaMemcpyAsync(h->eps, noise, SB * A * 4, cudaMemcpyHostToDevice, s));
+
+  NetBuf &pi = h->net[0], &q1 = h->net[1], &q2 = h->net[2], &pit = h->net[3], &q1t = h->net[4], &q2t = h->net[5];
+  const int Lq = q1.d.n_layers, Lp = pi.d.n_layers;
+  const int ew = 256;
+  int n_pol = 0;
+  for (int st = 0; st < S; ++st) {
+    const float* s_obs = h->obs + (size_t)st * B * O;
+    const float* s_act = h->act + (size_t)st * B * A;
+    const float* s_rew = h->rew + (size_t)st * B;
+    const float* s_nobs = h->nobs + (size_t)st * B * O;
+    const float* s_done = h->done + (size_t)st * B;
+    // ---- targets (td3.py:325-341 / ddpg.py:275-282) ----
+    float* ta[B200RL_MAX_LAYERS + 1];
+    ta[0] = const_cast<float*>(s_nobs);
+    for (int l = 1; l <= Lp; ++l) ta[l] = h->acts[0][l];
+    if (net_forward(pit, ta, B, s)) return 1;
+    if (hp->use_target_noise) {
+      target_action_kernel<<<(B * A + ew - 1) / ew, ew, 0, s>>>(ta[Lp], h->eps + (size_t)st * B * A, B * A,
+                                                                (float)hp->target_noise_scale,
+                                                                (float)hp->target_noise_clip, (float)hp->action_limit, 1);
+      B200RL_CUDA(cudaGetLastError());
+      count_launch(1);
+    }
+    concat_kernel<<<(B * (O + A) + ew - 1) / ew, ew, 0, s>>>(s_nobs, O, ta[Lp], A, A, B, h->x_cat2);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+    float* tq[B200RL_MAX_LAYERS + 1];
+    tq[0] = h->x_cat2;
+    for (int l = 1; l < Lq; ++l) tq[l] = h->acts[0][l];
+    tq[Lq] = h->qt1;
+    if (net_forward(q1t, tq, B, s)) return 1;
+    if (td3) {
+      tq[Lq] = h->qt2;
+      if (net_forward(q2t, tq, B, s)) return 1;
+    }
+    td_target_kernel<<<(B + ew - 1) / ew, ew, 0, s>>>(s_rew, s_done, h->qt1, td3 ? h->qt2 : nullptr, (float)hp->gamma, B,
+                                                      h->y);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+    // ---- Q steps (td3.py:343-358): forward on [s | a], MSE, backward, Adam.  The forward values are also the logged
+    //      Q-values (td3.py:231-235: same parameters, same inputs) ----
+    concat_kernel<<<(B * (O + A) + ew - 1) / ew, ew, 0, s>>>(s_obs, O, s_act, A, A, B, h->x_cat);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+    for (int qi = 0; qi < (td3 ? 2 : 1); ++qi) {
+      NetBuf& qn = qi == 0 ? q1 : q2;
+      float* qa[B200RL_MAX_LAYERS + 1];
+      qa[0] = h->x_cat;
+      for (int l = 1; l <= Lq; ++l) qa[l] = h->acts[1][l];
+      if (net_forward(qn, qa, B, s)) return 1;
+      q_loss_kernel<<<1, 1024, 0, s>>>(qa[Lq], h->y, B, h->dq, (qi == 0 ? h->out_l1 : h->out_l2) + st,
+                                       (qi == 0 ? h->out_q1 : h->out_q2) + (size_t)st * B);
+      B200RL_CUDA(cudaGetLastError());
+      count_launch(1);
+      if (net_backward(h, qn, qa, h->dq, 1, B, true, nullptr, s)) return 1;
+      if (adam_net(qn, qi == 0 ? hp->q1_lr : hp->q2_lr, hp->q_beta1, hp->q_beta2, hp->q_eps, s)) return 1;
+    }
+    // ---- delayed policy step + polyak (td3.py:244-263, 301-323; ddpg: every step) ----
+    if (st % hp->policy_delay == 0) {
+      float* pa[B200RL_MAX_LAYERS + 1];
+      pa[0] = const_cast<float*>(s_obs);
+      for (int l = 1; l <= Lp; ++l) pa[l] = h->acts[2][l];
+      if (net_forward(pi, pa, B, s)) return 1;
+      concat_kernel<<<(B * (O + A) + ew - 1) / ew, ew, 0, s>>>(s_obs, O, pa[Lp], A, A, B, h->x_cat2);
+      B200RL_CUDA(cudaGetLastError());
+      count_launch(1);
+      float* qa[B200RL_MAX_LAYERS + 1];
+      qa[0] = h->x_cat2;
+      for (int l = 1; l <= Lq; ++l) qa[l] = h->acts[1][l];
+      if (net_forward(q1, qa, B, s)) return 1;  // Q1 with its freshly updated parameters (td3.py:309)
+      q_loss_kernel<<<1, 1024, 0, s>>>(qa[Lq], nullptr, B, h->dq, h->out_lp + n_pol, nullptr);
+      B200RL_CUDA(cudaGetLastError());
+      count_launch(1);
+      // gradient w.r.t. Q1's input; its action columns are the gradient w.r.t. pi(s) (Q parameters frozen)
+      if (net_backward(h, q1, qa, h->dq, 1, B, false, h->x_cat, s)) return 1;
+      if (net_backward(h, pi, pa, h->x_cat + O, O + A, B, true, nullptr, s)) return 1;
+      if (adam_net(pi, hp->policy_lr, hp->policy_beta1, hp->policy_beta2, hp->policy_eps, s)) return 1;
+      const float rho = (float)hp->polyak_rho, omr = (float)(1.0 - hp->polyak_rho);
+      for (int k = 0; k < (td3 ? 3 : 2); ++k) {
+        NetBuf& src = h->net[k];
+        NetBuf& dst = h->net[3 + k];
+        polyak_kernel<<<(int)((src.P + ew - 1) / ew), ew, 0, s>>>(dst.params, src.params, rho, omr, (int)src.P);
+        B200RL_CUDA(cudaGetLastError());
+        count_launch(1);
+      }
+      ++n_pol;
+    }
+  }
+  // one device -> host read of everything train() logs
+  B200RL_CUDA(cudaMemcpyAsync(q1_values, h->out_q1, SB * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaMemcpyAsync(q1_losses, h->out_l1, (size_t)S * 4, cudaMemcpyDeviceToHost, s));
+  if (td3) {
+    B200RL_CUDA(cudaMemcpyAsync(q2_values, h->out_q2, SB * 4, cudaMemcpyDeviceToHost, s));
+    B200RL_CUDA(cudaMemcpyAsync(q2_losses, h->out_l2, (size_t)S * 4, cudaMemcpyDeviceToHost, s));
+  }
+  if (n_pol > 0) B200RL_CUDA(cudaMemcpyAsync(policy_losses, h->out_lp, (size_t)n_pol * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  *n_policy_updates = n_pol;
+  return 0;
+}

@@ -214,3 +214,81 @@ class OnPolicyEngine:
         p, n, d = C.c_void_p(), C.c_int64(), C.c_int32()
         check(self.lib.b200rl_onpolicy_device_view(self.h, name.encode(), C.byref(p), C.byref(n), C.byref(d)), "device_view")
         return torch.as_tensor(_CudaArray(p.value, int(n.value), "<f8" if d.value == 1 else "<f4"), device="cuda")
+
+
+class OffPolicyEngine:
+    """Device-resident state of one DDPG / TD3 learner (C ABI: b200rl_offpolicy_*)."""
+
+    NETS = {"policy": 0, "q1": 1, "q2": 2, "target_policy": 3, "target_q1": 4, "target_q2": 5}
+
+    def __init__(self, policy_sizes, q_sizes, n_q: int, max_minibatch: int, max_steps: int, policy_acts=("relu", "tanh"),
+                 q_acts=("relu", "identity")):
+        from ._lib import OffPolicyConfig
+        self.lib = _lib.load()
+        current_stream_handle()
+        cfg = OffPolicyConfig()
+        cfg.policy = MlpDesc.make(policy_sizes, *policy_acts)
+        cfg.q = MlpDesc.make(q_sizes, *q_acts)
+        cfg.n_q, cfg.max_minibatch, cfg.max_steps = int(n_q), int(max_minibatch), int(max_steps)
+        self.n_q, self.max_minibatch, self.max_steps = int(n_q), int(max_minibatch), int(max_steps)
+        self.policy_sizes, self.q_sizes = list(policy_sizes), list(q_sizes)
+        self.policy_acts, self.q_acts = tuple(policy_acts), tuple(q_acts)
+        self.n_policy = int(self.lib.b200rl_mlp_param_count(cfg.policy))
+        self.n_qp = int(self.lib.b200rl_mlp_param_count(cfg.q))
+        h = C.c_void_p()
+        check(self.lib.b200rl_offpolicy_create(C.byref(cfg), C.byref(h)), "offpolicy_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200rl_offpolicy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _n(self, which):
+        return self.n_policy if which in (0, 3) else self.n_qp
+
+    def set_params(self, which: int, flat: np.ndarray):
+        a = _c(flat, np.float32)
+        check(self.lib.b200rl_offpolicy_set_params(self.h, which, _ptr(a), a.size, current_stream_handle()), "set_params")
+        import torch
+        torch.cuda.current_stream().synchronize()  # `a` may be a temporary
+
+    def get_params(self, which: int) -> np.ndarray:
+        out = np.empty(self._n(which), dtype=np.float32)
+        check(self.lib.b200rl_offpolicy_get_params(self.h, which, _ptr(out), out.size, current_stream_handle()), "get_params")
+        return out
+
+    def set_adam(self, which: int, m, v, step: int):
+        m = None if m is None else _c(m, np.float32)
+        v = None if v is None else _c(v, np.float32)
+        check(self.lib.b200rl_offpolicy_set_adam(self.h, which, _ptr(m), _ptr(v), self._n(which), int(step),
+                                                 current_stream_handle()), "set_adam")
+        import torch
+        torch.cuda.current_stream().synchronize()
+
+    def get_adam(self, which: int):
+        m, v = np.empty(self._n(which), np.float32), np.empty(self._n(which), np.float32)
+        step = C.c_int64()
+        check(self.lib.b200rl_offpolicy_get_adam(self.h, which, _ptr(m), _ptr(v), m.size, C.byref(step),
+                                                 current_stream_handle()), "get_adam")
+        return m, v, int(step.value)
+
+    def train(self, hp, obs, act, rew, next_obs, done, noise=None):
+        """obs/next_obs [S,B,O], act [S,B,A], rew/done [S,B], noise [S,B,A] or None -> dict of logged quantities."""
+        obs, act, next_obs = _c(obs, np.float32), _c(act, np.float32), _c(next_obs, np.float32)
+        rew, done = _c(rew, np.float32), _c(done, np.float32)
+        noise = None if noise is None else _c(noise, np.float32)
+        S, B = obs.shape[0], obs.shape[1]
+        q1v, q2v = np.zeros((S, B), np.float32), np.zeros((S, B), np.float32)
+        l1, l2, lp = np.zeros(S, np.float32), np.zeros(S, np.float32), np.zeros(max(S, 1), np.float32)
+        npol = C.c_int32()
+        check(self.lib.b200rl_offpolicy_train(self.h, C.byref(hp), S, B, _ptr(obs), _ptr(act), _ptr(rew), _ptr(next_obs),
+                                              _ptr(done), _ptr(noise), _ptr(q1v), _ptr(q2v), _ptr(l1), _ptr(l2), _ptr(lp),
+                                              C.byref(npol), current_stream_handle()), "offpolicy_train")
+        return dict(q1_values=q1v, q2_values=q2v, q1_losses=l1, q2_losses=l2, policy_losses=lp[:npol.value])
