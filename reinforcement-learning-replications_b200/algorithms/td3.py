@@ -23,14 +23,15 @@ logger = logging.getLogger(__name__)
 class _OffPolicyBase:
     n_q = 1
 
+    def _trainable(self):
+        return [self.policy] + ([self.q_function_1, self.q_function_2] if self.n_q == 2 else [self.q_function])
+
     def _nets(self):
-        qs = [self.q_function_1, self.q_function_2] if self.n_q == 2 else [self.q_function]
         tq = [self.target_q_function_1, self.target_q_function_2] if self.n_q == 2 else [self.target_q_function]
-        return [self.policy] + qs, [self.target_policy] + tq
+        return self._trainable(), [self.target_policy] + tq
 
     def _make_targets(self):
-        trainable, _ = self._nets()
-        targets = [copy.deepcopy(m) for m in trainable]
+        targets = [copy.deepcopy(m) for m in self._trainable()]
         for t in targets:
             for p in t.network.parameters():
                 p.requires_grad = False
