@@ -12,32 +12,37 @@
 //   thread: 8 consecutive items sequentially (exactly the reference's float64 recurrence inside a thread),
 //   warp:   suffix scan of the 32 thread aggregates with shuffles,
 //   CTA:    8 warp aggregates through shared memory,
-//   grid:   single-pass decoupled look-back over tile descriptors (tiles take tickets from the end of the array, so a
-//           tile only ever waits for tiles that already started; a tile that contains an episode end has a == 0 and
-//           cuts the chain).
+//   grid:   single-pass decoupled look-back over tile descriptors.  The kernel is persistent: grid = resident CTAs,
+//           CTA c walks tiles T-1-c, T-1-c-G, ... from the END of the array, so the tile it waits on always belongs to
+//           a running CTA; a tile that contains an episode end has a == 0 and cuts the chain.  A producer warp
+//           prefetches the next tile (cp.async) and finds its episode range while the scan warps work.
 // HBM traffic = algorithmic traffic: read r (4 or 8 B) + v (4 B), write adv (4 B) + ret (4 B) per transition.
 // All carries are float64 (the reference scans in float64, utils.py:28); outputs are cast to float32 like ppo.py:151,160.
 #include "common.cuh"
 
 namespace b200rl {
 
-constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_CONSUMERS = 256;                 // 8 scan warps
+constexpr int SCAN_THREADS = SCAN_CONSUMERS + 32;   // + 1 producer warp (cp.async prefetch + episode search)
 constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 transitions per CTA
+constexpr int SCAN_TILE = SCAN_CONSUMERS * SCAN_ITEMS;  // 2048 transitions per tile
 
-struct __align__(16) ScanTileState {
-  double a_ret, b_ret, a_adv, b_adv;  // tile aggregate, valid once status >= 1
-  double y_ret, y_adv;                // recurrence values at the tile's FIRST element, valid once status == 2
-  int status;
-  int pad[3];
+// Look-back records.  Each tile owns 8 x 16-byte records {value, tag}; a record is valid iff tag == launch tag.
+// Value and tag travel in ONE 16-byte transaction, so no fence / release-acquire pair is needed to publish or to
+// consume them (the trick CUB's decoupled look-back uses for its packed tile descriptors):
+//   0 a_ret  1 b_ret  2 a_adv  3 b_adv   tile aggregate
+//   4 y_ret  5 y_adv                      recurrence values at the tile's FIRST element ("inclusive")
+struct __align__(16) ScanRec {
+  double val, tag;
 };
-static_assert(sizeof(ScanTileState) == 64, "tile state is one 64-byte record");
+constexpr int SCAN_RECS = 8;
+constexpr int SCAN_MAXE = 48;  // episodes per tile staged in shared memory (more: global-memory path)
 
 // Workspace header.  The workspace is zeroed ONCE (at allocation); after that every launch cleans up after itself:
-// tile status words carry the launch epoch (a stale word from an earlier launch reads as "not ready"), and the last
-// CTA to finish resets the ticket / done counters and bumps the epoch.  => one kernel launch per scan, no memset.
+// look-back records carry the launch epoch as their tag (a stale record from an earlier launch reads as "not ready"), and the last
+// CTA to finish resets the done counter and bumps the epoch.  => one kernel launch per scan, no memset.
 struct ScanHeader {
-  int ticket;
+  int reserved0;
   int done;
   int epoch;
   int error;
@@ -63,52 +68,51 @@ struct ScanArgs {
   float* adv;
   float* ret;
   ScanHeader* hdr;
-  ScanTileState* tiles;
+  ScanRec* recs;
   double2* partial;
   double* stats;
   int num_tiles;
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
+// one pipeline slot: a tile's rewards and values (+ the first value of the next tile) and its episode range
 template <typename RewT>
-__device__ __forceinline__ void load_rewards(const RewT* src, long long i0, bool full, long long n, double (&r)[SCAN_ITEMS]);
+struct __align__(16) TileBuf {
+  RewT r[SCAN_TILE];
+  float v[SCAN_TILE + 4];
+  long long e0, e1;
+  long long soff[SCAN_MAXE + 2];  // off[e0 .. e1 + 1] when staged
+  float slv[SCAN_MAXE];           // last_values[e0 .. e1]
+  int sdone[SCAN_MAXE];           // done[e0 .. e1]
+  int staged, pad;
+};
 
-template <>
-__device__ __forceinline__ void load_rewards<float>(const float* src, long long i0, bool full, long long n,
-                                                    double (&r)[SCAN_ITEMS]) {
-  if (full) {
-    const float4 x0 = __ldg(reinterpret_cast<const float4*>(src + i0));
-    const float4 x1 = __ldg(reinterpret_cast<const float4*>(src + i0 + 4));
-    r[0] = x0.x; r[1] = x0.y; r[2] = x0.z; r[3] = x0.w;
-    r[4] = x1.x; r[5] = x1.y; r[6] = x1.z; r[7] = x1.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) r[j] = (i0 + j < n) ? (double)src[i0 + j] : 0.0;
-  }
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ld_rec(const ScanRec* p, double& v, double& t) {
+  asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "l"(p) : "memory");
 }
-template <>
-__device__ __forceinline__ void load_rewards<double>(const double* src, long long i0, bool full, long long n,
-                                                     double (&r)[SCAN_ITEMS]) {
-  if (full) {
-#pragma unroll
-    for (int q = 0; q < SCAN_ITEMS / 2; ++q) {
-      const double2 x = __ldg(reinterpret_cast<const double2*>(src + i0 + 2 * q));
-      r[2 * q] = x.x;
-      r[2 * q + 1] = x.y;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) r[j] = (i0 + j < n) ? src[i0 + j] : 0.0;
-  }
+__device__ __forceinline__ void st_rec(ScanRec* p, double v, double t) {
+  asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(t) : "memory");
 }
+__device__ __forceinline__ void sbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool sbar_wait(uint32_t bar, uint32_t parity) {  // bounded: false = protocol failure
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void scan_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SCAN_CONSUMERS) : "memory"); }
 
 // suffix scan of per-thread aggregates inside a warp; returns the EXCLUSIVE suffix (composition of lanes > lane)
 // and leaves the inclusive aggregate of the whole warp in lane 0's `incl`.
@@ -133,7 +137,6 @@ __device__ __forceinline__ Aff warp_suffix_exclusive(Aff& incl, int lane) {
 }
 
 // Warp-cooperative 32-ary search: max e in [0, n_ep) with off[e] <= target (requires off[0] <= target < off[n_ep]).
-// ~log32(n_ep) rounds of one coalesced probe per lane instead of log2(n_ep) dependent loads per thread.
 __device__ __forceinline__ long long warp_find_episode(const long long* __restrict__ off, long long n_ep,
                                                        long long target, int lane) {
   long long lo = 0, hi = n_ep;  // invariant: off[lo] <= target < off[hi]
@@ -148,240 +151,351 @@ __device__ __forceinline__ long long warp_find_episode(const long long* __restri
   return lo;
 }
 
+// Persistent kernel: CTA c owns tiles T-1-c, T-1-c-G, ... (from the END of the array; G = gridDim.x <= resident
+// CTAs, so the tile a CTA waits on always belongs to a CTA that is running).  Warp 8 prefetches the next tile's
+// rewards / values with cp.async and finds its episode range while warps 0..7 scan the current tile.
 template <typename RewT>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) gae_scan_kernel(const ScanArgs p) {
-  __shared__ int s_tile, s_epoch, s_last;
-  __shared__ long long s_e0, s_e1;
-  __shared__ Aff s_wret[SCAN_THREADS / 32], s_wadv[SCAN_THREADS / 32];
+__global__ void __launch_bounds__(SCAN_THREADS, 3) gae_scan_kernel(const ScanArgs p) {
+  extern __shared__ __align__(16) unsigned char scan_smem[];
+  TileBuf<RewT>* buf = reinterpret_cast<TileBuf<RewT>*>(scan_smem);
+  __shared__ __align__(8) unsigned long long bars[4];  // full[0], full[1], empty[0], empty[1]
+  __shared__ int s_epoch, s_last;
+  __shared__ Aff s_wret[SCAN_CONSUMERS / 32], s_wadv[SCAN_CONSUMERS / 32];
+  __shared__ Aff s_xret[SCAN_CONSUMERS / 32], s_xadv[SCAN_CONSUMERS / 32];  // composition of the warps AFTER w
   __shared__ double s_carry[2];
-  __shared__ double s_red[2][SCAN_THREADS / 32];
+  __shared__ double s_red[2][SCAN_CONSUMERS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, c = blockIdx.x, T = p.num_tiles;
+  const long long n = p.n;
+  const int n_mine = (T - 1 - c) / G + 1;  // host guarantees G <= T
   if (tid == 0) {
     s_epoch = *reinterpret_cast<volatile int*>(&p.hdr->epoch);  // constant for the whole launch
-    s_tile = p.num_tiles - 1 - atomicAdd(&p.hdr->ticket, 1);
-  }
-  __syncthreads();
-  const int tile = s_tile;
-  const int st_agg = s_epoch * 4 + 1, st_incl = s_epoch * 4 + 2;  // status words of THIS launch
-  const long long n = p.n;
-  const long long i0 = (long long)tile * SCAN_TILE + (long long)tid * SCAN_ITEMS;
-  const bool full = (i0 + SCAN_ITEMS <= n);
-
-  // ---- loads first (vectorised when the thread's 8 items are all in range): their DRAM latency overlaps the
-  //      episode search below ----
-  double r[SCAN_ITEMS];
-  float v[SCAN_ITEMS + 1];
-  load_rewards<RewT>(static_cast<const RewT*>(p.rew), i0, full, n, r);
-  if (full) {
-    const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.values + i0));
-    const float4 x1 = __ldg(reinterpret_cast<const float4*>(p.values + i0 + 4));
-    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-    v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (i0 + j < n) ? p.values[i0 + j] : 0.f;
-  }
-  v[SCAN_ITEMS] = (i0 + SCAN_ITEMS < n) ? __ldg(p.values + i0 + SCAN_ITEMS) : 0.f;
-
-  // ---- episodes that overlap this tile: found once per CTA, cooperatively by warp 0 ----
-  if (warp == 0) {
-    const long long t0 = (long long)tile * SCAN_TILE;
-    const long long t1 = (t0 + SCAN_TILE - 1 < n - 1) ? t0 + SCAN_TILE - 1 : n - 1;
-    const long long e0 = warp_find_episode(p.off, p.n_ep, t0, lane);
-    const long long e1 = warp_find_episode(p.off, p.n_ep, t1, lane);
-    if (lane == 0) {
-      s_e0 = e0;
-      s_e1 = e1;
-    }
+    sbar_init(sm_addr(&bars[0]), 32);
+    sbar_init(sm_addr(&bars[1]), 32);
+    sbar_init(sm_addr(&bars[2]), 1);
+    sbar_init(sm_addr(&bars[3]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // ---- which episode does item i0 belong to?  e = max{e : off[e] <= i0} ----
-  long long e = 0, next_off = 0;
-  if (i0 < n) {
-    long long lo = s_e0, hi = s_e1 + 1;  // only the episodes that overlap this tile
-    while (hi - lo > 1) {
-      const long long mid = (lo + hi) >> 1;
-      if (__ldg(p.off + mid) <= i0) lo = mid; else hi = mid;
-    }
-    e = lo;
-    next_off = __ldg(p.off + e + 1);
-  }
-
-  // ---- per-item (a,b) of both recurrences; a is gamma / gamma*lambda, or 0 on an episode's last step ----
-  double b_ret[SCAN_ITEMS], b_adv[SCAN_ITEMS];
-  unsigned cut = 0;  // bit j set: a_j == 0 (episode end, or out of range)
-#pragma unroll
-  for (int j = 0; j < SCAN_ITEMS; ++j) {
-    const long long i = i0 + j;
-    if (i < n) {
-      while (i >= next_off) {
-        ++e;
-        next_off = __ldg(p.off + e + 1);
-      }
-      const bool last = (i == next_off - 1);
-      float vnext = v[j + 1];
-      double boot = 0.0;
-      if (last) {
-        const float vl = __ldg(p.last_values + e);
-        vnext = vl;                                            // utils.py:41: delta_{L-1} uses V(last_obs) even when done
-        if (!__ldg(p.done + e)) boot = p.gamma * (double)vl;   // utils.py:81-85 + ppo.py:149: ret_{L-1} = r + gamma*R_L
-        cut |= 1u << j;
-      }
-      // utils.py:41: rewards[:-1] (f64) + gamma*values[1:] (evaluated in float32) - values[:-1]
-      const double delta = (r[j] + (double)__fmul_rn(p.gamma_f, vnext)) - (double)v[j];
-      b_ret[j] = r[j] + boot;
-      b_adv[j] = delta;
-    } else {
-      cut |= 1u << j;
-      b_ret[j] = 0.0;
-      b_adv[j] = 0.0;
-    }
-  }
-
-  // ---- thread aggregate: compose items 7..0 ----
-  Aff tr{1.0, 0.0}, ta{1.0, 0.0};
-#pragma unroll
-  for (int j = SCAN_ITEMS - 1; j >= 0; --j) {
-    const bool c = (cut >> j) & 1u;
-    const double ar = c ? 0.0 : p.gamma, aa = c ? 0.0 : p.gl;
-    tr.b = b_ret[j] + ar * tr.b;
-    tr.a = ar * tr.a;
-    ta.b = b_adv[j] + aa * ta.b;
-    ta.a = aa * ta.a;
-  }
-
-  // ---- warp + CTA suffix scans ----
-  const Aff ex_r = warp_suffix_exclusive(tr, lane);
-  const Aff ex_a = warp_suffix_exclusive(ta, lane);
-  if (lane == 0) {
-    s_wret[warp] = tr;
-    s_wadv[warp] = ta;
-  }
-  __syncthreads();
-
-  // ---- thread 0: publish the tile aggregate, look back over later tiles for the carry-in, publish inclusive ----
-  if (tid == 0) {
-    Aff agg_r{1.0, 0.0}, agg_a{1.0, 0.0};
-    for (int w = SCAN_THREADS / 32 - 1; w >= 0; --w) {
-      agg_r = compose(s_wret[w], agg_r);
-      agg_a = compose(s_wadv[w], agg_a);
-    }
-    ScanTileState* me = p.tiles + tile;
-    me->a_ret = agg_r.a; me->b_ret = agg_r.b; me->a_adv = agg_a.a; me->b_adv = agg_a.b;
-    st_release(&me->status, st_agg);
-
-    Aff acc_r{1.0, 0.0}, acc_a{1.0, 0.0};
-    for (int j = tile + 1; j < p.num_tiles; ++j) {
-      if (acc_r.a == 0.0 && acc_a.a == 0.0) break;  // an episode end in between: nothing further matters
-      const ScanTileState* t = p.tiles + j;
-      int st = 0;
-      long long spins = 0;
-      while ((st = ld_acquire(&t->status)) != st_agg && st != st_incl) {
-        if (++spins > (1ll << 22)) break;  // bounded: never hang the GPU; flag and bail out
-        __nanosleep(32);
-      }
-      if (st != st_agg && st != st_incl) {
+  if (warp == SCAN_CONSUMERS / 32) {
+    // ================================ producer warp ================================
+    const RewT* rew = static_cast<const RewT*>(p.rew);
+    for (int k = 0; k < n_mine; ++k) {
+      const int tile = T - 1 - c - k * G, b = k & 1;
+      if (k >= 2 && !sbar_wait(sm_addr(&bars[2 + b]), ((k >> 1) - 1) & 1)) {
         p.hdr->error = 1;
-        break;
+        return;
       }
-      if (st == st_incl) {
-        acc_r = Aff{0.0, acc_r.b + acc_r.a * __ldcg(&t->y_ret)};
-        acc_a = Aff{0.0, acc_a.b + acc_a.a * __ldcg(&t->y_adv)};
-        break;
+      const long long t0 = (long long)tile * SCAN_TILE;
+      const int cnt = (int)((n - t0) < SCAN_TILE ? (n - t0) : SCAN_TILE);
+      const int cntv = cnt + ((t0 + cnt < n) ? 1 : 0);  // + first value of the next tile (v_{i+1} of the last item)
+      // whole 16-byte chunks with cp.async (tile starts are 16-byte aligned), the ragged tail with plain copies
+      const int r16 = (int)((size_t)cnt * sizeof(RewT) / 16), v16 = cntv * 4 / 16;
+      const char* gr = reinterpret_cast<const char*>(rew + t0);
+      const char* gv = reinterpret_cast<const char*>(p.values + t0);
+      const uint32_t sr = sm_addr(buf[b].r), sv = sm_addr(buf[b].v);
+      for (int i = lane; i < r16; i += 32) scan_cp_async16(sr + 16 * i, gr + 16 * (size_t)i);
+      for (int i = lane; i < v16; i += 32) scan_cp_async16(sv + 16 * i, gv + 16 * (size_t)i);
+      for (int i = r16 * (int)(16 / sizeof(RewT)) + lane; i < cnt; i += 32) buf[b].r[i] = rew[t0 + i];
+      for (int i = v16 * 4 + lane; i < cntv; i += 32) buf[b].v[i] = p.values[t0 + i];
+      // episodes that overlap this tile (warp-cooperative; overlaps the copies in flight)
+      const long long e0 = warp_find_episode(p.off, p.n_ep, t0, lane);
+      const long long e1 = warp_find_episode(p.off, p.n_ep, t0 + cnt - 1, lane);
+      const int ne = (int)(e1 - e0 + 1);
+      if (lane == 0) {
+        buf[b].e0 = e0;
+        buf[b].e1 = e1;
+        buf[b].staged = ne <= SCAN_MAXE ? 1 : 0;
       }
-      acc_r = compose(acc_r, Aff{__ldcg(&t->a_ret), __ldcg(&t->b_ret)});
-      acc_a = compose(acc_a, Aff{__ldcg(&t->a_adv), __ldcg(&t->b_adv)});
+      if (ne <= SCAN_MAXE) {  // the scan warps then never touch global memory for episode boundaries
+        for (int i = lane; i <= ne; i += 32) buf[b].soff[i] = __ldg(p.off + e0 + i);
+        for (int i = lane; i < ne; i += 32) {
+          buf[b].slv[i] = __ldg(p.last_values + e0 + i);
+          buf[b].sdone[i] = (int)__ldg(p.done + e0 + i);
+        }
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      sbar_arrive(sm_addr(&bars[b]));  // 32 arrivals (release): this lane's copies and stores are visible
     }
-    // beyond the end of the array the recurrence value is 0
-    s_carry[0] = acc_r.b;
-    s_carry[1] = acc_a.b;
-    me->y_ret = agg_r.b + agg_r.a * acc_r.b;
-    me->y_adv = agg_a.b + agg_a.a * acc_a.b;
-    st_release(&me->status, st_incl);
+    return;
   }
-  __syncthreads();
 
-  // ---- carry-in of this thread = (lanes after me in my warp) o (warps after mine) applied to the tile carry ----
-  Aff xw_r{1.0, 0.0}, xw_a{1.0, 0.0};
-  for (int w = SCAN_THREADS / 32 - 1; w > warp; --w) {
-    xw_r = compose(s_wret[w], xw_r);
-    xw_a = compose(s_wadv[w], xw_a);
-  }
-  const Aff x_r = compose(ex_r, xw_r), x_a = compose(ex_a, xw_a);
-  double y_r = x_r.b + x_r.a * s_carry[0];
-  double y_a = x_a.b + x_a.a * s_carry[1];
-
-  // ---- final sequential recurrence over the thread's items (the reference's own float64 loop) ----
-  float o_ret[SCAN_ITEMS], o_adv[SCAN_ITEMS];
-  double s1 = 0.0, s2 = 0.0;
+  // ================================== scan warps ====================================
+  const double tag = (double)(s_epoch + 1);  // records of THIS launch carry this tag (0 = never written)
+  for (int k = 0; k < n_mine; ++k) {
+    const int tile = T - 1 - c - k * G, b = k & 1;
+    if (!sbar_wait(sm_addr(&bars[b]), (k >> 1) & 1)) {
+      if (tid == 0) p.hdr->error = 1;
+      break;
+    }
+    const long long t0 = (long long)tile * SCAN_TILE;
+    const long long i0 = t0 + (long long)tid * SCAN_ITEMS;
+    const TileBuf<RewT>* tb = &buf[b];
+    const long long te0 = tb->e0, te1 = tb->e1;
+    const bool staged = tb->staged != 0;
+    const bool fast = staged && (t0 + SCAN_TILE <= n);  // whole tile in range, episode data in shared memory
+    double r[SCAN_ITEMS];
+    float v[SCAN_ITEMS + 1];
+    double b_ret[SCAN_ITEMS], b_adv[SCAN_ITEMS];
+    unsigned cut = 0;  // bit j set: a_j == 0 (episode end, or out of range)
+    if (fast) {
+      // ---- hot path: vector shared loads, 32-bit tile-relative indices, no bounds checks ----
+      const int base = tid * SCAN_ITEMS;
+      if (sizeof(RewT) == 8) {
 #pragma unroll
-  for (int j = SCAN_ITEMS - 1; j >= 0; --j) {
-    const bool c = (cut >> j) & 1u;
-    y_r = b_ret[j] + (c ? 0.0 : p.gamma) * y_r;
-    y_a = b_adv[j] + (c ? 0.0 : p.gl) * y_a;
-    o_ret[j] = (float)y_r;
-    o_adv[j] = (float)y_a;
-    if (i0 + j < n) {
-      const double af = (double)o_adv[j];  // statistics of the float32 tensor, like normalize_tensor's input
-      s1 += af;
-      s2 += af * af;
+        for (int q = 0; q < SCAN_ITEMS / 2; ++q) {
+          const double2 x = *reinterpret_cast<const double2*>(reinterpret_cast<const double*>(tb->r) + base + 2 * q);
+          r[2 * q] = x.x;
+          r[2 * q + 1] = x.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tb->r) + base + 4 * q);
+          r[4 * q] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
+        }
+      }
+      {
+        const float4 x0 = *reinterpret_cast<const float4*>(tb->v + base);
+        const float4 x1 = *reinterpret_cast<const float4*>(tb->v + base + 4);
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+        v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+        v[8] = tb->v[base + 8];  // the producer staged values[t0 + 2048] when it exists (else unused: episode end)
+      }
+      const int ne = (int)(te1 - te0 + 1);
+      int el = 0;  // local episode index of item `base`: last k with off[k] - t0 <= base
+      for (int k = 1; k < ne; ++k)
+        if ((int)(tb->soff[k] - t0) <= base) el = k;
+      int next_rel = (int)(tb->soff[el + 1] - t0);
+#pragma unroll
+      for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const bool last = (base + j == next_rel - 1);
+        float vnext = v[j + 1];
+        double boot = 0.0;
+        if (last) {
+          const float vl = tb->slv[el];
+          vnext = vl;                                        // utils.py:41: delta_{L-1} uses V(last_obs) even when done
+          if (!tb->sdone[el]) boot = p.gamma * (double)vl;   // utils.py:81-85 + ppo.py:149: ret_{L-1} = r + gamma*R_L
+          cut |= 1u << j;
+          ++el;
+          next_rel = (el < ne) ? (int)(tb->soff[el + 1] - t0) : 0x7fffffff;
+        }
+        // utils.py:41: rewards[:-1] (f64) + gamma*values[1:] (evaluated in float32) - values[:-1]
+        b_adv[j] = (r[j] + (double)__fmul_rn(p.gamma_f, vnext)) - (double)v[j];
+        b_ret[j] = r[j] + boot;
+      }
+    } else {
+      // ---- general path: partial last tile and / or more episodes than the staging area holds ----
+#pragma unroll
+      for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const bool in = i0 + j < n;
+        r[j] = in ? (double)tb->r[tid * SCAN_ITEMS + j] : 0.0;
+        v[j] = in ? tb->v[tid * SCAN_ITEMS + j] : 0.f;
+      }
+      v[SCAN_ITEMS] = (i0 + SCAN_ITEMS < n) ? tb->v[tid * SCAN_ITEMS + SCAN_ITEMS] : 0.f;
+      auto off_at = [&](long long ee) { return staged ? tb->soff[ee - te0] : __ldg(p.off + ee); };
+      long long e = 0, next_off = 0;
+      if (i0 < n) {  // e = max{e : off[e] <= i0}, within the tile's episode range
+        long long lo = te0, hi = te1 + 1;
+        while (hi - lo > 1) {
+          const long long mid = (lo + hi) >> 1;
+          if (off_at(mid) <= i0) lo = mid; else hi = mid;
+        }
+        e = lo;
+        next_off = off_at(e + 1);
+      }
+#pragma unroll
+      for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const long long i = i0 + j;
+        if (i < n) {
+          while (i >= next_off) {
+            ++e;
+            next_off = off_at(e + 1);
+          }
+          const bool last = (i == next_off - 1);
+          float vnext = v[j + 1];
+          double boot = 0.0;
+          if (last) {
+            const float vl = staged ? tb->slv[e - te0] : __ldg(p.last_values + e);
+            const int dn = staged ? tb->sdone[e - te0] : (int)__ldg(p.done + e);
+            vnext = vl;
+            if (!dn) boot = p.gamma * (double)vl;
+            cut |= 1u << j;
+          }
+          b_adv[j] = (r[j] + (double)__fmul_rn(p.gamma_f, vnext)) - (double)v[j];
+          b_ret[j] = r[j] + boot;
+        } else {
+          cut |= 1u << j;
+          b_ret[j] = 0.0;
+          b_adv[j] = 0.0;
+        }
+      }
+    }
+    // every consumer has taken what it needs from the slot: hand it back to the producer (runs two tiles ahead)
+    consumer_sync();
+    if (tid == 0) sbar_arrive(sm_addr(&bars[2 + b]));
+
+    // ---- thread aggregate: compose items 7..0 ----
+    Aff tr{1.0, 0.0}, ta{1.0, 0.0};
+#pragma unroll
+    for (int j = SCAN_ITEMS - 1; j >= 0; --j) {
+      const bool cj = (cut >> j) & 1u;
+      const double ar = cj ? 0.0 : p.gamma, aa = cj ? 0.0 : p.gl;
+      tr.b = b_ret[j] + ar * tr.b;
+      tr.a = ar * tr.a;
+      ta.b = b_adv[j] + aa * ta.b;
+      ta.a = aa * ta.a;
+    }
+
+    // ---- warp + CTA suffix scans ----
+    const Aff ex_r = warp_suffix_exclusive(tr, lane);
+    const Aff ex_a = warp_suffix_exclusive(ta, lane);
+    if (lane == 0) {
+      s_wret[warp] = tr;
+      s_wadv[warp] = ta;
+    }
+    consumer_sync();
+
+    // ---- warp 0: publish the tile aggregate, look back over later tiles for the carry-in, publish inclusive.
+    //      Records are self-validating 16-byte {value, tag} pairs: six lanes poll six records in one round trip. ----
+    if (warp == 0) {
+      Aff agg_r{1.0, 0.0}, agg_a{1.0, 0.0};
+      for (int w = SCAN_CONSUMERS / 32 - 1; w >= 0; --w) {
+        agg_r = compose(s_wret[w], agg_r);
+        agg_a = compose(s_wadv[w], agg_a);
+      }
+      if (lane < SCAN_CONSUMERS / 32) {  // lane w: composition of warps w+1 .. 7 (what follows warp w inside the tile)
+        Aff xr{1.0, 0.0}, xa{1.0, 0.0};
+        for (int w = SCAN_CONSUMERS / 32 - 1; w > lane; --w) {
+          xr = compose(s_wret[w], xr);
+          xa = compose(s_wadv[w], xa);
+        }
+        s_xret[lane] = xr;
+        s_xadv[lane] = xa;
+      }
+      ScanRec* mine = p.recs + (size_t)tile * SCAN_RECS;
+      if (lane < 4) st_rec(mine + lane, lane == 0 ? agg_r.a : lane == 1 ? agg_r.b : lane == 2 ? agg_a.a : agg_a.b, tag);
+
+      Aff acc_r{1.0, 0.0}, acc_a{1.0, 0.0};
+      bool failed = false;
+      for (int j = tile + 1; j < T && !failed; ++j) {
+        if (acc_r.a == 0.0 && acc_a.a == 0.0) break;  // an episode end in between: nothing further matters
+        const ScanRec* theirs = p.recs + (size_t)j * SCAN_RECS;
+        double val = 0.0, tg = 0.0;
+        unsigned m = 0;
+        for (int spins = 0;; ++spins) {
+          if (lane < 6) ld_rec(theirs + lane, val, tg);
+          m = __ballot_sync(0xffffffffu, lane < 6 && tg == tag);
+          if ((m & 0x0fu) == 0x0fu || (m & 0x30u) == 0x30u) break;
+          if (spins > (1 << 20)) {  // bounded: never hang the GPU; flag and bail out
+            failed = true;
+            break;
+          }
+          __nanosleep(20);
+        }
+        if (failed) break;
+        if ((m & 0x30u) == 0x30u) {  // their inclusive values are known: the chain ends here
+          const double yr = __shfl_sync(0xffffffffu, val, 4), ya = __shfl_sync(0xffffffffu, val, 5);
+          acc_r = Aff{0.0, acc_r.b + acc_r.a * yr};
+          acc_a = Aff{0.0, acc_a.b + acc_a.a * ya};
+          break;
+        }
+        const double ar = __shfl_sync(0xffffffffu, val, 0), br = __shfl_sync(0xffffffffu, val, 1);
+        const double aa = __shfl_sync(0xffffffffu, val, 2), ba = __shfl_sync(0xffffffffu, val, 3);
+        acc_r = compose(acc_r, Aff{ar, br});
+        acc_a = compose(acc_a, Aff{aa, ba});
+      }
+      // beyond the end of the array the recurrence value is 0
+      if (lane == 4) st_rec(mine + 4, agg_r.b + agg_r.a * acc_r.b, tag);
+      if (lane == 5) st_rec(mine + 5, agg_a.b + agg_a.a * acc_a.b, tag);
+      if (lane == 0) {
+        s_carry[0] = acc_r.b;
+        s_carry[1] = acc_a.b;
+        if (failed) p.hdr->error = 1;
+      }
+    }
+    consumer_sync();
+
+    // ---- carry-in of this thread = (lanes after me in my warp) o (warps after mine) applied to the tile carry ----
+    const Aff xw_r = s_xret[warp], xw_a = s_xadv[warp];
+    const Aff x_r = compose(ex_r, xw_r), x_a = compose(ex_a, xw_a);
+    double y_r = x_r.b + x_r.a * s_carry[0];
+    double y_a = x_a.b + x_a.a * s_carry[1];
+
+    // ---- final sequential recurrence over the thread's items (the reference's own float64 loop) ----
+    float o_ret[SCAN_ITEMS], o_adv[SCAN_ITEMS];
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = SCAN_ITEMS - 1; j >= 0; --j) {
+      const bool cj = (cut >> j) & 1u;
+      y_r = b_ret[j] + (cj ? 0.0 : p.gamma) * y_r;
+      y_a = b_adv[j] + (cj ? 0.0 : p.gl) * y_a;
+      o_ret[j] = (float)y_r;
+      o_adv[j] = (float)y_a;
+      if (fast || i0 + j < n) {
+        const double af = (double)o_adv[j];  // statistics of the float32 tensor, like normalize_tensor's input
+        s1 += af;
+        s2 += af * af;
+      }
+    }
+    if (fast || i0 + SCAN_ITEMS <= n) {
+      *reinterpret_cast<float4*>(p.ret + i0) = make_float4(o_ret[0], o_ret[1], o_ret[2], o_ret[3]);
+      *reinterpret_cast<float4*>(p.ret + i0 + 4) = make_float4(o_ret[4], o_ret[5], o_ret[6], o_ret[7]);
+      *reinterpret_cast<float4*>(p.adv + i0) = make_float4(o_adv[0], o_adv[1], o_adv[2], o_adv[3]);
+      *reinterpret_cast<float4*>(p.adv + i0 + 4) = make_float4(o_adv[4], o_adv[5], o_adv[6], o_adv[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < SCAN_ITEMS; ++j)
+        if (i0 + j < n) {
+          p.ret[i0 + j] = o_ret[j];
+          p.adv[i0 + j] = o_adv[j];
+        }
+    }
+
+    // ---- per-tile advantage statistics (fixed order => deterministic) ----
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      s_red[0][warp] = s1;
+      s_red[1][warp] = s2;
+    }
+    consumer_sync();
+    if (tid == 0) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int w = 0; w < SCAN_CONSUMERS / 32; ++w) {
+        t1 += s_red[0][w];
+        t2 += s_red[1][w];
+      }
+      p.partial[tile] = make_double2(t1, t2);
     }
   }
-  if (full) {
-    *reinterpret_cast<float4*>(p.ret + i0) = make_float4(o_ret[0], o_ret[1], o_ret[2], o_ret[3]);
-    *reinterpret_cast<float4*>(p.ret + i0 + 4) = make_float4(o_ret[4], o_ret[5], o_ret[6], o_ret[7]);
-    *reinterpret_cast<float4*>(p.adv + i0) = make_float4(o_adv[0], o_adv[1], o_adv[2], o_adv[3]);
-    *reinterpret_cast<float4*>(p.adv + i0 + 4) = make_float4(o_adv[4], o_adv[5], o_adv[6], o_adv[7]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j)
-      if (i0 + j < n) {
-        p.ret[i0 + j] = o_ret[j];
-        p.adv[i0 + j] = o_adv[j];
-      }
-  }
 
-  // ---- per-tile advantage statistics (fixed order => deterministic) ----
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if (lane == 0) {
-    s_red[0][warp] = s1;
-    s_red[1][warp] = s2;
-  }
-  __syncthreads();
+  // ---- the last CTA to finish sums the per-tile statistics in a fixed order and resets the header ----
   if (tid == 0) {
-    double t1 = 0.0, t2 = 0.0;
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-      t1 += s_red[0][w];
-      t2 += s_red[1][w];
-    }
-    p.partial[tile] = make_double2(t1, t2);
     __threadfence();
-    s_last = (atomicAdd(&p.hdr->done, 1) == p.num_tiles - 1) ? 1 : 0;
+    s_last = (atomicAdd(&p.hdr->done, 1) == G - 1) ? 1 : 0;
   }
-  __syncthreads();
+  consumer_sync();
   if (!s_last) return;
-
-  // ---- last CTA: fixed-order sum of the per-tile statistics -> stats = (sum, sum of squares, n); reset the header ----
   __threadfence();
-  __shared__ double f1[SCAN_THREADS], f2[SCAN_THREADS];
+  __shared__ double f1[SCAN_CONSUMERS], f2[SCAN_CONSUMERS];
   double fa = 0.0, fb = 0.0;
-  for (int i = tid; i < p.num_tiles; i += SCAN_THREADS) {
+  for (int i = tid; i < T; i += SCAN_CONSUMERS) {
     const double2 x = __ldcg(p.partial + i);
     fa += x.x;
     fb += x.y;
   }
   f1[tid] = fa;
   f2[tid] = fb;
-  __syncthreads();
-  for (int o = SCAN_THREADS / 2; o > 0; o >>= 1) {
+  consumer_sync();
+  for (int o = SCAN_CONSUMERS / 2; o > 0; o >>= 1) {
     if (tid < o) {
       f1[tid] += f1[tid + o];
       f2[tid] += f2[tid + o];
     }
-    __syncthreads();
+    consumer_sync();
   }
   if (tid == 0) {
     const bool bad = p.hdr->error != 0;
@@ -389,7 +503,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) gae_scan_kernel(const ScanArg
     p.stats[0] = bad ? nan : f1[0];
     p.stats[1] = bad ? nan : f2[0];
     p.stats[2] = (double)n;
-    p.hdr->ticket = 0;
     p.hdr->done = 0;
     p.hdr->error = 0;
     p.hdr->epoch = (s_epoch + 1) & 0x0fffffff;
@@ -398,13 +511,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) gae_scan_kernel(const ScanArg
 
 static inline int scan_tiles(int64_t n) { return (int)((n + SCAN_TILE - 1) / SCAN_TILE); }
 
+template <typename RewT>
+static int launch_scan(const ScanArgs& a, cudaStream_t s) {
+  const size_t smem = 2 * sizeof(TileBuf<RewT>);
+  static int cached_blocks = 0;  // resident CTAs per device for this instantiation
+  if (cached_blocks == 0) {
+    B200RL_CUDA(cudaFuncSetAttribute(gae_scan_kernel<RewT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    B200RL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gae_scan_kernel<RewT>, SCAN_THREADS, smem));
+    const int sms = device_sm_count();
+    B200RL_REQUIRE(per_sm > 0 && sms > 0, "gae_scan: kernel does not fit on this device");
+    cached_blocks = per_sm * sms;
+  }
+  const int grid = a.num_tiles < cached_blocks ? a.num_tiles : cached_blocks;  // all CTAs co-resident (look-back)
+  gae_scan_kernel<RewT><<<grid, SCAN_THREADS, smem, s>>>(a);
+  B200RL_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
 }  // namespace b200rl
 
 using namespace b200rl;
 
 extern "C" size_t b200rl_gae_scan_workspace_bytes(int64_t n) {
   const size_t t = (size_t)scan_tiles(n < 1 ? 1 : n);
-  return sizeof(ScanHeader) + t * sizeof(ScanTileState) + t * sizeof(double2);
+  return sizeof(ScanHeader) + t * SCAN_RECS * sizeof(ScanRec) + t * sizeof(double2);
 }
 
 extern "C" int b200rl_gae_scan(const void* rewards, int rewards_f64, const float* values, const float* last_values,
@@ -440,15 +572,9 @@ extern "C" int b200rl_gae_scan(const void* rewards, int rewards_f64, const float
   a.adv = adv_raw;
   a.ret = ret;
   a.hdr = static_cast<ScanHeader*>(workspace);
-  a.tiles = reinterpret_cast<ScanTileState*>(static_cast<char*>(workspace) + sizeof(ScanHeader));
-  a.partial = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.tiles) + (size_t)tiles * sizeof(ScanTileState));
-  a.num_tiles = tiles;
+  a.recs = reinterpret_cast<ScanRec*>(static_cast<char*>(workspace) + sizeof(ScanHeader));
+  a.partial = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.recs) + (size_t)tiles * SCAN_RECS * sizeof(ScanRec));
   a.stats = stats;
-  if (rewards_f64)
-    gae_scan_kernel<double><<<tiles, SCAN_THREADS, 0, s>>>(a);
-  else
-    gae_scan_kernel<float><<<tiles, SCAN_THREADS, 0, s>>>(a);
-  B200RL_CUDA(cudaGetLastError());
-  count_launch(1);
-  return 0;
+  a.num_tiles = tiles;
+  return rewards_f64 ? launch_scan<double>(a, s) : launch_scan<float>(a, s);
 }
