@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1024)
     ap.add_argument("--horizon", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the TRPO (config 3) / TD3 (config 4) side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -293,8 +294,109 @@ def main():
         ms = ev0.elapsed_time(ev1) / 10
         return n2, ms, 20.0 * n2 / (ms * 1e-3) / 1e9
 
+    # ---------------- BASELINE configs 3 and 4 (rank 0 only; reported as extra fields, not the headline) ----------------
+    def trpo_config3():
+        """TRPO synthetic Ant-shaped obs(27) act(8), 1024 envs x 1000 steps, CG iters 10 (11 FVPs), 80 value steps."""
+        import types
+        from rl_replicas_b200 import synthetic
+        from test_gpu_trpo import build_trpo
+        rng = np.random.default_rng(1)
+        ps, vs = [27, 64, 64, 8], [27, 64, 64, 1]
+        mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+                         for i, o in zip(sz[:-1], sz[1:])]
+        pl2, vl2 = mk(ps), mk(vs)
+        g = {"policy_sizes": ps, "value_sizes": vs, "policy_flat0": O.flatten_layers(pl2),
+             "value_flat0": O.flatten_layers(vl2), "log_std": np.full(8, -0.5, np.float32)}
+        trpo = build_trpo(g, num_value_gradients=N_VALUE)
+        trpo.metrics_manager = None
+        b = synthetic.fixed_batch(E, T, 27, 8, seed=9, frac_not_done=0.1,
+                                  mean_fn=lambda o: O.mlp_forward(pl2, o)[0])
+        for _ in range(2):
+            trpo.train_packed(b)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        trpo.train_packed(b)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_update = ev0.elapsed_time(ev1)
+        eng = trpo._engine
+        hp3 = trpo._hparams(eng, 0)
+        eng.run_stage("fvp", hp3)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(10):
+            eng.run_stage("fvp", hp3)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_fvp = ev0.elapsed_time(ev1) / 10
+        flop_fvp = 2 * 6336 * 2 + 2 * (6336 + 4608) + 2 * (6336 + 4608)  # tangent fwd (2 products/layer) + fwd + bwd
+        ts = trpo.last_trpo_stats
+        return {"workload": "TRPO synthetic Ant-shaped obs(27) act(8), 1024 envs x 1000 steps, 10 CG iterations",
+                "ms_per_update_e2e": ms_update, "transitions_per_s_e2e": E * T / (ms_update * 1e-3),
+                "ms_per_fvp": ms_fvp, "fvp_per_s": 1e3 / ms_fvp, "fvp_launches": int(ts.fvp_launches),
+                "fvp_tflops_fp32": flop_fvp * E * T / (ms_fvp * 1e-3) / 1e12,
+                "accepted_ratio_index": int(ts.accepted_index), "rejected": int(ts.rejected), "kl": ts.kl,
+                "kernel": "mlp_fused_kernel<*,2> (fp32 CUDA cores: forward + tangents + metric + backward)"}
+
+    def td3_config4():
+        """TD3 synthetic Hopper-shaped replay (obs 11, act 3), minibatch 256, 256-256 nets, 50 train steps per call."""
+        from rl_replicas_b200.experience import Experience
+        from test_gpu_offpolicy import build as build_off
+        rng = np.random.default_rng(2)
+        H = 256
+        mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+                         for i, o in zip(sz[:-1], sz[1:])]
+        PSz, QSz = [11, H, H, 3], [14, H, H, 1]
+        algo, rb = build_off(True, H, O.flatten_layers(mk(PSz)), [O.flatten_layers(mk(QSz)), O.flatten_layers(mk(QSz))])
+        algo.metrics_manager = None
+        n_rb = 100000  # sampling cost does not depend on the buffer size; 1 M Python-list entries only cost host RAM/time
+        ex = Experience()
+        obs_rb = rng.standard_normal((n_rb + 1, 11)).astype(np.float32)
+        ex.observations = [[obs_rb[i] for i in range(n_rb)]]
+        ex.actions = [[a for a in rng.uniform(-1, 1, (n_rb, 3)).astype(np.float32)]]
+        ex.rewards = [[float(x) for x in rng.standard_normal(n_rb)]]
+        ex.dones = [[bool(x) for x in (rng.random(n_rb) < 0.001)]]
+        ex.last_observations = [obs_rb[n_rb]]
+        rb.add_experience(ex)
+        S4, B4 = 50, 256
+        algo.train(rb, S4, B4)
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            algo.train(rb, S4, B4)
+        torch.cuda.synchronize()
+        ms_call = (time.perf_counter() - t0) * 1e3 / reps
+        # device part only: replay the last staged minibatches through the engine
+        eng = algo._engine
+        mbs = [rb.sample_minibatch(B4) for _ in range(S4)]
+        st = lambda k: np.stack([np.asarray(m[k]) for m in mbs]).astype(np.float32)
+        noise = torch.stack([torch.randn(B4, 3) for _ in range(S4)]).numpy()
+        hp4 = algo._hparams(True, 2)
+        args4 = (hp4, st("observations"), st("actions"), st("rewards"), st("next_observations"), st("dones"), noise)
+        eng.train(*args4)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.train(*args4)
+        ms_dev = (time.perf_counter() - t0) * 1e3 / reps
+        return {"workload": "TD3 synthetic Hopper-shaped (obs 11, act 3), minibatch 256, MLP(256,256), 50 train steps/call, "
+                            "replay 100k transitions",
+                "ms_per_train_call_e2e": ms_call, "train_steps_per_s_e2e": S4 / (ms_call * 1e-3),
+                "transitions_per_s_e2e": S4 * B4 / (ms_call * 1e-3),
+                "ms_per_train_call_engine": ms_dev, "train_steps_per_s_engine": S4 / (ms_dev * 1e-3),
+                "note": "e2e includes the reference-compatible host sampling (numpy RNG + Python-list gather); engine = "
+                        "one upload + 50 steps of kernels + one read-back"}
+
     if rank == 0:
         n_big, ms_big, gbs_big = scan_large()
+        extras = {}
+        if world == 1 and not args.no_extras:
+            try:
+                extras["config3_trpo"] = trpo_config3()
+                extras["config4_td3"] = td3_config4()
+            except Exception as exc:  # extras must never break the headline line
+                extras["error"] = repr(exc)
     if rank == 0:
         total_transitions = n_local * world
         value = total_transitions / (ms_dev * 1e-3)
@@ -327,6 +429,7 @@ def main():
             "update_flops_per_transition": FLOP_PER_TRANSITION,
             "update_tflops_fp32_equiv": FLOP_PER_TRANSITION * total_transitions / (ms_dev * 1e-3) / 1e12,
             "clocks": clocks,
+            "other_configs": extras,
         }
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_reference_run(1, 0)

@@ -705,6 +705,10 @@ extern "C" int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, 
   if (strcmp(stage, "value_grad_kernel") == 0)
     return launch_fused(h, h->cfg.value, B200RL_LOSS_MSE, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, n_glob, 0.0,
                         false, false, nullptr, true, nullptr, s);
+  if (strcmp(stage, "fvp") == 0) {  // one Fisher-vector product (kernel + fixed-order reduction) on the current direction
+    if (ensure_trpo(h)) return 1;
+    return launch_fvp(h, h->cg_p, h->cg_z, n_glob, s);
+  }
   set_error("run_stage: unknown stage '%s'", stage);
   return 2;
 }

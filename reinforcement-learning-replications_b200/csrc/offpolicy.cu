@@ -8,7 +8,7 @@
 // launch-latency bound, not throughput bound.  The design therefore minimises host involvement:
 // ALL `num_train_steps` minibatches (and the target-smoothing noise) are uploaded once, every step runs as a fixed
 // sequence of small fp32 kernels with no host synchronisation, and losses / Q-values are read back once at the end.
-// GEMMs are one generic 64x64x16 shared-memory-tiled fp32 kernel in three operand arrangements (forward NT, dX NN,
+// GEMMs are one generic 32x32x16 shared-memory-tiled fp32 kernel in three operand arrangements (forward NT, dX NN,
 // dW TN) with the activation derivative fused into the operand load, so activations are never rewritten.
 #include <cmath>
 #include <cstring>
@@ -18,7 +18,7 @@
 
 namespace b200rl {
 
-constexpr int GT = 64;   // output tile
+constexpr int GT = 32;   // output tile (256x256 outputs -> 64 CTAs; the batch is small, parallelism matters more than reuse)
 constexpr int GK = 16;   // k tile
 constexpr int GTHREADS = 256;
 
@@ -51,12 +51,12 @@ __global__ void __launch_bounds__(GTHREADS) gemm_kernel(const GemmArgs g) {
   __shared__ float As[GK][GT + 4], Bs[GK][GT + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
-  const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
-  float acc[4][4];
+  const int tm = (tid / 16) * 2, tn = (tid % 16) * 2;  // 16 x 16 threads, 2 x 2 outputs each
+  float acc[2][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 2; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < g.K; k0 += GK) {
     // stage A^T-style: As[k][m], Bs[k][n]
     for (int idx = tid; idx < GK * GT; idx += GTHREADS) {
@@ -86,20 +86,20 @@ __global__ void __launch_bounds__(GTHREADS) gemm_kernel(const GemmArgs g) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][tm]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tn]);
-      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float2 av = *reinterpret_cast<const float2*>(&As[k][tm]);
+      const float2 bv = *reinterpret_cast<const float2*>(&Bs[k][tn]);
+      const float ar[2] = {av.x, av.y}, br[2] = {bv.x, bv.y};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        for (int j = 0; j < 2; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
       const int gm = m0 + tm + i, gn = n0 + tn + j;
       if (gm < g.M && gn < g.N) {
         float v = acc[i][j];
