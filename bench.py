@@ -418,11 +418,11 @@ def main():
                          "ms_per_launch": ms_pol},
             "roofline_value_kernel": {"bound": "tensor", "achieved": tf_val, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                                       "frac": tf_val / pk["tf_sust"], "ms_per_launch": ms_val},
-            "roofline_scan": {"kernel": "gae_scan_kernel<double> (single launch: scan + statistics)", "bound": "hbm", "achieved": gbs_scan,
+            "roofline_scan": {"kernel": "gae_scan_episode_kernel<double> (single launch: scan + statistics)", "bound": "hbm", "achieved": gbs_scan,
                               "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_scan / pk["hbm"], "traffic": None,
                               "bytes_per_transition": 20, "ms_per_launch": ms_scan_pair,
                               "note": "16.4 MB problem: launch-latency bound at this size (SURVEY 7.3-3)"},
-            "roofline_scan_large": {"kernel": "gae_scan_kernel<double>", "bound": "hbm", "achieved": gbs_big,
+            "roofline_scan_large": {"kernel": "gae_scan_episode_kernel<double>", "bound": "hbm", "achieved": gbs_big,
                                     "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_big / pk["hbm"], "traffic": None,
                                     "transitions": n_big, "bytes_per_transition": 20, "ms_per_launch": ms_big,
                                     "note": "65536 episodes x 1000 steps: 1.31 GB of algorithmic traffic (> L2)"},

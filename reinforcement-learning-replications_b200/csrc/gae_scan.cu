@@ -72,6 +72,7 @@ struct ScanArgs {
   double2* partial;
   double* stats;
   int num_tiles;
+  double pw_r[5], pw_a[5];  // gamma^(8*2^k), (gamma*lambda)^(8*2^k): warp-scan multipliers of uncut chunks
 };
 
 // one pipeline slot: a tile's rewards and values (+ the first value of the next tile) and its episode range
@@ -509,6 +510,258 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) gae_scan_kernel(const ScanArg
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Episode-parallel variant: ONE WARP PER EPISODE, walking 256-transition chunks (aligned to the flat array) from the
+// episode's end to its start with the recurrence carries in registers.  No CTA barrier, no look-back, no per-item
+// boundary search: the only special element is the episode's last step.  This is the regime RL batches live in
+// (hundreds to millions of episodes of up to a few thousand steps); the tile kernel above covers few / very long
+// episodes.  Per-episode advantage statistics go to ep_partial[e]; the last CTA sums them in a fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EP_WARPS = 8;
+constexpr int EP_STAGES = 4;  // chunks in flight per warp (cp.async ring)
+
+template <typename RewT>
+__global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const ScanArgs p, double2* ep_partial) {
+  extern __shared__ __align__(16) unsigned char ep_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n_warps = (long long)gridDim.x * EP_WARPS;
+  const RewT* __restrict__ rew = static_cast<const RewT*>(p.rew);
+  double lp_r = 1.0, lp_a = 1.0;  // gamma^(8*(31-lane)): coefficient of the incoming carry for this lane
+  for (int k = 0; k < 31 - lane; ++k) {
+    lp_r *= p.pw_r[0];
+    lp_a *= p.pw_a[0];
+  }
+  // Chunks of an episode [beg, end): 256 items each, anchored at top = round_up(end, 8) and walked downwards until
+  // bot = round_down(beg, 8) is covered; chunk starts are multiples of 8 items, so every lane's 8 rewards / 8 values
+  // are 16-byte aligned.  Items outside [beg, end) are masked (their recurrence inputs are zeroed, which makes the
+  // constant-coefficient recurrence exact at the episode's last step) and never stored.
+  // Per-warp ring of EP_STAGES chunks filled with cp.async: every lane copies exactly the items it will consume, so
+  // the ring needs no barrier -- the lane's own wait_group orders its copies before its reads.  The issue side runs
+  // EP_STAGES chunks ahead of the consumer ACROSS episode boundaries (episodes w, w + n_warps, ... belong to warp w).
+  constexpr int STAGE_BYTES = 256 * (int)sizeof(RewT) + 256 * 4;
+  unsigned char* wbase = ep_smem + (size_t)warp * EP_STAGES * STAGE_BYTES;
+  long long ie = (long long)blockIdx.x * EP_WARPS + warp, ics = 0, ibot = 0;  // issue-side iterator
+  if (ie < p.n_ep) {
+    ibot = __ldg(p.off + ie) & ~7LL;
+    ics = ((__ldg(p.off + ie + 1) + 7) & ~7LL) - 256;
+  }
+  auto issue_next = [&](int st) {
+    if (ie < p.n_ep) {
+      const long long j0 = ics + lane * SCAN_ITEMS;
+      if (j0 >= ibot && j0 + SCAN_ITEMS <= p.n) {
+        const uint32_t dr = sm_addr(wbase + st * STAGE_BYTES + lane * SCAN_ITEMS * (int)sizeof(RewT));
+        const char* sr = reinterpret_cast<const char*>(rew + j0);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS * (int)sizeof(RewT) / 16; ++k) scan_cp_async16(dr + 16 * k, sr + 16 * k);
+        const uint32_t dv = sm_addr(wbase + st * STAGE_BYTES + 256 * (int)sizeof(RewT) + lane * SCAN_ITEMS * 4);
+        scan_cp_async16(dv, p.values + j0);
+        scan_cp_async16(dv + 16, p.values + j0 + 4);
+      }
+      ics -= 256;
+      if (ics + 256 <= ibot) {  // episode covered: move to this warp's next one
+        ie += n_warps;
+        if (ie < p.n_ep) {
+          ibot = __ldg(p.off + ie) & ~7LL;
+          ics = ((__ldg(p.off + ie + 1) + 7) & ~7LL) - 256;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int st = 0; st < EP_STAGES; ++st) issue_next(st);
+  int stage = 0;
+  // episode metadata is fetched one episode ahead so its latency hides behind the current episode's chunks
+  long long nbeg = 0, nend = 0;
+  float nvl = 0.f;
+  unsigned char ndn = 0;
+  {
+    const long long e0 = (long long)blockIdx.x * EP_WARPS + warp;
+    if (e0 < p.n_ep) {
+      nbeg = __ldg(p.off + e0);
+      nend = __ldg(p.off + e0 + 1);
+      nvl = __ldg(p.last_values + e0);
+      ndn = __ldg(p.done + e0);
+    }
+  }
+  for (long long e = (long long)blockIdx.x * EP_WARPS + warp; e < p.n_ep; e += n_warps) {
+    const long long beg = nbeg, end = nend;
+    const long long bot = beg & ~7LL;
+    const float vl = nvl;
+    const double boot = ndn ? 0.0 : p.gamma * (double)vl;  // utils.py:81-85 + ppo.py:149
+    if (e + n_warps < p.n_ep) {
+      nbeg = __ldg(p.off + e + n_warps);
+      nend = __ldg(p.off + e + n_warps + 1);
+      nvl = __ldg(p.last_values + e + n_warps);
+      ndn = __ldg(p.done + e + n_warps);
+    }
+    double carry_r = 0.0, carry_a = 0.0;  // recurrence values at the first item of the chunk processed before
+    float v_first_prev = vl;              // value of that item (v_{i+1} of this chunk's last item)
+    double s1 = 0.0, s2 = 0.0;
+    long long cs = ((end + 7) & ~7LL) - 256;
+    do {
+      const long long i0 = cs + lane * SCAN_ITEMS;
+      double r[SCAN_ITEMS];
+      float v[SCAN_ITEMS];
+      asm volatile("cp.async.wait_group %0;" ::"n"(EP_STAGES - 1) : "memory");
+      if (i0 >= bot && i0 + SCAN_ITEMS <= p.n) {
+        const unsigned char* sb = wbase + stage * STAGE_BYTES;
+        if (sizeof(RewT) == 8) {
+          const double2* q = reinterpret_cast<const double2*>(sb) + lane * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 x = q[j];
+            r[2 * j] = x.x;
+            r[2 * j + 1] = x.y;
+          }
+        } else {
+          const float4* q = reinterpret_cast<const float4*>(sb) + lane * 2;
+          const float4 y0 = q[0], y1 = q[1];
+          r[0] = y0.x; r[1] = y0.y; r[2] = y0.z; r[3] = y0.w;
+          r[4] = y1.x; r[5] = y1.y; r[6] = y1.z; r[7] = y1.w;
+        }
+        const float4* qv = reinterpret_cast<const float4*>(sb + 256 * sizeof(RewT)) + lane * 2;
+        const float4 x0 = qv[0], x1 = qv[1];
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+        v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      } else {  // lane below the episode (all masked) or straddling the end of the arrays (not in the ring)
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+          const bool in = i0 + j >= bot && i0 + j < p.n;
+          r[j] = in ? (double)rew[i0 + j] : 0.0;
+          v[j] = in ? p.values[i0 + j] : 0.f;
+        }
+      }
+      issue_next(stage);  // refill the slot just drained
+      stage = stage + 1 == EP_STAGES ? 0 : stage + 1;
+
+      float vn7 = __shfl_down_sync(0xffffffffu, v[0], 1);  // value of the next lane's first item
+      if (lane == 31) vn7 = v_first_prev;
+      double d[SCAN_ITEMS];
+#pragma unroll
+      for (int j = 0; j < SCAN_ITEMS; ++j) {
+        const float vnext = j < SCAN_ITEMS - 1 ? v[j + 1] : vn7;  // utils.py:41: gamma * values[1:] in float32
+        d[j] = (r[j] + (double)__fmul_rn(p.gamma_f, vnext)) - (double)v[j];
+      }
+      const bool edge = cs < beg || cs + 256 >= end;  // warp-uniform: chunk holds masked items or the last step
+      int lo = 0, hi = SCAN_ITEMS;
+      if (edge) {
+        lo = (int)min(max(beg - i0, 0LL), (long long)SCAN_ITEMS);
+        hi = (int)max(min(end - i0, (long long)SCAN_ITEMS), 0LL);
+        const long long jl64 = end - 1 - i0;
+        const int jl = (jl64 >= 0 && jl64 < SCAN_ITEMS) ? (int)jl64 : -1;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+          if (j < lo || j >= hi) {
+            r[j] = 0.0;
+            d[j] = 0.0;
+          } else if (j == jl) {  // last step: delta uses V(last_obs) even when done; the return bootstraps if not done
+            d[j] = (r[j] + (double)__fmul_rn(p.gamma_f, vl)) - (double)v[j];
+            r[j] += boot;
+          }
+        }
+      }
+      double tr = r[SCAN_ITEMS - 1], ta = d[SCAN_ITEMS - 1];
+#pragma unroll
+      for (int j = SCAN_ITEMS - 2; j >= 0; --j) {
+        tr = r[j] + p.gamma * tr;
+        ta = d[j] + p.gl * ta;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double r2 = __shfl_down_sync(0xffffffffu, tr, 1 << k);
+        const double a2 = __shfl_down_sync(0xffffffffu, ta, 1 << k);
+        if (lane + (1 << k) < 32) {
+          tr += p.pw_r[k] * r2;
+          ta += p.pw_a[k] * a2;
+        }
+      }
+      double y_r = __shfl_down_sync(0xffffffffu, tr, 1);
+      double y_a = __shfl_down_sync(0xffffffffu, ta, 1);
+      if (lane == 31) {
+        y_r = 0.0;
+        y_a = 0.0;
+      }
+      y_r += lp_r * carry_r;
+      y_a += lp_a * carry_a;
+      float o_ret[SCAN_ITEMS], o_adv[SCAN_ITEMS];
+#pragma unroll
+      for (int j = SCAN_ITEMS - 1; j >= 0; --j) {
+        y_r = r[j] + p.gamma * y_r;
+        y_a = d[j] + p.gl * y_a;
+        o_ret[j] = (float)y_r;
+        o_adv[j] = (float)y_a;
+      }
+      if (lo == 0 && hi == SCAN_ITEMS && i0 + SCAN_ITEMS <= p.n) {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+          const double af = (double)o_adv[j];
+          s1 += af;
+          s2 += af * af;
+        }
+        *reinterpret_cast<float4*>(p.ret + i0) = make_float4(o_ret[0], o_ret[1], o_ret[2], o_ret[3]);
+        *reinterpret_cast<float4*>(p.ret + i0 + 4) = make_float4(o_ret[4], o_ret[5], o_ret[6], o_ret[7]);
+        *reinterpret_cast<float4*>(p.adv + i0) = make_float4(o_adv[0], o_adv[1], o_adv[2], o_adv[3]);
+        *reinterpret_cast<float4*>(p.adv + i0 + 4) = make_float4(o_adv[4], o_adv[5], o_adv[6], o_adv[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+          if (j >= lo && j < hi) {
+            const double af = (double)o_adv[j];
+            s1 += af;
+            s2 += af * af;
+            p.ret[i0 + j] = o_ret[j];
+            p.adv[i0 + j] = o_adv[j];
+          }
+        }
+      }
+      // carries for the next (earlier) chunk: the recurrence values and the value at this chunk's first item
+      carry_r = __shfl_sync(0xffffffffu, y_r, 0);
+      carry_a = __shfl_sync(0xffffffffu, y_a, 0);
+      v_first_prev = __shfl_sync(0xffffffffu, v[0], 0);
+      cs -= 256;
+    } while (cs + 256 > bot);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) ep_partial[e] = make_double2(s1, s2);
+  }
+
+  // ---- the last CTA to finish sums the per-episode statistics in a fixed order ----
+  __shared__ int s_last;
+  __shared__ double f1[EP_WARPS * 32], f2[EP_WARPS * 32];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&p.hdr->done, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double fa = 0.0, fb = 0.0;
+  for (long long i = tid; i < p.n_ep; i += EP_WARPS * 32) {
+    const double2 x = __ldcg(ep_partial + i);
+    fa += x.x;
+    fb += x.y;
+  }
+  f1[tid] = fa;
+  f2[tid] = fb;
+  __syncthreads();
+  for (int o = EP_WARPS * 16; o > 0; o >>= 1) {
+    if (tid < o) {
+      f1[tid] += f1[tid + o];
+      f2[tid] += f2[tid + o];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    p.stats[0] = f1[0];
+    p.stats[1] = f2[0];
+    p.stats[2] = (double)p.n;
+    p.hdr->done = 0;
+  }
+}
+
 static inline int scan_tiles(int64_t n) { return (int)((n + SCAN_TILE - 1) / SCAN_TILE); }
 
 template <typename RewT>
@@ -536,7 +789,8 @@ using namespace b200rl;
 
 extern "C" size_t b200rl_gae_scan_workspace_bytes(int64_t n) {
   const size_t t = (size_t)scan_tiles(n < 1 ? 1 : n);
-  return sizeof(ScanHeader) + t * SCAN_RECS * sizeof(ScanRec) + t * sizeof(double2);
+  // header | look-back records | per-tile statistics | per-episode statistics (episode kernel, n_ep <= n / 16)
+  return sizeof(ScanHeader) + t * SCAN_RECS * sizeof(ScanRec) + t * sizeof(double2) + (((size_t)(n < 1 ? 1 : n) + 15) & ~(size_t)15);
 }
 
 extern "C" int b200rl_gae_scan(const void* rewards, int rewards_f64, const float* values, const float* last_values,
@@ -569,6 +823,10 @@ extern "C" int b200rl_gae_scan(const void* rewards, int rewards_f64, const float
   a.gamma = gamma;
   a.gl = gamma * gae_lambda;
   a.gamma_f = (float)gamma;
+  for (int k = 0; k < 5; ++k) {
+    a.pw_r[k] = pow(a.gamma, 8.0 * (1 << k));
+    a.pw_a[k] = pow(a.gl, 8.0 * (1 << k));
+  }
   a.adv = adv_raw;
   a.ret = ret;
   a.hdr = static_cast<ScanHeader*>(workspace);
@@ -576,5 +834,26 @@ extern "C" int b200rl_gae_scan(const void* rewards, int rewards_f64, const float
   a.partial = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.recs) + (size_t)tiles * SCAN_RECS * sizeof(ScanRec));
   a.stats = stats;
   a.num_tiles = tiles;
+  // Regime switch: many episodes of moderate length -> one warp per episode (no inter-CTA dependency at all);
+  // few or very long episodes -> tile kernel with decoupled look-back.
+  const bool by_episode = n_ep >= 256 && n_ep <= n / 16 && n / n_ep <= 32768;
+  if (by_episode) {
+    double2* ep_partial = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.partial) + (size_t)tiles * sizeof(double2));
+    const int grid = (int)std::min<long long>((n_ep + EP_WARPS - 1) / EP_WARPS, 2LL * device_sm_count());
+    const int smem64 = EP_WARPS * EP_STAGES * (256 * 8 + 1024), smem32 = EP_WARPS * EP_STAGES * (256 * 4 + 1024);
+    static bool configured = false;
+    if (!configured) {
+      B200RL_CUDA(cudaFuncSetAttribute(gae_scan_episode_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+      B200RL_CUDA(cudaFuncSetAttribute(gae_scan_episode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32));
+      configured = true;
+    }
+    if (rewards_f64)
+      gae_scan_episode_kernel<double><<<grid, EP_WARPS * 32, smem64, s>>>(a, ep_partial);
+    else
+      gae_scan_episode_kernel<float><<<grid, EP_WARPS * 32, smem32, s>>>(a, ep_partial);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+  }
   return rewards_f64 ? launch_scan<double>(a, s) : launch_scan<float>(a, s);
 }
