@@ -118,9 +118,20 @@ typedef struct {
                               kl_divergence(old_dist, dist) of trpo.py:167-175 (Gaussian: same log_std for both) */
   const float* direction;  /* [P] the vector v of B200RL_LOSS_FVP, same flat layout as params */
   int32_t flags;           /* B200RL_FLAG_* */
+  const float* obs_absmax; /* optional device scalar: max |obs| over the batch (range hint of the fp16 tensor-core
+                              kernel; NULL = a pre-pass computes it on every launch, see b200rl_absmax) */
+  const float* target_absmax; /* optional device scalar: max |target| (MSE backward); NULL = pre-pass */
 } b200rl_mlp_loss_grad_args;
 
 int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* args, void* stream);
+
+/* out[0] = max |x[i]| (+inf if x holds a NaN); `out` is a device float.  Callers that launch mlp_loss_grad many times
+ * over the same observations / targets compute the hints once with this. */
+int b200rl_absmax(const float* x, int64_t n, float* out, void* stream);
+
+/* Number of mlp_loss_grad launches (since process start) whose fp16 tensor-core pass left the fp16 range and were
+ * recomputed by the wide-range bf16 kernel queued behind it.  Synchronises the device; diagnostics / tests only. */
+int64_t b200rl_tc_fallback_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * reduce_adam -- fixed-order reduction of the per-CTA partials into the flat gradient, then torch.optim.Adam's

@@ -40,7 +40,8 @@ class LossGradArgs(C.Structure):
                 ("actions", C.c_void_p), ("log_std", C.c_void_p), ("adv_raw", C.c_void_p), ("adv_stats", C.c_void_p),
                 ("old_logp", C.c_void_p), ("target", C.c_void_p), ("row_out", C.c_void_p), ("partials", C.c_void_p),
                 ("scalar_partials", C.c_void_p), ("skip_flag", C.c_void_p), ("out_full", C.c_void_p),
-                ("old_out", C.c_void_p), ("direction", C.c_void_p), ("flags", C.c_int32)]
+                ("old_out", C.c_void_p), ("direction", C.c_void_p), ("flags", C.c_int32),
+                ("obs_absmax", C.c_void_p), ("target_absmax", C.c_void_p)]
 
 
 class OnPolicyConfig(C.Structure):
@@ -103,6 +104,8 @@ SIGNATURES = {
                                   C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
     "b200rl_mlp_loss_grad": (C.c_int, [C.POINTER(LossGradArgs), C.c_void_p]),
+    "b200rl_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b200rl_tc_fallback_count": (C.c_int64, []),
     "b200rl_reduce_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p]),
     "b200rl_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double,

@@ -49,6 +49,8 @@ struct b200rl_onpolicy {
   int64_t* off = nullptr;
   uint8_t* done = nullptr;
   int64_t n_rows = 0, n_ep = 0;
+  float* absmax = nullptr;   // [4] max |obs|, max |last_obs|, max |returns| (range hints of the fp16 tensor-core kernel)
+  bool hints_valid = false;  // set by the preamble, cleared whenever the batch buffers may have been rewritten
   // derived
   float *values = nullptr, *last_values = nullptr, *adv_raw = nullptr, *ret = nullptr, *old_logp = nullptr;
   double* adv_stats = nullptr;
@@ -137,6 +139,11 @@ int launch_fused(b200rl_onpolicy* h, const b200rl_mlp_desc& mlp, int loss, int d
   a.partials = h->partials;
   a.scalar_partials = want_scalars ? h->scalar_partials : nullptr;
   a.skip_flag = skip;
+  if (h->hints_valid) {
+    if (obs == h->obs) a.obs_absmax = h->absmax;
+    if (obs == h->last_obs) a.obs_absmax = h->absmax + 1;
+    if (loss == B200RL_LOSS_MSE) a.target_absmax = h->absmax + 2;
+  }
   return b200rl_mlp_loss_grad(&a, s);
 }
 
@@ -186,8 +193,9 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
   rc |= dev_alloc(h, &h->pol_v, (size_t)Pp);
   rc |= dev_alloc(h, &h->val_m, (size_t)Pv);
   rc |= dev_alloc(h, &h->val_v, (size_t)Pv);
-  rc |= dev_alloc(h, &h->partials, (size_t)sms * Pmax);
-  rc |= dev_alloc(h, &h->scalar_partials, (size_t)sms * B200RL_N_SCALARS);
+  rc |= dev_alloc(h, &h->partials, (size_t)2 * sms * Pmax);  // mlp_tc2 emits two partial rows per CTA
+  rc |= dev_alloc(h, &h->scalar_partials, (size_t)2 * sms * B200RL_N_SCALARS);
+  rc |= dev_alloc(h, &h->absmax, 4);
   rc |= dev_alloc(h, &h->pol_grad, (size_t)Pp + B200RL_N_SCALARS);
   rc |= dev_alloc(h, &h->val_grad, (size_t)Pv + B200RL_N_SCALARS);
   rc |= dev_alloc(h, &h->flags, 8);
@@ -308,12 +316,18 @@ extern "C" int b200rl_onpolicy_load_batch(b200rl_onpolicy* h, const float* obs, 
   B200RL_CUDA(cudaMemcpyAsync(h->done, ep_done, (size_t)n_episodes, k, s));
   h->n_rows = n_rows;
   h->n_ep = n_episodes;
+  h->hints_valid = false;
   return 0;
 }
 
 // ---- the shared preamble of PPO / VPG / TRPO train(): value inference -> scan -> (all-reduce of 3 scalars) ----
 static int run_preamble(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
                         cudaStream_t s) {
+  // range hints for the fp16 tensor-core kernel: one pass over the observations per update instead of per launch
+  h->hints_valid = false;
+  if (b200rl_absmax(h->obs, h->n_rows * h->obs_dim, h->absmax, s)) return 1;
+  if (b200rl_absmax(h->last_obs, h->n_ep * h->obs_dim, h->absmax + 1, s)) return 1;
+  h->hints_valid = true;
   // utils.py:60-71 compute_values: V(obs_t) for every step and V(last_observation) for every episode
   if (launch_fused(h, h->cfg.value, B200RL_LOSS_EVAL, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, h->n_rows, 0.0,
                    false, false, h->values, false, nullptr, s)) return 1;
@@ -322,6 +336,7 @@ static int run_preamble(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl
   if (b200rl_gae_scan(h->rew, h->cfg.rewards_f64, h->values, h->last_values, h->off, h->done, h->n_rows, h->n_ep,
                       hp->gamma, hp->gae_lambda, h->adv_raw, h->ret, h->adv_stats, h->scan_ws, h->scan_ws_bytes, s))
     return 1;
+  if (b200rl_absmax(h->ret, h->n_rows, h->absmax + 2, s)) return 1;
   // normalize_tensor (utils.py:90-92) is over the GLOBAL batch: one 3-scalar all-reduce per update
   if (ar && ar(user, h->adv_stats, 3, 1, s)) {
     set_error("allreduce callback failed (advantage statistics)");
@@ -648,6 +663,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
 extern "C" int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr, int64_t* count,
                                            int32_t* dtype) {
   B200RL_REQUIRE(h && name && ptr && count && dtype, "device_view: NULL argument");
+  h->hints_valid = false;  // the caller may write through the view
   struct V { const char* n; void* p; int64_t c; int32_t d; };
   const V views[] = {
       {"values", h->values, h->n_rows, 0},        {"last_values", h->last_values, h->n_ep, 0},

@@ -593,6 +593,15 @@ static int fused_grid(const MlpLayout& lay, int64_t n_rows) {
 bool tc_shape_ok(const b200rl_mlp_desc& d);
 int tc_grid(int64_t n_rows);
 int launch_mlp_tc(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s);
+// second-generation tensor-core path (mlp_tc2.cu): fp16 x 2 splits, two partial rows per CTA
+int tc2_grid(int64_t n_rows);
+int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s);
+// B200RL_TC_MODE=bf16 pins the bf16 x 3 kernel (A/B runs); default is the fp16 x 2 kernel with bf16 x 3 as its
+// wide-range fallback
+static bool use_tc2() {
+  const char* e = getenv("B200RL_TC_MODE");
+  return !(e != nullptr && e[0] == 'b');
+}
 
 // B200RL_DISABLE_TC=1 forces the fp32 CUDA-core kernel (A/B parity runs); read on every call so tests can flip it.
 static bool use_tc(const b200rl_mlp_desc& d) {
@@ -619,7 +628,11 @@ extern "C" int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp) {
 // (launches that use out_full / old_out / B200RL_FLAG_NO_TC)
 extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward) {
   if (!mlp) return -1;
-  if (with_backward < 2 && use_tc(*mlp)) return tc_grid(n_rows);
+  if (with_backward < 2 && use_tc(*mlp)) {
+    if (!use_tc2()) return tc_grid(n_rows);
+    const int g = tc2_grid(n_rows);
+    return g > 0 ? 2 * g : -1;
+  }
   MlpLayout lay;
   if (build_layout(*mlp, with_backward == 1 || with_backward == 2, &lay, with_backward == 2)) return -1;
   return fused_grid(lay, n_rows);
@@ -657,7 +670,10 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
   }
   if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
   const bool needs_fp32 = fvp || a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC);
-  if (!needs_fp32 && use_tc(a->mlp)) return launch_mlp_tc(a, a->n_global > 0 ? a->n_global : a->n_rows, s);
+  if (!needs_fp32 && use_tc(a->mlp)) {
+    const int64_t n_glob_tc = a->n_global > 0 ? a->n_global : a->n_rows;
+    return use_tc2() ? launch_mlp_tc2(a, n_glob_tc, s) : launch_mlp_tc(a, n_glob_tc, s);
+  }
   const size_t smem_bytes = (size_t)k.lay.total_floats * sizeof(float);
   B200RL_REQUIRE(smem_bytes <= 227 * 1024,
                  "mlp_loss_grad: network needs %zu bytes of shared memory (> 227 KiB); too large for the fused kernel",

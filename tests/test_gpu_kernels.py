@@ -196,3 +196,76 @@ def test_adam_step_matches_oracle_and_golden():
     g = load_golden("ppo_gaussian_small")
     p1, _, _ = adam_step(g["policy_flat0"], g["grad0"], np.zeros(n, np.float32), np.zeros(n, np.float32), 1, 3e-4)
     assert rel_err(p1, g["policy_flat1"]) < 1e-6
+
+
+# ---- fp16 x 2 tensor-core kernel (mlp_tc2): range handling ----------------------------------------------------------
+def _fallbacks():
+    from rl_replicas_b200 import _lib
+    return int(_lib.load().b200rl_tc_fallback_count())
+
+
+@pytest.mark.parametrize("obs_scale,w_scale,ret_scale", [(1.0, 1.0, 5.0), (1e3, 1e-3, 5.0), (1e-4, 1e4, 5.0),
+                                                        (1e-4, 1.0, 5.0), (1.0, 1.0, 3e4), (1.0, 1.0, 1e-3)])
+def test_tc2_scaled_operands_stay_on_the_fp16_path(obs_scale, w_scale, ret_scale):
+    """Power-of-two pre-scales keep small / large observations, weights and targets inside fp16's normal range: the
+    fast kernel's result stands (no wide-range re-run) and still meets the 1e-5 bar."""
+    from gpu_helpers import loss_grad
+    rng = np.random.default_rng(5)
+    n, sizes = 3000, [17, 64, 64, 1]
+    layers = _net(rng, sizes)
+    layers[0] = ((layers[0][0] * w_scale).astype(np.float32), layers[0][1])  # first layer absorbs the obs scale
+    obs = (obs_scale * rng.standard_normal((n, sizes[0]))).astype(np.float32)
+    ret = (ret_scale * rng.standard_normal(n)).astype(np.float32)
+    before = _fallbacks()
+    r = loss_grad(sizes, O.flatten_layers(layers), obs, "mse", "none", target=ret)
+    assert _fallbacks() == before
+    ref = O.value_loss_and_grad(layers, obs, ret)
+    assert rel_err(r["grad"], ref["grad"]) < TOL
+    assert abs(r["scalars"][0] / n - ref["loss"]) < 1e-5 * ref["loss"]
+
+
+def test_tc2_out_of_range_launch_is_redone_by_the_wide_range_kernel():
+    """One observation of 1e30 cannot be represented after scaling (the rest of the batch underflows next to it is
+    fine, but a gradient outlier 1e12 times the typical one is not): the status slot fires and the bf16 x 3 kernel
+    queued behind recomputes the launch -- results still match the oracle."""
+    from gpu_helpers import loss_grad
+    rng = np.random.default_rng(6)
+    n, sizes = 2000, [17, 64, 64, 6]
+    layers = _net(rng, sizes)
+    obs = rng.standard_normal((n, sizes[0])).astype(np.float32)
+    log_std = np.full(6, -0.5, np.float32)
+    act = (O.mlp_forward(layers, obs)[0] + np.exp(-0.5) * rng.standard_normal((n, 6))).astype(np.float32)
+    adv_raw = rng.standard_normal(n).astype(np.float32)
+    adv_raw[7] = 1e12  # un-normalised advantages (adv_stats=None): one gradient row 1e12 times the others
+    before = _fallbacks()
+    r = loss_grad(sizes, O.flatten_layers(layers), obs, "vpg", "gaussian", act=act, log_std=log_std, adv_raw=adv_raw)
+    assert _fallbacks() == before + 1
+    ref = O.policy_loss_and_grad(layers, "gaussian", log_std, obs, act, adv_raw, None, "vpg", 0.2)
+    assert rel_err(r["grad"], ref["grad"]) < TOL
+
+
+def test_tc2_nan_input_is_reported_not_hidden():
+    from gpu_helpers import loss_grad
+    rng = np.random.default_rng(8)
+    n, sizes = 500, [17, 64, 64, 1]
+    layers = _net(rng, sizes)
+    obs = rng.standard_normal((n, sizes[0])).astype(np.float32)
+    obs[3, 2] = np.nan
+    r = loss_grad(sizes, O.flatten_layers(layers), obs, "eval", "none")
+    assert np.isnan(r["rows"][3]) and np.isfinite(np.delete(r["rows"], 3)).all()
+
+
+def test_tc_mode_bf16_matches(monkeypatch):
+    """B200RL_TC_MODE=bf16 pins the bf16 x 3 kernel (one partial row per CTA): same results through the same ABI."""
+    from gpu_helpers import loss_grad
+    rng = np.random.default_rng(9)
+    n, sizes = 4000, [17, 64, 64, 1]
+    layers = _net(rng, sizes)
+    obs = rng.standard_normal((n, sizes[0])).astype(np.float32)
+    ret = (5 * rng.standard_normal(n)).astype(np.float32)
+    ref = O.value_loss_and_grad(layers, obs, ret)
+    fast = loss_grad(sizes, O.flatten_layers(layers), obs, "mse", "none", target=ret)
+    monkeypatch.setenv("B200RL_TC_MODE", "bf16")
+    wide = loss_grad(sizes, O.flatten_layers(layers), obs, "mse", "none", target=ret)
+    assert rel_err(fast["grad"], ref["grad"]) < TOL and rel_err(wide["grad"], ref["grad"]) < TOL
+    assert rel_err(fast["grad"], wide["grad"]) < TOL

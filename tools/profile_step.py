@@ -21,3 +21,18 @@ if __name__ == "__main__":
     ppo.train_packed(b)
     st = ppo.last_update_stats
     print("launches", st.kernel_launches, "kl", st.kl_divergence, "vloss", st.value_loss_mean)
+    if os.environ.get("B200RL_TC_TIMING"):
+        import ctypes as C
+        from rl_replicas_b200 import _lib
+        import torch
+        torch.cuda.synchronize()
+        out = (C.c_ulonglong * 16)()
+        kind = os.environ["B200RL_TC_TIMING"]
+        (_lib.load().b200rl_debug_tc2_timing if kind == "2" else _lib.load().b200rl_debug_tc_timing)(out)
+        names = ["obs", "F1wait", "act1", "F2wait", "act2", "F3wait", "loss", "S3wait", "dz2", "S4wait", "dz1", "S5wait",
+                 "offwait"]
+        tiles = (envs * 1000 // 128 + 147) // 148
+        print("cycles per tile (CTA 0, last backward launch):", {n: int(out[i]) // tiles for i, n in enumerate(names)},
+              "total", sum(int(out[i]) for i in range(13)) // tiles)
+    from rl_replicas_b200 import _lib as _L
+    print("tc fallbacks:", _L.load().b200rl_tc_fallback_count())
