@@ -10,10 +10,12 @@
 //     range.  A logical product is then 3 MMAs (h.l, l.h, h.h) on the forward/back-propagation chain and 2 MMAs for
 //     the weight-gradient products, whose A operand (dZ^T) is read MN-major with BOTH splits stacked along M
 //     (M = 128: rows 0..63 = h-split features, 64..127 = l-split features -- the second 64-element atom of an
-//     MN-major operand sits one leading-byte-offset further, i.e. in the next split buffer).  98 MMAs per tile.
-//   * the weight-gradient products are off the dependency chain: they run on the tensor pipe while the epilogue
-//     warps already compute the next dZ (separate dZ buffers make that legal), tracked by a second mbarrier.
-//   * 16 epilogue warps (4 per TMEM lane quadrant, 16 columns each) instead of 8.
+//     MN-major operand sits one leading-byte-offset further, i.e. in the next split buffer).  101 MMAs per tile.
+//   * with one tile in flight the epilogue warps spent 43% of their time on mbarriers (ncu source view): the
+//     MMA -> tanh -> MMA chain is latency bound.  Two fp16 splits instead of three bf16 ones make TWO tiles fit in
+//     shared memory (2 x 96 KB), so the CTA runs two independent tile pipelines ("slots", 8 epilogue warps each)
+//     that share the MMA-issuing warp, the tensor pipe and the gradient accumulators in tensor memory: while one
+//     slot waits for its MMAs the other one runs its epilogue.
 // fp16 has a narrow exponent range: the scales come from the data (max |W| per layer computed per CTA, max |obs| and
 // max |target| from a pre-pass or the caller) and every converted value is range-checked.  A launch that sees a
 // value outside +-60000 after scaling raises its slot in a status ring and the host has already queued the
@@ -31,7 +33,9 @@
 namespace b200rl {
 
 constexpr int T2_ROWS = 128;
-constexpr int T2_EPI_WARPS = 16;
+constexpr int T2_SLOT_WARPS = 8;
+constexpr int T2_SLOT_THREADS = T2_SLOT_WARPS * 32;
+constexpr int T2_EPI_WARPS = 2 * T2_SLOT_WARPS;
 constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
 constexpr int T2_THREADS = T2_EPI_THREADS + 32;
 constexpr float T2_LOG_SQRT_2PI = 0.91893853320467274178f;
@@ -40,32 +44,34 @@ constexpr float T2_RANGE = 60000.f;  // |scaled value| above this (or NaN) => fa
 constexpr int T2_H_EXP = 14;         // activations (|H| <= 1) are stored as H * 2^14
 
 // shared-memory map (bytes from the 1024-aligned base); every operand buffer = 2 fp16 splits, 128-byte rows, SW128
-constexpr uint32_t T2_ACT = 128 * 128;  // one split of a [128][64] fp16 buffer
-constexpr uint32_t T2_W = 64 * 128;     // one split of a [64][64] weight
-constexpr uint32_t T2_W3 = 16 * 128;    // one split of the [16][64] output weight
-constexpr uint32_t S2_XD = 0;           // obs cols 0..31 | dOut cols 32..46 | ones col 47
-constexpr uint32_t S2_H1 = S2_XD + 2 * T2_ACT;
-constexpr uint32_t S2_H2 = S2_H1 + 2 * T2_ACT;
-constexpr uint32_t S2_DZ1 = S2_H2 + 2 * T2_ACT;
-constexpr uint32_t S2_DZ2 = S2_DZ1 + 2 * T2_ACT;
-constexpr uint32_t S2_W1 = S2_DZ2 + 2 * T2_ACT;
-constexpr uint32_t S2_W2 = S2_W1 + 2 * T2_W;
+constexpr uint32_t T2_ACT = 128 * 128;      // one split of a [128][64] fp16 buffer
+constexpr uint32_t T2_SLOT = 6 * T2_ACT;    // XD, H1, H2 of one slot
+constexpr uint32_t T2_W1T = 32 * 128;       // one split of W1^T [32 in][64 out]
+constexpr uint32_t T2_W = 64 * 128;         // one split of W2 [64 out][64 in]
+constexpr uint32_t T2_W3 = 16 * 128;        // one split of W3 [16 out][64 in]
+constexpr uint32_t S2_XD = 0;               // (slot-relative) obs cols 0..31 | dOut cols 32..46 | ones col 47
+constexpr uint32_t S2_H1 = 2 * T2_ACT;      // (slot-relative) H1, overwritten in place by dZ1
+constexpr uint32_t S2_H2 = 4 * T2_ACT;      // (slot-relative) H2, overwritten in place by dZ2
+constexpr uint32_t S2_W1T = 2 * T2_SLOT;
+constexpr uint32_t S2_W2 = S2_W1T + 2 * T2_W1T;
 constexpr uint32_t S2_W3 = S2_W2 + 2 * T2_W;
 constexpr uint32_t S2_OPERANDS_END = S2_W3 + 2 * T2_W3;
-constexpr uint32_t S2_BIAS = S2_OPERANDS_END;     // b1[64] b2[64] b3[16] floats
-constexpr uint32_t S2_DIST = S2_BIAS + 1024;      // var[16], log_scale[16] floats
-constexpr uint32_t S2_DB3 = S2_DIST + 256;        // [4 warps][16] floats
-constexpr uint32_t S2_SCALE = S2_DB3 + 256;       // scale factors (floats), see Scales
-constexpr uint32_t S2_RED = S2_SCALE + 128;       // block reduction scratch [17 warps][4] floats
-constexpr uint32_t S2_STAGE = S2_RED + 384;       // fp32 staging of the NEXT tile's observations [128][n_in<=32]
-constexpr uint32_t S2_TOTAL = S2_STAGE + 128 * 32 * 4;
+constexpr uint32_t S2_BIAS = S2_OPERANDS_END;  // b1[64] b2[64] b3[16] floats
+constexpr uint32_t S2_DIST = S2_BIAS + 640;    // var[16], log_scale[16], 1/(2 var)[16], 1/var[16] floats
+constexpr uint32_t S2_DB3 = S2_DIST + 256;     // [8 loss warps][16] floats
+constexpr uint32_t S2_SCALE = S2_DB3 + 512;    // scale factors (floats)
+constexpr uint32_t S2_RED = S2_SCALE + 64;     // block reduction scratch [17 warps][4] floats
+constexpr uint32_t S2_SC = S2_RED + 320;       // [6][8 loss warps] doubles
+constexpr uint32_t S2_BARS = S2_SC + 384;      // mbarriers: ready[2], chain[2], off[2]; tmem holder; bad flag
+constexpr uint32_t S2_TOTAL = S2_BARS + 64;
 constexpr uint32_t T2_SMEM_BYTES = S2_TOTAL + 1024;  // + alignment slack
 static_assert(T2_SMEM_BYTES <= 227 * 1024, "mlp_tc2 shared memory");
 
-// tensor-memory column map (fp32).  Z*/OUT/DH*: one row per lane.  DW*/DB2: stacked accumulators, lane = feature
-// (+64 for the l-split half).
-constexpr uint32_t M2_Z1 = 0, M2_Z2 = 64, M2_OUT = 128, M2_DH2 = 160, M2_DH1 = 224, M2_DW2 = 288, M2_DW1 = 352,
-                   M2_DW3 = 400, M2_DB2 = 416;
+// tensor-memory column map (fp32).  Per slot (base = slot * 144): Z1 (kept as H1 for tanh'), ZB (Z2, then dH2, then
+// dH1 -- each consumed by its epilogue before the next product overwrites it), OUT.  Shared stacked accumulators,
+// lane = feature (+64 for the l-split half): DW2, DW1 (cols 0..31 dW1, col 47 db1), DW3, DB2 (col 15).
+constexpr uint32_t M2_SLOT = 144, M2_Z1 = 0, M2_ZB = 64, M2_OUT = 128;
+constexpr uint32_t M2_DW2 = 288, M2_DW1 = 352, M2_DW3 = 400, M2_DB2 = 416;
 
 // indices into the scale table in shared memory
 enum { SC_X = 0, SC_G, SC_U1, SC_U2, SC_U3, SC_UH2, SC_UH1, SC_W1, SC_W2, SC_W3, SC_OW3, SC_OW2, SC_OW1, SC_OB, SC_N };
@@ -128,6 +134,20 @@ __device__ __forceinline__ void store_chunk2(uint8_t* sm, uint32_t buf, int r, i
   *reinterpret_cast<uint4*>(sm + off) = h;
   *reinterpret_cast<uint4*>(sm + off + T2_ACT) = l;
 }
+// read them back as fp32 (h + l), still carrying the storage scale
+__device__ __forceinline__ void load_chunk2(const uint8_t* sm, uint32_t buf, int r, int ch, float (&x)[8]) {
+  const uint32_t off = buf + (uint32_t)r * 128u + ((uint32_t)(ch ^ (r & 7)) << 4);
+  const uint4 h = *reinterpret_cast<const uint4*>(sm + off);
+  const uint4 l = *reinterpret_cast<const uint4*>(sm + off + T2_ACT);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+    x[2 * j] = a.x + b.x;
+    x[2 * j + 1] = a.y + b.y;
+  }
+}
 __device__ __forceinline__ bool out_of_range8(const float (&x)[8]) {
   float m = fabsf(x[0]);
 #pragma unroll
@@ -143,8 +163,14 @@ __device__ __forceinline__ void t2_tmem_st16(uint32_t taddr, const uint32_t (&v)
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
-__device__ __forceinline__ void t2_cp_async16(uint32_t smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 
 // Instruction descriptor, kind::f16 with fp16 operands (format 0), fp32 accumulate (fields as in tc_common.cuh)
@@ -166,47 +192,38 @@ __device__ __forceinline__ Op2 op2_mnmajor(uint32_t addr, uint32_t atom_stride, 
   const uint64_t d = make_smem_desc_sw128(addr, atom_stride, 1024);
   return Op2{(uint32_t)d, (uint32_t)(d >> 32), split_bytes >> 4, 2048u >> 4};
 }
+__device__ __forceinline__ Op2 op2_at(Op2 o, uint32_t byte_off) {  // same view, `byte_off` further (slot select)
+  o.lo += byte_off >> 4;
+  return o;
+}
+// Issue path: fully unrolled with compile-time k-step offsets, every operand derived from warp-uniform values
+// (shared-memory window offsets, kernel parameters, vote results) -- measured 100 -> 74 cycles per MMA on B200.
 // chain product: (h,l) + (l,h) + (h,h), smallest terms first; overwrites D
-__device__ __forceinline__ void issue_chain3(uint32_t d_tmem, uint32_t idesc, int ksteps, const Op2 a, const Op2 b) {
+template <int KSTEPS>
+__device__ __forceinline__ void issue_chain3(uint32_t d_tmem, uint32_t idesc, const Op2 a, const Op2 b) {
   constexpr int TI[3] = {0, 1, 0};
   constexpr int TJ[3] = {1, 0, 0};
-  uint32_t acc = 0u;
 #pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    uint32_t alo = a.lo + TI[t] * a.split_step, blo = b.lo + TJ[t] * b.split_step;
-#pragma unroll 1
-    for (int k = 0; k < ksteps; ++k) {
-      umma_f16_elect2(d_tmem, alo, a.hi, blo, b.hi, idesc, acc);
-      acc = 1u;
-      alo += a.k_step;
-      blo += b.k_step;
-    }
-  }
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k)
+      umma_f16_elect2(d_tmem, a.lo + TI[t] * a.split_step + k * a.k_step, a.hi,
+                      b.lo + TJ[t] * b.split_step + k * b.k_step, b.hi, idesc, (t | k) ? 1u : 0u);
 }
 // stacked product: A covers both of its splits along M; B split l (optional) then h
-__device__ __forceinline__ void issue_stacked(uint32_t d_tmem, uint32_t idesc, int ksteps, bool accumulate_first,
-                                              const Op2 a, const Op2 b, int b_splits) {
-  uint32_t acc = accumulate_first ? 1u : 0u;
-  for (int sp = b_splits - 1; sp >= 0; --sp) {
-    uint32_t alo = a.lo, blo = b.lo + sp * b.split_step;
-#pragma unroll 1
-    for (int k = 0; k < ksteps; ++k) {
-      umma_f16_elect2(d_tmem, alo, a.hi, blo, b.hi, idesc, acc);
-      acc = 1u;
-      alo += a.k_step;
-      blo += b.k_step;
-    }
-  }
-}
-
-__device__ __forceinline__ void epi_arrive() {  // epilogue thread -> issuer: "my stage inputs are in shared memory"
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  asm volatile("bar.arrive 1, %0;" ::"n"(T2_THREADS) : "memory");
+template <int KSTEPS, int B_SPLITS>
+__device__ __forceinline__ void issue_stacked(uint32_t d_tmem, uint32_t idesc, bool accumulate_first,
+                                              const Op2 a, const Op2 b) {
+#pragma unroll
+  for (int sp = B_SPLITS - 1; sp >= 0; --sp)
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k)
+      umma_f16_elect2(d_tmem, a.lo + k * a.k_step, a.hi, b.lo + sp * b.split_step + k * b.k_step, b.hi, idesc,
+                      (sp != B_SPLITS - 1 || k != 0 || accumulate_first) ? 1u : 0u);
 }
 
 #ifdef B200RL_TC_TIMING
-__device__ unsigned long long g_tc2_t[16];
+__device__ unsigned long long g_tc2_t[24];
 #define T2_T(i)                                   \
   do {                                            \
     if (tid == 0) {                               \
@@ -222,10 +239,6 @@ __device__ unsigned long long g_tc2_t[16];
 template <bool BACKWARD>
 __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) unsigned long long mbar_chain, mbar_off;
-  __shared__ uint32_t tmem_holder;
-  __shared__ double s_sc[6][4];
-  __shared__ int s_bad;
   if (p.skip_flag != nullptr && *p.skip_flag != 0) return;  // early stop: whole launch is a no-op
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -237,12 +250,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
   float* s_db3 = reinterpret_cast<float*>(sm + S2_DB3);
   float* s_scale = reinterpret_cast<float*>(sm + S2_SCALE);
   float* s_red = reinterpret_cast<float*>(sm + S2_RED);
+  double* s_sc = reinterpret_cast<double*>(sm + S2_SC);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + S2_BARS + 48);
+  int* s_bad = reinterpret_cast<int*>(sm + S2_BARS + 52);
+  const uint32_t bars = base + S2_BARS;  // ready[s] at +8s, chain[s] at +16+8s, off[s] at +32+8s
   const int n_in = p.n_in, A_out = p.n_out;
   bool bad = false;
 
   // ---- one-time setup: zero operand buffers; per-layer weight scales; stage W (two fp16 splits), biases ----
   for (uint32_t i = tid; i < S2_OPERANDS_END / 16; i += T2_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
-  if (tid == 0) s_bad = 0;
+  if (tid == 0) *s_bad = 0;
   {
     float m1 = 0.f, m2 = 0.f, m3 = 0.f;
     for (int idx = tid; idx < 64 * n_in; idx += T2_THREADS) {
@@ -273,7 +290,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     }
   }
   __syncthreads();
-  if (bad) s_bad = 1;  // NaN weight
+  if (bad) *s_bad = 1;  // NaN weight
+  bad = false;
   if (tid == 0) {
     float m1 = 0.f, m2 = 0.f, m3 = 0.f;
     for (int w = 0; w < T2_THREADS / 32; ++w) {
@@ -315,7 +333,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     s_scale[SC_OW2] = pow2i(-(T2_H_EXP + eg));
     s_scale[SC_OW1] = pow2i(-(ex + eg));
     s_scale[SC_OB] = pow2i(-eg);
-    if (b0) s_bad = 1;
+    if (b0) *s_bad = 1;
   }
   __syncthreads();
   {
@@ -327,8 +345,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       *reinterpret_cast<__half*>(sm + off + stride) = lb;
     };
     const float sw1 = s_scale[SC_W1], sw2 = s_scale[SC_W2], sw3 = s_scale[SC_W3];
-    for (int idx = tid; idx < 64 * n_in; idx += T2_THREADS)
-      put(S2_W1, T2_W, idx / n_in, idx % n_in, __ldg(p.params + p.w_off[0] + idx) * sw1);
+    for (int idx = tid; idx < 64 * n_in; idx += T2_THREADS)  // W1 stored transposed: row = input, column = output
+      put(S2_W1T, T2_W1T, idx % n_in, idx / n_in, __ldg(p.params + p.w_off[0] + idx) * sw1);
     for (int idx = tid; idx < 64 * 64; idx += T2_THREADS)
       put(S2_W2, T2_W, idx >> 6, idx & 63, __ldg(p.params + p.w_off[1] + idx) * sw2);
     for (int idx = tid; idx < A_out * 64; idx += T2_THREADS)
@@ -343,25 +361,31 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         const float scale = expf(__ldg(p.log_std + a));  // gaussian_policy.py:34
         s_dist[a] = scale * scale;                       // Normal.log_prob: var = scale ** 2
         s_dist[16 + a] = logf(scale);
+        s_dist[32 + a] = 1.f / (2.f * (scale * scale));  // reciprocals: one multiply per row instead of a division
+        s_dist[48 + a] = 1.f / (scale * scale);
       }
   }
   if (warp == T2_EPI_WARPS) {
-    tmem_alloc(smem_u32(&tmem_holder), 512);
+    tmem_alloc(smem_u32(s_tmem), 512);
     tmem_relinquish();
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&mbar_chain), 1);
-    mbar_init(smem_u32(&mbar_off), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bars + 8 * s, T2_SLOT_THREADS);  // ready[s]: every epilogue thread of the slot arrives
+      mbar_init(bars + 16 + 8 * s, 1);           // chain[s]: tcgen05.commit
+      mbar_init(bars + 32 + 8 * s, 1);           // off[s]:   tcgen05.commit
+    }
     fence_mbar_init();
   }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = tmem_holder;
-  const uint32_t bar_chain = smem_u32(&mbar_chain), bar_off = smem_u32(&mbar_off);
+  const uint32_t tmem = *s_tmem;
 
   const long long num_tiles = (p.n_rows + T2_ROWS - 1) / T2_ROWS;
+  // tiles of this CTA: blockIdx.x + k * gridDim.x; slot s takes k = s, s + 2, ...
+  const long long cta_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   constexpr int STAGES = BACKWARD ? 6 : 3;
 
   if (warp == T2_EPI_WARPS) {
@@ -369,61 +393,107 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     constexpr uint32_t I_128_64_KK = make_idesc_f16(128, 64, 0, 0), I_128_16_KK = make_idesc_f16(128, 16, 0, 0),
                        I_128_64_KM = make_idesc_f16(128, 64, 0, 1), I_128_64_MM = make_idesc_f16(128, 64, 1, 1),
                        I_128_48_MM = make_idesc_f16(128, 48, 1, 1), I_128_16_MM = make_idesc_f16(128, 16, 1, 1);
-    const uint32_t ub = __shfl_sync(0xffffffffu, base, 0);
-    const uint32_t ut = __shfl_sync(0xffffffffu, tmem, 0);
+    // warp-uniform by construction: `base` comes from the shared-memory window, and a 512-column allocation is the
+    // whole tensor memory, whose base address is 0 (checked once below)
+    const uint32_t ub = base, ut = 0u, ubar = bars;
+    if (tmem != 0u) __trap();
+    // slot-0 views of the per-slot buffers (slot 1 = T2_SLOT further)
     const Op2 XD_K = op2_kmajor(ub + S2_XD, T2_ACT), H1_K = op2_kmajor(ub + S2_H1, T2_ACT),
-              H2_K = op2_kmajor(ub + S2_H2, T2_ACT), DZ2_K = op2_kmajor(ub + S2_DZ2, T2_ACT),
-              W1_K = op2_kmajor(ub + S2_W1, T2_W), W2_K = op2_kmajor(ub + S2_W2, T2_W),
-              W3_K = op2_kmajor(ub + S2_W3, T2_W3);
+              H2_K = op2_kmajor(ub + S2_H2, T2_ACT);
     const Op2 XD_K2 = op2_kmajor(ub + S2_XD + 64, T2_ACT);  // cols 32..47 (dOut) as a K-major A operand
     // MN-major views; as A operands (M = 128) the second atom is the l-split buffer, T2_ACT further
-    const Op2 H2_M = op2_mnmajor(ub + S2_H2, T2_ACT, T2_ACT), DZ2_M = op2_mnmajor(ub + S2_DZ2, T2_ACT, T2_ACT),
-              DZ1_M = op2_mnmajor(ub + S2_DZ1, T2_ACT, T2_ACT), H1_M = op2_mnmajor(ub + S2_H1, T2_ACT, T2_ACT),
+    const Op2 H2_M = op2_mnmajor(ub + S2_H2, T2_ACT, T2_ACT), H1_M = op2_mnmajor(ub + S2_H1, T2_ACT, T2_ACT),
               XD_M0 = op2_mnmajor(ub + S2_XD, T2_ACT, T2_ACT),        // X | dOut | ones (cols 0..47)
-              XD_M32 = op2_mnmajor(ub + S2_XD + 64, T2_ACT, T2_ACT),  // dOut | ones (cols 32..47)
-              W2_M = op2_mnmajor(ub + S2_W2, 64 * 128, T2_W), W3_M = op2_mnmajor(ub + S2_W3, 16 * 128, T2_W3);
-    bool first = true;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-#pragma unroll 1
-      for (int s = 0; s < STAGES; ++s) {
-        asm volatile("bar.sync 1, %0;" ::"n"(T2_THREADS) : "memory");  // operands of stage s are in shared memory
-        tc_fence_after_sync();
-        if (s == 0) {  // Z1 = X W1^T
-          issue_chain3(ut + M2_Z1, I_128_64_KK, 2, XD_K, W1_K);
-          umma_commit_elect(bar_chain);
-        } else if (s == 1) {  // Z2 = H1 W2^T
-          issue_chain3(ut + M2_Z2, I_128_64_KK, 4, H1_K, W2_K);
-          umma_commit_elect(bar_chain);
-        } else if (s == 2) {  // OUT = H2 W3^T
-          issue_chain3(ut + M2_OUT, I_128_16_KK, 4, H2_K, W3_K);
-          umma_commit_elect(bar_chain);
-        } else if (s == 3) {
-          // chain: dH2 = dOut W3 (A: XD cols 32..47; B: W3 read MN-major, K = output index)
-          issue_chain3(ut + M2_DH2, I_128_64_KM, 1, XD_K2, W3_M);
-          umma_commit_elect(bar_chain);
-          // off chain: dW3^T[i][o] += sum_r H2[r][i] dOut[r][o]
-          issue_stacked(ut + M2_DW3, I_128_16_MM, 8, !first, H2_M, XD_M32, 2);
-        } else if (s == 4) {
-          // chain: dH1 = dZ2 W2 ; off chain: dW2[o][i] += sum_r dZ2[r][o] H1[r][i] ; db2[o] += sum_r dZ2[r][o] * 1
-          issue_chain3(ut + M2_DH1, I_128_64_KM, 4, DZ2_K, W2_M);
-          umma_commit_elect(bar_chain);
-          issue_stacked(ut + M2_DW2, I_128_64_MM, 8, !first, DZ2_M, H1_M, 2);
-          issue_stacked(ut + M2_DB2, I_128_16_MM, 8, !first, DZ2_M, XD_M32, 1);
-        } else {
-          // dW1[o][i] += sum_r dZ1[r][o] X[r][i] and, through the ones column, db1[o] += sum_r dZ1[r][o]
-          issue_stacked(ut + M2_DW1, I_128_48_MM, 8, !first, DZ1_M, XD_M0, 2);
-          umma_commit_elect(bar_off);
-        }
-        __syncwarp();
+              XD_M32 = op2_mnmajor(ub + S2_XD + 64, T2_ACT, T2_ACT);  // dOut | ones (cols 32..47)
+    // weights (shared by the slots)
+    const Op2 W1T_M = op2_mnmajor(ub + S2_W1T, 32 * 128, T2_W1T), W2_K = op2_kmajor(ub + S2_W2, T2_W),
+              W3_K = op2_kmajor(ub + S2_W3, T2_W3), W2_M = op2_mnmajor(ub + S2_W2, 64 * 128, T2_W),
+              W3_M = op2_mnmajor(ub + S2_W3, 16 * 128, T2_W3);
+    bool acc_dw3 = false, acc_dw2 = false, acc_dw1 = false;  // the first product into an accumulator overwrites it
+    long long left[2] = {(cta_tiles + 1) / 2 * STAGES, cta_tiles / 2 * STAGES};
+    int st[2] = {0, 0};
+    int acc_done[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // accumulating stages issued so far, per stage and slot
+    uint32_t par[2] = {0u, 0u};
+    int s = 0;
+#ifdef B200RL_TC_TIMING
+    unsigned long long iacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long ilast = clock64();
+#endif
+    while (left[0] + left[1] > 0) {
+      // serve whichever slot has its stage inputs ready (the vote makes the predicate provably warp-uniform)
+      if (left[s] == 0 || !__all_sync(0xffffffffu, mbar_test(ubar + 8 * s, par[s]))) {
+        s ^= 1;
+        continue;
       }
-      first = false;
+      // The gradient accumulators are shared by the slots and fp32 addition is not associative: products that
+      // accumulate (stages 3..5) are issued in TILE order, whatever order the slots become ready in, so that a launch
+      // is bit-reproducible.  Slot s's j-th tile is the CTA's tile 2j + s.
+      if (BACKWARD && st[s] >= 3) {
+        const int x = st[s] - 3;
+        if (acc_done[x][s ^ 1] < acc_done[x][s] + s) {
+          s ^= 1;
+          continue;
+        }
+        ++acc_done[x][s];
+      }
+      par[s] ^= 1u;
+      --left[s];
+      tc_fence_after_sync();
+      const uint32_t so = (uint32_t)s * T2_SLOT, tz = ut + (uint32_t)s * M2_SLOT;
+      const uint32_t bar_chain = ubar + 16 + 8 * s, bar_off = ubar + 32 + 8 * s;
+      const int stage = st[s];
+      st[s] = stage + 1 == STAGES ? 0 : stage + 1;
+      if (stage == 0) {  // Z1 = X W1^T
+        issue_chain3<2>(tz + M2_Z1, I_128_64_KM, op2_at(XD_K, so), W1T_M);
+        umma_commit_elect(bar_chain);
+      } else if (stage == 1) {  // Z2 = H1 W2^T
+        issue_chain3<4>(tz + M2_ZB, I_128_64_KK, op2_at(H1_K, so), W2_K);
+        umma_commit_elect(bar_chain);
+      } else if (stage == 2) {  // OUT = H2 W3^T
+        issue_chain3<4>(tz + M2_OUT, I_128_16_KK, op2_at(H2_K, so), W3_K);
+        umma_commit_elect(bar_chain);
+      } else if (stage == 3) {
+        // dH2 = dOut W3 (A: XD cols 32..47; B: W3 read MN-major, K = output index);
+        // dW3^T[i][o] += sum_r H2[r][i] dOut[r][o]  -- must retire before the epilogue turns H2 into dZ2 in place
+        issue_chain3<1>(tz + M2_ZB, I_128_64_KM, op2_at(XD_K2, so), W3_M);
+        issue_stacked<8, 2>(ut + M2_DW3, I_128_16_MM, acc_dw3, op2_at(H2_M, so), op2_at(XD_M32, so));
+        acc_dw3 = true;
+        umma_commit_elect(bar_chain);
+      } else if (stage == 4) {
+        // dH1 = dZ2 W2 ; dW2[o][i] += sum_r dZ2[r][o] H1[r][i] ; db2[o] += sum_r dZ2[r][o] * 1
+        issue_chain3<4>(tz + M2_ZB, I_128_64_KM, op2_at(H2_K, so), W2_M);
+        issue_stacked<8, 2>(ut + M2_DW2, I_128_64_MM, acc_dw2, op2_at(H2_M, so), op2_at(H1_M, so));
+        issue_stacked<8, 1>(ut + M2_DB2, I_128_16_MM, acc_dw2, op2_at(H2_M, so), op2_at(XD_M32, so));
+        acc_dw2 = true;
+        umma_commit_elect(bar_chain);
+      } else {
+        // dW1[o][i] += sum_r dZ1[r][o] X[r][i] and, through the ones column, db1[o] += sum_r dZ1[r][o]
+        issue_stacked<8, 2>(ut + M2_DW1, I_128_48_MM, acc_dw1, op2_at(H1_M, so), op2_at(XD_M0, so));
+        acc_dw1 = true;
+        umma_commit_elect(bar_off);
+      }
+      __syncwarp();
+#ifdef B200RL_TC_TIMING
+      {
+        const long long n = clock64();
+        iacc[stage] += (unsigned long long)(n - ilast);  // issuing (incl. back-pressure from the MMA queue)
+        ilast = n;
+      }
+#endif
     }
+#ifdef B200RL_TC_TIMING
+    if (lane == 0 && blockIdx.x == 0 && BACKWARD)
+      for (int i = 0; i < 8; ++i) g_tc2_t[16 + i] = iacc[i];
+#endif
   } else {
-    // =============================== epilogue warps ==================================================
-    const int q = warp & 3, part = warp >> 2;
+    // =============================== epilogue warps: two slots of 8 ==================================
+    const int slot = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
     const int r = 32 * q + lane;                          // row of the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;  // this warp's TMEM lane quadrant
-    const int c0 = 16 * part;                             // this warp's 16 columns
+    const uint32_t tz = tmem + lane_addr + (uint32_t)slot * M2_SLOT;
+    const uint32_t so = (uint32_t)slot * T2_SLOT;
+    const int c0 = 32 * half;  // this warp's 32 columns of a 64-column epilogue
+    const uint32_t bar_ready = bars + 8 * slot, bar_chain = bars + 16 + 8 * slot, bar_off = bars + 32 + 8 * slot;
     uint32_t ph_chain = 0, ph_off = 0;
     const float sX = s_scale[SC_X], sG = s_scale[SC_G];
     const float sH = pow2i(T2_H_EXP);
@@ -435,67 +505,49 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       adv_mean = (float)mean;
       adv_std = (float)sqrt((s2 - cnt * mean * mean) / (cnt - 1.0));
     }
+    const float adv_inv_std = 1.f / adv_std;
     double sc[6] = {0, 0, 0, 0, 0, 0};
     float db3[15];
 #pragma unroll
     for (int a = 0; a < 15; ++a) db3[a] = 0.f;
 
+    auto epi_arrive = [&]() {  // -> issuer: "this thread's share of the slot's next stage inputs is in shared memory"
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(bar_ready);
+    };
     auto wait_chain = [&]() {
       mbar_wait(bar_chain, ph_chain);
       ph_chain ^= 1u;
       tc_fence_after_sync();
     };
-    // tanh layer epilogue: Z (TMEM) * unscale + bias -> tanh -> fp32 copy back to TMEM (for tanh') + fp16 splits
-    auto act_epilogue = [&](uint32_t tm_col, const float* bias, float unscale, uint32_t dst_buf) {
-      uint32_t v[16];
-      tmem_ld16(tmem + lane_addr + tm_col + c0, v);
-      tmem_wait_ld();
+    // tanh layer epilogue: Z (TMEM) * unscale + bias -> tanh -> [fp32 copy back to TMEM for tanh'] + fp16 splits
+    auto act_epilogue = [&](uint32_t tm_col, const float* bias, float unscale, uint32_t dst_buf, bool keep_fp32) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(tanhf(fmaf(__uint_as_float(v[j]), unscale, bias[c0 + j])));
-      if (BACKWARD) t2_tmem_st16(tmem + lane_addr + tm_col + c0, v);
+      for (int sub = 0; sub < 2; ++sub) {  // 16 columns at a time keeps the live register set small
+        const int cs = c0 + 16 * sub;
+        uint32_t v[16];
+        tmem_ld16(tz + tm_col + cs, v);
+        tmem_wait_ld();
+        float nan_probe = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        float x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * ch + j]) * sH;
-        if (out_of_range8(x)) bad = true;  // NaN pre-activation
-        store_chunk2(sm, dst_buf, r, (c0 >> 3) + ch, x);
-      }
-      if (BACKWARD) tmem_wait_st();
-    };
-    // backward epilogue: dZ (scaled) = dH_acc * unscale * (1 - H^2)  -> fp16 splits in the dZ buffer
-    auto dz_epilogue = [&](uint32_t tm_dh, uint32_t tm_h, float unscale, uint32_t dst_buf) {
-      uint32_t g[16], h[16];
-      tmem_ld16(tmem + lane_addr + tm_dh + c0, g);
-      tmem_ld16(tmem + lane_addr + tm_h + c0, h);
-      tmem_wait_ld();
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        float x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float hv = __uint_as_float(h[8 * ch + j]);
-          x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * (1.f - hv * hv);
+        for (int j = 0; j < 16; ++j) {
+          const float h = tanhf(fmaf(__uint_as_float(v[j]), unscale, bias[cs + j]));
+          nan_probe += h;
+          v[j] = __float_as_uint(h);
         }
-        if (out_of_range8(x)) bad = true;
-        store_chunk2(sm, dst_buf, r, (c0 >> 3) + ch, x);
+        if (nan_probe != nan_probe) bad = true;  // |tanh| <= 1: only a NaN pre-activation can break the range
+        if (keep_fp32) t2_tmem_st16(tz + tm_col + cs, v);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * ch + j]) * sH;
+          store_chunk2(sm, so + dst_buf, r, (cs >> 3) + ch, x);
+        }
       }
+      if (keep_fp32) tmem_wait_st();
     };
-
-    const float* s_stage = reinterpret_cast<const float*>(sm + S2_STAGE);
-    // stage one tile's observations (contiguous rows_here*n_in floats, 16-byte aligned) with cp.async; warps 4..15
-    auto stage_obs = [&](long long t) {
-      if (part != 0 && t < num_tiles) {
-        const long long r0 = t * T2_ROWS;
-        const long long rows_here = (p.n_rows - r0) < T2_ROWS ? (p.n_rows - r0) : T2_ROWS;
-        const int n16 = (int)((rows_here * n_in * 4 + 15) / 16);  // the obs buffer is padded to 16 bytes by the caller
-        const char* g = reinterpret_cast<const char*>(p.obs + r0 * n_in);
-        for (int i = tid - 128; i < n16; i += T2_EPI_THREADS - 128) t2_cp_async16(base + S2_STAGE + 16 * i, g + 16 * (size_t)i);
-      }
-      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-    };
-    stage_obs(blockIdx.x);
-    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");
 
 #ifdef B200RL_TC_TIMING
     unsigned long long tacc[16];
@@ -503,39 +555,46 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     long long tlast = clock64();
 #endif
     bool first = true;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (long long k = slot; k < cta_tiles; k += 2) {
+      const long long tile = blockIdx.x + k * gridDim.x;
       const long long row = tile * T2_ROWS + r;
       const bool valid = row < p.n_rows;
 
-      // ---- E0: observations (fp32 staging -> scaled fp16 splits, cols 0..31 of XD; 8 columns per thread) ----
-      if (BACKWARD && !first) {  // the previous tile's weight-gradient MMAs still read XD / H1 / H2 / dZ
-        mbar_wait(bar_off, ph_off);
-        ph_off ^= 1u;
-        tc_fence_after_sync();
-      }
-      first = false;
-      T2_T(12);
+      // ---- E0: observations (global fp32 -> scaled fp16 splits, cols 0..31 of XD; 16 columns per thread) ----
       {
-        const float* src = s_stage + r * n_in;
-        float x[8];
+        float x0[8], x1[8];
+        const float* src = p.obs + row * n_in + 16 * half;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int c = 8 * part + j;
-          x[j] = (valid && c < n_in) ? src[c] * sX : 0.f;
+          x0[j] = (valid && 16 * half + j < n_in) ? __ldg(src + j) : 0.f;
+          x1[j] = (valid && 16 * half + 8 + j < n_in) ? __ldg(src + 8 + j) : 0.f;
         }
-        if (out_of_range8(x)) bad = true;
-        store_chunk2(sm, S2_XD, r, part, x);
+        if (BACKWARD && !first) {  // the slot's previous tile: dW1 still reads XD and H1 (dZ1)
+          mbar_wait(bar_off, ph_off);
+          ph_off ^= 1u;
+          tc_fence_after_sync();
+        }
+        first = false;
+        T2_T(12);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          x0[j] *= sX;
+          x1[j] *= sX;
+        }
+        if (out_of_range8(x0) || out_of_range8(x1)) bad = true;
+        store_chunk2(sm, so + S2_XD, r, 2 * half, x0);
+        store_chunk2(sm, so + S2_XD, r, 2 * half + 1, x1);
       }
       T2_T(0);
       epi_arrive();
       wait_chain();  // F1
       T2_T(1);
-      act_epilogue(M2_Z1, s_bias, s_scale[SC_U1], S2_H1);
+      act_epilogue(M2_Z1, s_bias, s_scale[SC_U1], S2_H1, BACKWARD);
       T2_T(2);
       epi_arrive();
       wait_chain();  // F2
       T2_T(3);
-      act_epilogue(M2_Z2, s_bias + 64, s_scale[SC_U2], S2_H2);
+      act_epilogue(M2_ZB, s_bias + 64, s_scale[SC_U2], S2_H2, false);
       T2_T(4);
       epi_arrive();
 
@@ -543,7 +602,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       float pf_act[15], pf_adv = 0.f, pf_old = 0.f, pf_tgt = 0.f;
 #pragma unroll
       for (int a = 0; a < 15; ++a) pf_act[a] = 0.f;
-      if (part == 0 && valid) {
+      if (half == 0 && valid) {
         if (p.dist == B200RL_DIST_GAUSSIAN) {
 #pragma unroll
           for (int a = 0; a < 15; ++a)
@@ -554,15 +613,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         if (p.loss != B200RL_LOSS_EVAL && p.adv_raw != nullptr) pf_adv = __ldg(p.adv_raw + row);
         if (p.old_logp != nullptr) pf_old = __ldg(p.old_logp + row);
         if (p.loss == B200RL_LOSS_MSE) pf_tgt = __ldg(p.target + row);
+      } else if (half == 1) {  // idle during the loss epilogue: pull the slot's next observations towards L2
+        const long long nrow = row + 2 * (long long)gridDim.x * T2_ROWS;
+        if (nrow < p.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obs + nrow * n_in));
       }
       wait_chain();  // F3
       T2_T(5);
 
-      // ---- E3: warps 4..15 fetch the next tile's observations; warps 0..3 do the distribution / loss epilogue ----
-      stage_obs(tile + gridDim.x);
-      if (part == 0) {
+      // ---- E3: distribution / loss epilogue, one row per thread (warps 0..3 of the slot) ----
+      if (half == 0) {
         uint32_t o[16];
-        tmem_ld16(tmem + lane_addr + M2_OUT, o);
+        tmem_ld16(tz + M2_OUT, o);
         tmem_wait_ld();
         float out[16], dout[16];
         const float u3 = s_scale[SC_U3];
@@ -591,11 +652,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
 #pragma unroll
               for (int a = 0; a < 15; ++a)
                 if (a < A_out) {
-                  const float var = s_dist[a], lsc = s_dist[16 + a];
+                  const float lsc = s_dist[16 + a];
                   const float d = pf_act[a] - out[a];
-                  lp += -(d * d) / (2.f * var) - lsc - T2_LOG_SQRT_2PI;  // torch Normal.log_prob
-                  ent += T2_ENT_CONST + lsc;                             // torch Normal.entropy
-                  dlp[a] = d / var;
+                  lp += -(d * d) * s_dist[32 + a] - lsc - T2_LOG_SQRT_2PI;  // torch Normal.log_prob
+                  ent += T2_ENT_CONST + lsc;                                // torch Normal.entropy
+                  dlp[a] = d * s_dist[48 + a];
                 }
             } else {
               float m = out[0];
@@ -622,7 +683,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
             float adv = 0.f, oldlp = 0.f;
             if (p.loss != B200RL_LOSS_EVAL) {
               adv = pf_adv;
-              if (p.adv_stats != nullptr) adv = (adv - adv_mean) / adv_std;  // utils.py:91
+              if (p.adv_stats != nullptr) adv = (adv - adv_mean) * adv_inv_std;  // utils.py:91
             }
             if (p.old_logp != nullptr) oldlp = pf_old;
             if (p.loss == B200RL_LOSS_PPO_CLIP) {  // ppo.py:245-255
@@ -660,48 +721,92 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
             x1[j] = j < 7 ? dout[8 + j] * sG : 1.0f;  // ones column (col 47): db1 / db2 fall out of the dW products
           }
           if (out_of_range8(x0) || out_of_range8(x1)) bad = true;
-          store_chunk2(sm, S2_XD, r, 4, x0);  // cols 32..39
-          store_chunk2(sm, S2_XD, r, 5, x1);  // cols 40..47
+          store_chunk2(sm, so + S2_XD, r, 4, x0);  // cols 32..39
+          store_chunk2(sm, so + S2_XD, r, 5, x1);  // cols 40..47
         }
       }
       T2_T(6);
       if (BACKWARD) {
         epi_arrive();
-        wait_chain();  // dH2
+        wait_chain();  // dH2 (and dW3: H2 may be overwritten now)
         T2_T(7);
-        dz_epilogue(M2_DH2, M2_Z2, s_scale[SC_UH2], S2_DZ2);
+        // dZ2 (scaled) = dH2_acc * 2^-ew3 * (1 - H2^2), H2 re-read from its fp16 splits, written in place
+        {
+          const float unscale = s_scale[SC_UH2], hh = pow2i(-2 * T2_H_EXP);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int cs = c0 + 16 * sub;
+            uint32_t g[16];
+            tmem_ld16(tz + M2_ZB + cs, g);
+            tmem_wait_ld();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              float x[8];
+              load_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * fmaf(-(x[j] * hh), x[j], 1.f);
+              if (out_of_range8(x)) bad = true;
+              store_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
+            }
+          }
+        }
         T2_T(8);
         epi_arrive();
-        wait_chain();  // dH1
+        wait_chain();  // dH1 (and dW2 / db2: H1 may be overwritten now)
         T2_T(9);
-        dz_epilogue(M2_DH1, M2_Z1, s_scale[SC_UH1], S2_DZ1);
+        // dZ1 (scaled) = dH1_acc * 2^-ew2 * (1 - H1^2), H1 kept as fp32 in tensor memory, written over H1
+        {
+          const float unscale = s_scale[SC_UH1];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int cs = c0 + 16 * sub;
+            uint32_t g[16], h[16];
+            tmem_ld16(tz + M2_ZB + cs, g);
+            tmem_ld16(tz + M2_Z1 + cs, h);
+            tmem_wait_ld();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+              float x[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float hv = __uint_as_float(h[8 * ch + j]);
+                x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * (1.f - hv * hv);
+              }
+              if (out_of_range8(x)) bad = true;
+              store_chunk2(sm, so + S2_H1, r, (cs >> 3) + ch, x);
+            }
+          }
+        }
         T2_T(10);
         epi_arrive();  // -> dW1 / db1, completion tracked by bar_off
-      } else {
-        // forward only: the next tile may not overwrite XD / the staging buffer before everyone is done with them
-        tc_fence_before_sync();
-        asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-        tc_fence_after_sync();
       }
     }
-
 #ifdef B200RL_TC_TIMING
     if (tid == 0 && blockIdx.x == 0 && BACKWARD)
       for (int i = 0; i < 16; ++i) g_tc2_t[i] = tacc[i];
 #endif
+
     // ---- per-CTA results ----
-    if (BACKWARD) {
-      mbar_wait(bar_off, ph_off);  // all weight-gradient MMAs of the last tile have retired
+    if (BACKWARD && !first) {  // this slot's last dW1 (slots that had no tile never armed the barrier)
+      mbar_wait(bar_off, ph_off);
       tc_fence_after_sync();
+    }
+    tc_fence_before_sync();
+    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // both slots: every MMA of the CTA has retired
+    tc_fence_after_sync();
+    if (BACKWARD) {
       // stacked accumulators: lanes 0..63 = h-split half (partial row 2b), lanes 64..127 = l-split half (row 2b+1)
+      const int part = warp >> 2;  // 0..3: which accumulator columns this warp moves
       float* dst = p.partials + ((size_t)blockIdx.x * 2 + (q >> 1)) * p.P;
       const int m = 32 * (q & 1) + lane;  // feature index
+      const uint32_t ta = tmem + lane_addr;
       uint32_t v[16];
       if (part < 2) {  // dW2 [64 o][64 i]: columns 32*part .. +31
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           const int cc = 32 * part + 16 * cb;
-          tmem_ld16(tmem + lane_addr + M2_DW2 + cc, v);
+          tmem_ld16(ta + M2_DW2 + cc, v);
           tmem_wait_ld();
           const float u = s_scale[SC_OW2];
 #pragma unroll
@@ -710,7 +815,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       } else if (part == 2) {  // dW1 [64 o][32 i] in cols 0..31, db1 in col 47
 #pragma unroll
         for (int cb = 0; cb < 3; ++cb) {
-          tmem_ld16(tmem + lane_addr + M2_DW1 + 16 * cb, v);
+          tmem_ld16(ta + M2_DW1 + 16 * cb, v);
           tmem_wait_ld();
           if (cb < 2) {
             const float u = s_scale[SC_OW1];
@@ -722,58 +827,55 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
           }
         }
       } else {  // dW3^T [64 i][16 o] and db2 (col 15 = sum_r dZ2[r][o])
-        tmem_ld16(tmem + lane_addr + M2_DW3, v);
+        tmem_ld16(ta + M2_DW3, v);
         tmem_wait_ld();
         const float u = s_scale[SC_OW3];
 #pragma unroll
         for (int a = 0; a < 15; ++a)
           if (a < A_out) dst[p.w_off[2] + a * 64 + m] = __uint_as_float(v[a]) * u;
-        tmem_ld16(tmem + lane_addr + M2_DB2, v);
+        tmem_ld16(ta + M2_DB2, v);
         tmem_wait_ld();
         dst[p.b_off[1] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
       }
       // db3: fixed-order reduction of the per-row accumulators (true scale, fp32 registers)
-      if (part == 0) {
+      if (half == 0) {
 #pragma unroll
         for (int a = 0; a < 15; ++a) {
           float s = db3[a];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) s_db3[q * 16 + a] = s;
+          if (lane == 0) s_db3[(slot * 4 + q) * 16 + a] = s;
         }
+      }
+    }
+    if (p.scalar_partials != nullptr && half == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double v = warp_sum(sc[k]);
+        if (lane == 0) s_sc[k * 8 + slot * 4 + q] = v;
       }
     }
     asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");
     if (BACKWARD && tid < A_out) {
       float s = 0.f;
-      for (int w4 = 0; w4 < 4; ++w4) s += s_db3[w4 * 16 + tid];
+      for (int w8 = 0; w8 < 8; ++w8) s += s_db3[w8 * 16 + tid];
       p.partials[((size_t)blockIdx.x * 2) * p.P + p.b_off[2] + tid] = s;
       p.partials[((size_t)blockIdx.x * 2 + 1) * p.P + p.b_off[2] + tid] = 0.f;
     }
-    if (p.scalar_partials != nullptr) {
-      if (part == 0) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const double v = warp_sum(sc[k]);
-          if (lane == 0) s_sc[k][q] = v;
-        }
-      }
-      asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-      if (tid < B200RL_N_SCALARS) {
-        double t = 0.0;
-        if (tid < 6)
-          for (int w4 = 0; w4 < 4; ++w4) t += s_sc[tid][w4];
-        p.scalar_partials[((size_t)blockIdx.x * 2) * B200RL_N_SCALARS + tid] = t;
-        p.scalar_partials[((size_t)blockIdx.x * 2 + 1) * B200RL_N_SCALARS + tid] = 0.0;
-      }
+    if (p.scalar_partials != nullptr && tid < B200RL_N_SCALARS) {
+      double t = 0.0;
+      if (tid < 6)
+        for (int w8 = 0; w8 < 8; ++w8) t += s_sc[tid * 8 + w8];
+      p.scalar_partials[((size_t)blockIdx.x * 2) * B200RL_N_SCALARS + tid] = t;
+      p.scalar_partials[((size_t)blockIdx.x * 2 + 1) * B200RL_N_SCALARS + tid] = 0.0;
     }
-    if (bad) s_bad = 1;
+    if (bad) *s_bad = 1;
   }
 
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
-  if (tid == 0 && s_bad != 0) *p.status = p.seq;  // this launch is redone by the bf16 x 3 kernel queued behind it
+  if (tid == 0 && *s_bad != 0) *p.status = p.seq;  // this launch is redone by the bf16 x 3 kernel queued behind it
   if (warp == T2_EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
@@ -892,7 +994,7 @@ int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStrea
 
 #ifdef B200RL_TC_TIMING
 extern "C" int b200rl_debug_tc2_timing(unsigned long long* out16) {
-  return (int)cudaMemcpyFromSymbol(out16, b200rl::g_tc2_t, sizeof(unsigned long long) * 16);
+  return (int)cudaMemcpyFromSymbol(out16, b200rl::g_tc2_t, sizeof(unsigned long long) * 24);
 }
 #endif
 
