@@ -408,13 +408,18 @@ def main():
             "config": workload_config(world, E, T),
             "e2e": {"value": e2e, "unit": "transitions/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
+            "dtype_note": "fp32 semantics (1e-5 parity vs the float32 reference); tensor-core products are 3 fp16 MMAs "
+                          "on two-way fp16 splits with fp32 accumulation, range-checked with a bf16x3 re-run",
+            "tc_wide_range_reruns": int(_lib.load().b200rl_tc_fallback_count()),
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": {"kernel": "mlp_tc_kernel<true> (tcgen05 policy fwd+loss+bwd, one launch per policy step)",
+            "roofline": {"kernel": "mlp_tc2_kernel<true> (tcgen05 fp16x2 policy fwd+loss+bwd, one launch per policy step; "
+                                   "timed with the predicated wide-range re-run queued behind it)",
                          "bound": "tensor", "achieved": tf_pol, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                          "frac": tf_pol / pk["tf_sust"], "traffic": None,
                          "note": f"fp32-equivalent algorithmic FLOPs ({FLOP_POLICY_STEP}/row) over the CUDA-event "
-                                 f"launch time; peak = bf16 sustained GEMM ({pk['src']})",
+                                 f"launch time; peak = 16-bit dense sustained GEMM ({pk['src']}); the kernel executes 3 fp16 MMAs per "
+                                 f"logical fp32 product",
                          "ms_per_launch": ms_pol},
             "roofline_value_kernel": {"bound": "tensor", "achieved": tf_val, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                                       "frac": tf_val / pk["tf_sust"], "ms_per_launch": ms_val},

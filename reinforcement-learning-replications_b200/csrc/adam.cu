@@ -8,24 +8,56 @@
 
 namespace b200rl {
 
-// grad[p] = sum over CTAs (ascending) of partials[c][p]; scalars[k] likewise.  Fixed order => run-to-run identical.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials,
-                                                              const double* __restrict__ scalar_partials, int grid,
-                                                              long long n_params, float* __restrict__ grad,
-                                                              double* __restrict__ scalars, int grad_tail,
-                                                              const int* __restrict__ skip_flag) {
+// grad[p] = sum over partial rows c of partials[c][p]; scalars[k] likewise.  The order is FIXED (independent of timing
+// and of the launch geometry of the producer), so gradients are run-to-run identical: a block owns 32 parameters,
+// warp w adds rows w, w+8, w+16, ... with four interleaved accumulators (independent loads in flight), and the eight
+// warp sums are added in warp order.
+constexpr int RP_WARPS = 8;
+__global__ void __launch_bounds__(RP_WARPS * 32) reduce_partials_kernel(const float* __restrict__ partials,
+                                                                        const double* __restrict__ scalar_partials,
+                                                                        int grid, long long n_params,
+                                                                        float* __restrict__ grad,
+                                                                        double* __restrict__ scalars, int grad_tail,
+                                                                        const int* __restrict__ skip_flag) {
   if (skip_flag != nullptr && *skip_flag != 0) return;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (partials != nullptr && p < n_params) {
-    float s = 0.f;
-    for (int c = 0; c < grid; ++c) s += partials[(size_t)c * n_params + p];
-    grad[p] = s;
+  __shared__ float part[RP_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long p = (long long)blockIdx.x * 32 + lane;
+  if (partials != nullptr) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (p < n_params) {
+      const float* q = partials + p;
+      int c = warp;
+      for (; c + 3 * RP_WARPS < grid; c += 4 * RP_WARPS) {
+        s0 += q[(size_t)c * n_params];
+        s1 += q[(size_t)(c + RP_WARPS) * n_params];
+        s2 += q[(size_t)(c + 2 * RP_WARPS) * n_params];
+        s3 += q[(size_t)(c + 3 * RP_WARPS) * n_params];
+      }
+      for (; c < grid; c += RP_WARPS) s0 += q[(size_t)c * n_params];
+    }
+    part[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0 && p < n_params) {
+      float s = part[0][lane];
+#pragma unroll
+      for (int w = 1; w < RP_WARPS; ++w) s += part[w][lane];
+      grad[p] = s;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x < B200RL_N_SCALARS && scalar_partials != nullptr) {
+  if (blockIdx.x == 0 && scalar_partials != nullptr) {  // scalars: 32 row classes x 8 scalars, then classes in order
+    __shared__ double spart[RP_WARPS * 4][B200RL_N_SCALARS];
+    const int k = lane & 7, cls = warp * 4 + (lane >> 3);
     double s = 0.0;
-    for (int c = 0; c < grid; ++c) s += scalar_partials[(size_t)c * B200RL_N_SCALARS + threadIdx.x];
-    if (scalars != nullptr) scalars[threadIdx.x] = s;
-    if (grad_tail) grad[n_params + threadIdx.x] = (float)s;  // piggy-backed on the gradient all-reduce
+    for (int c = cls; c < grid; c += RP_WARPS * 4) s += scalar_partials[(size_t)c * B200RL_N_SCALARS + k];
+    spart[cls][k] = s;
+    __syncthreads();
+    if (threadIdx.x < B200RL_N_SCALARS) {
+      double t = 0.0;
+      for (int c = 0; c < RP_WARPS * 4; ++c) t += spart[c][threadIdx.x];
+      if (scalars != nullptr) scalars[threadIdx.x] = t;
+      if (grad_tail) grad[n_params + threadIdx.x] = (float)t;  // piggy-backed on the gradient all-reduce
+    }
   }
 }
 
@@ -88,8 +120,8 @@ extern "C" int b200rl_reduce_partials(const float* partials, const double* scala
                                       const int32_t* skip_flag, void* stream) {
   B200RL_REQUIRE(grid > 0 && n_params > 0, "reduce_partials: bad arguments");
   B200RL_REQUIRE((partials == nullptr && !grad_tail) || grad != nullptr, "reduce_partials: grad is NULL");
-  const int blocks = partials == nullptr ? 1 : (int)((n_params + 255) / 256);
-  reduce_partials_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, scalar_partials, grid,
+  const int blocks = partials == nullptr ? 1 : (int)((n_params + 31) / 32);
+  reduce_partials_kernel<<<blocks, RP_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(partials, scalar_partials, grid,
                                                                                 n_params, grad, scalars, grad_tail,
                                                                                 skip_flag);
   B200RL_CUDA(cudaGetLastError());
