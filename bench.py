@@ -385,8 +385,10 @@ def main():
                 "ms_per_train_call_e2e": ms_call, "train_steps_per_s_e2e": S4 / (ms_call * 1e-3),
                 "transitions_per_s_e2e": S4 * B4 / (ms_call * 1e-3),
                 "ms_per_train_call_engine": ms_dev, "train_steps_per_s_engine": S4 / (ms_dev * 1e-3),
-                "note": "e2e includes the reference-compatible host sampling (numpy RNG + Python-list gather); engine = "
-                        "one upload + 50 steps of kernels + one read-back"}
+                "note": "e2e = TD3.train(replay_buffer, 50, 256): host index draws with the reference's numpy stream, "
+                        "device-resident replay columns gathered on the GPU, CUDA-graph replay of the 50-step loop, "
+                        "parameters / Adam state synchronised back to the host modules; engine = host-staged "
+                        "minibatches: one upload + graph + one read-back"}
 
     if rank == 0:
         n_big, ms_big, gbs_big = scan_large()

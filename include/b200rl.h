@@ -304,6 +304,16 @@ int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* 
                            const float* done, const float* noise, float* q1_values, float* q2_values, float* q1_losses,
                            float* q2_losses, float* policy_losses, int32_t* n_policy_updates, void* stream);
 
+/* Same, with the minibatches gathered ON THE DEVICE from replay-buffer columns that already live in HBM
+ * (d_obs / d_next_obs [rows,O], d_act [rows,A], d_rew / d_done [rows] float32): only the indices idx [S,B] (host,
+ * int64, physical rows drawn by the host RNG exactly as replay_buffer.py:58 does) and the noise cross PCIe.
+ *   replaces: replay_buffer.py:51-74 (sample_minibatch gather) + td3.py:222-228 (tensor conversion). */
+int b200rl_offpolicy_train_gather(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S, int32_t B,
+                                  const float* d_obs, const float* d_act, const float* d_rew, const float* d_next_obs,
+                                  const float* d_done, int64_t rows, const int64_t* idx, const float* noise,
+                                  float* q1_values, float* q2_values, float* q1_losses, float* q2_losses,
+                                  float* policy_losses, int32_t* n_policy_updates, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Diagnostics (not on the product path): issue a chain of tcgen05.mma kind::tf32 instructions on a caller-supplied
  * shared-memory image and return the raw TMEM contents [128 lanes, read_cols]; tests use it to pin the descriptor

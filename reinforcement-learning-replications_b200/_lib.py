@@ -139,6 +139,9 @@ SIGNATURES = {
                                             C.POINTER(C.c_int64), C.c_void_p]),
     "b200rl_offpolicy_train": (C.c_int, [C.c_void_p, C.POINTER(OffPolicyHparams), C.c_int32, C.c_int32] +
                                [C.c_void_p] * 11 + [C.POINTER(C.c_int32), C.c_void_p]),
+    "b200rl_offpolicy_train_gather": (C.c_int, [C.c_void_p, C.POINTER(OffPolicyHparams), C.c_int32, C.c_int32] +
+                                      [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 7 +
+                                      [C.POINTER(C.c_int32), C.c_void_p]),
     "b200rl_tc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200rl_onpolicy_run_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(PpoHparams), C.c_void_p]),
 }

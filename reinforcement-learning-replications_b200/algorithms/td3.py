@@ -75,14 +75,28 @@ class _OffPolicyBase:
         # host side, same random streams as the reference: numpy RNG for the indices (replay_buffer.py:58), torch CPU
         # RNG for the target-smoothing noise (td3.py:328); the two streams are independent, so drawing all minibatches
         # first and all noise second consumes each exactly as the interleaved reference loop does.
-        mbs = [replay_buffer.sample_minibatch(B) for _ in range(S)]
         A = self.policy.network.sizes[-1] if hasattr(self.policy.network, "sizes") else describe_mlp(self.policy.network)[0][-1]
-        noise = torch.stack([torch.randn(B, A) for _ in range(S)]).numpy() if (noisy and S > 0) else None
-        stack = lambda k, dt: np.stack([np.asarray(m[k]) for m in mbs]).astype(dt) if S > 0 else np.zeros((0, B), dt)
-        obs, act = stack("observations", np.float32), stack("actions", np.float32)
-        rew = stack("rewards", np.float32)                      # rewards f64 -> .float() (td3.py:226)
-        nobs = stack("next_observations", np.float32)
-        done = stack("dones", np.float32)                       # bool -> .int() (td3.py:228), used as (1 - d)
+        device_replay = (S > 0 and getattr(self, "use_device_replay", True) and hasattr(replay_buffer, "device_columns")
+                         and hasattr(replay_buffer, "sample_indices"))
+        noise_of = lambda: torch.stack([torch.randn(B, A) for _ in range(S)]).numpy() if (noisy and S > 0) else None
+        if device_replay:
+            # device-resident replay columns: S index draws on the host (the same numpy stream as S sample_minibatch
+            # calls); the gather happens on the GPU, only indices and noise cross PCIe
+            idx = replay_buffer.physical_rows(np.stack([replay_buffer.sample_indices(B) for _ in range(S)]))
+            noise = noise_of()
+        else:
+            if S > 0 and hasattr(replay_buffer, "sample_indices") and hasattr(replay_buffer, "gather"):
+                idx_l = np.stack([replay_buffer.sample_indices(B) for _ in range(S)])
+                cols = replay_buffer.gather(idx_l)
+                stack = lambda k, dt: np.ascontiguousarray(cols[k], dtype=dt).reshape((S, B) + cols[k].shape[2:])
+            else:  # any object with the reference's sample_minibatch
+                mbs = [replay_buffer.sample_minibatch(B) for _ in range(S)]
+                stack = lambda k, dt: np.stack([np.asarray(m[k]) for m in mbs]).astype(dt) if S > 0 else np.zeros((0, B), dt)
+            noise = noise_of()
+            obs, act = stack("observations", np.float32), stack("actions", np.float32)
+            rew = stack("rewards", np.float32)                      # rewards f64 -> .float() (td3.py:226)
+            nobs = stack("next_observations", np.float32)
+            done = stack("dones", np.float32)                       # bool -> .int() (td3.py:228), used as (1 - d)
         e = self._ensure_engine(max(S, 1), B)
         lins = [describe_mlp(m.network)[3] for m in trainable + targets]
         for i, (m, l) in enumerate(zip(trainable, lins)):
@@ -90,7 +104,13 @@ class _OffPolicyBase:
             e.set_adam(i, *read_adam_state(m.optimizer, l))
         for i, l in enumerate(lins[len(trainable):]):
             e.set_params(3 + i, flat_params(l))
-        out = e.train(self._hparams(noisy, delay), obs, act, rew, nobs, done, noise) if S > 0 else None
+        if S == 0:
+            out = None
+        elif device_replay:
+            columns, rows = replay_buffer.device_columns()
+            out = e.train_gather(self._hparams(noisy, delay), columns, rows, idx, noise)
+        else:
+            out = e.train(self._hparams(noisy, delay), obs, act, rew, nobs, done, noise)
         for i, (m, l) in enumerate(zip(trainable, lins)):
             write_flat(l, e.get_params(i))
             write_adam_state(m.optimizer, l, *e.get_adam(i))

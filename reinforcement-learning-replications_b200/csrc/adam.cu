@@ -78,6 +78,8 @@ struct AdamArgs {
   int* applied_counter;
   const float* tail_src;
   double* tail_dst;
+  const float2* table;  // optional: {step_size, bc2_sqrt} read from device memory (CUDA-graph replays: the node's
+  int table_idx;        // arguments stay fixed while the host refreshes the table before each launch)
 };
 
 __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
@@ -92,14 +94,20 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
   }
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (!stop && i < a.n) {
+    float step_size = a.step_size, bc2_sqrt = a.bc2_sqrt;
+    if (a.table != nullptr) {
+      const float2 t = a.table[a.table_idx];
+      step_size = t.x;
+      bc2_sqrt = t.y;
+    }
     const float g = a.grad[i];
     float m = a.m[i], v = a.v[i];
-    m = m + a.one_minus_b1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
-    v = v * a.b2 + a.one_minus_b2 * (g * g);                // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;      // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    m = m + a.one_minus_b1 * (g - m);                     // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * a.b2 + a.one_minus_b2 * (g * g);              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / bc2_sqrt + a.eps;      // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
     a.m[i] = m;
     a.v[i] = v;
-    a.params[i] = a.params[i] - a.step_size * (m / denom);  // param.addcdiv_(exp_avg, denom, value=-step_size)
+    a.params[i] = a.params[i] - step_size * (m / denom);  // param.addcdiv_(exp_avg, denom, value=-step_size)
   }
   // every CTA evaluated `stop` from the same inputs; the flag is written by the LAST CTA only after all read it:
   // other CTAs never re-read it inside this launch, and later launches are stream-ordered behind this one.
@@ -158,9 +166,39 @@ extern "C" int b200rl_adam_step(float* params, const float* grad, float* exp_avg
   a.kl_limit = kl_limit;
   a.stop_flag = stop_flag;
   a.applied_counter = applied_counter;
+  a.table = nullptr;
+  a.table_idx = 0;
   const int blocks = (int)((n_params + 255) / 256);
   adam_step_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   B200RL_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
 }
+
+namespace b200rl {
+// torch's host-side scalar math for step `step` (see b200rl_adam_step): {lr / (1 - beta1^t), sqrt(1 - beta2^t)}
+void adam_scalars(int64_t step, double lr, double beta1, double beta2, float* step_size, float* bc2_sqrt) {
+  *step_size = (float)(lr / (1.0 - pow(beta1, (double)step)));
+  *bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+}
+// Adam step whose two step-dependent scalars come from table[idx] in device memory (off-policy engine, graph replay)
+int adam_step_table(float* params, const float* grad, float* m, float* v, int64_t n, const float2* table, int idx,
+                    double beta1, double beta2, double eps, cudaStream_t s) {
+  AdamArgs a{};
+  a.params = params;
+  a.grad = grad;
+  a.m = m;
+  a.v = v;
+  a.n = n;
+  a.one_minus_b1 = (float)(1.0 - beta1);
+  a.b2 = (float)beta2;
+  a.one_minus_b2 = (float)(1.0 - beta2);
+  a.eps = (float)eps;
+  a.table = table;
+  a.table_idx = idx;
+  adam_step_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(a);
+  B200RL_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+}  // namespace b200rl

@@ -19,7 +19,7 @@
 namespace b200rl {
 
 constexpr int GT = 32;   // output tile (256x256 outputs -> 64 CTAs; the batch is small, parallelism matters more than reuse)
-constexpr int GK = 16;   // k tile
+constexpr int GK = 32;   // k tile
 constexpr int GTHREADS = 256;
 
 __device__ __forceinline__ float op_act(float z, int kind) {
@@ -35,7 +35,8 @@ __device__ __forceinline__ float op_act_prime(float y, int kind) {  // derivativ
 
 // MODE 0 (NT): C[M,N] = act(A[M,K] * B[N,K]^T + bias[N])              forward: A = X, B = W [out,in]
 // MODE 1 (NN): C[M,N] = (A (.) act'(Y))[M,K] * B[K,N]                  dX = dZ * W,   A = dY, Y = layer output
-// MODE 2 (TN): C[M,N] = (A (.) act'(Y))[K,M]^T * B[K,N]                dW = dZ^T * X, A = dY [rows, out]
+// MODE 2 (TN): C[M,N] = (A (.) act'(Y))[K,M]^T * B[K,N]                dW = dZ^T * X, A = dY [rows, out];
+//              and, when dbias is set, dbias[M] = column sums of (A (.) act'(Y)) -- the bias gradient rides along
 // All matrices row-major with explicit leading dimensions.  Y (same shape / ld as A) may be NULL (no derivative).
 struct GemmArgs {
   const float* A; int lda;
@@ -44,55 +45,72 @@ struct GemmArgs {
   const float* bias;
   const float* Y; int ldy; int act;  // MODE 0: output activation; MODE 1/2: activation whose derivative gates A
   int M, N, K;
+  float* dbias;                      // MODE 2 only
 };
 
+// These GEMMs are tiny (256 x 256 x 256) and sit on a long dependency chain, so latency is what counts: the next k-tile
+// is fetched into registers (coalesced along the contiguous dimension of each operand) while the current one is
+// multiplied out of shared memory.
 template <int MODE>
 __global__ void __launch_bounds__(GTHREADS) gemm_kernel(const GemmArgs g) {
-  __shared__ float As[GK][GT + 4], Bs[GK][GT + 4];
+  __shared__ float As[GK][GT + 2], Bs[GK][GT + 2];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
   const int tm = (tid / 16) * 2, tn = (tid % 16) * 2;  // 16 x 16 threads, 2 x 2 outputs each
-  float acc[2][2];
+  constexpr int PER = GK * GT / GTHREADS;               // elements of each operand tile per thread (4)
+  float ra[PER], rb[PER];
+  // element e of a tile handled by this thread: idx = tid + e * GTHREADS; (hi, lo) = (idx / 32, idx % 32) with `lo`
+  // running along the operand's contiguous dimension
+  auto fetch = [&](int k0) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < g.K; k0 += GK) {
-    // stage A^T-style: As[k][m], Bs[k][n]
-    for (int idx = tid; idx < GK * GT; idx += GTHREADS) {
-      int k, m;
-      if (MODE == 2) { k = idx / GT; m = idx % GT; } else { m = idx / GK; k = idx % GK; }
-      const int gm = m0 + m, gk = k0 + k;
-      float a = 0.f;
-      if (gm < g.M && gk < g.K) {
-        if (MODE == 2) {
-          a = g.A[(size_t)gk * g.lda + gm];
-          if (g.Y) a *= op_act_prime(g.Y[(size_t)gk * g.ldy + gm], g.act);
-        } else {
-          a = g.A[(size_t)gm * g.lda + gk];
-          if (MODE == 1 && g.Y) a *= op_act_prime(g.Y[(size_t)gm * g.ldy + gk], g.act);
+    for (int e = 0; e < PER; ++e) {
+      const int idx = tid + e * GTHREADS, hi = idx >> 5, lo = idx & 31;
+      {  // A
+        const int k = MODE == 2 ? hi : lo, m = MODE == 2 ? lo : hi;
+        const int gm = m0 + m, gk = k0 + k;
+        float a = 0.f;
+        if (gm < g.M && gk < g.K) {
+          const size_t ia = MODE == 2 ? (size_t)gk * g.lda + gm : (size_t)gm * g.lda + gk;
+          a = g.A[ia];
+          if (MODE != 0 && g.Y) a *= op_act_prime(g.Y[MODE == 2 ? (size_t)gk * g.ldy + gm : (size_t)gm * g.ldy + gk], g.act);
         }
+        ra[e] = a;
       }
-      As[k][m] = a;
+      {  // B
+        const int k = MODE == 0 ? lo : hi, n = MODE == 0 ? hi : lo;
+        const int gn = n0 + n, gk = k0 + k;
+        float b = 0.f;
+        if (gn < g.N && gk < g.K) b = MODE == 0 ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn];
+        rb[e] = b;
+      }
     }
-    for (int idx = tid; idx < GK * GT; idx += GTHREADS) {
-      int k, n;
-      if (MODE == 0) { n = idx / GK; k = idx % GK; } else { k = idx / GT; n = idx % GT; }
-      const int gn = n0 + n, gk = k0 + k;
-      float b = 0.f;
-      if (gn < g.N && gk < g.K) b = (MODE == 0) ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn];
-      Bs[k][n] = b;
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      const int idx = tid + e * GTHREADS, hi = idx >> 5, lo = idx & 31;
+      if (MODE == 2) As[hi][lo] = ra[e]; else As[lo][hi] = ra[e];
+      if (MODE == 0) Bs[lo][hi] = rb[e]; else Bs[hi][lo] = rb[e];
     }
+  };
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float colsum[2] = {0.f, 0.f};
+  fetch(0);
+  for (int k0 = 0; k0 < g.K; k0 += GK) {
+    stash();
     __syncthreads();
+    if (k0 + GK < g.K) fetch(k0 + GK);  // in flight while this tile is multiplied
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
       const float2 av = *reinterpret_cast<const float2*>(&As[k][tm]);
       const float2 bv = *reinterpret_cast<const float2*>(&Bs[k][tn]);
       const float ar[2] = {av.x, av.y}, br[2] = {bv.x, bv.y};
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i) {
+        if (MODE == 2) colsum[i] += ar[i];
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
     }
     __syncthreads();
   }
@@ -107,6 +125,11 @@ __global__ void __launch_bounds__(GTHREADS) gemm_kernel(const GemmArgs g) {
         g.C[(size_t)gm * g.ldc + gn] = v;
       }
     }
+  if (MODE == 2 && g.dbias != nullptr && blockIdx.x == 0 && tn == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (m0 + tm + i < g.M) g.dbias[m0 + tm + i] = colsum[i];
+  }
 }
 
 // db[n] = sum_rows dY[r][n] * act'(Y[r][n])
@@ -139,6 +162,14 @@ __global__ void target_action_kernel(float* a, const float* eps, int n, float si
   float e = sigma * eps[i];
   e = fminf(fmaxf(e, -clipv), clipv);
   a[i] = fminf(fmaxf(a[i] + e, -limit), limit);
+}
+
+// staged[i, :] = table[idx[i], :]  (replay-buffer gather; one launch per column)
+__global__ void gather_rows_kernel(const float* table, const long long* idx, int width, long long n_out, float* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out * width) return;
+  const long long r = i / width;
+  out[i] = table[idx[r] * width + (i - r * width)];
 }
 
 // y = r + gamma * (1 - d) * min(q1t, q2t)   (td3.py:337-339; ddpg.py:280: single target Q)
@@ -211,6 +242,16 @@ struct b200rl_offpolicy {
   float *dbuf0 = nullptr, *dbuf1 = nullptr;  // gradient ping-pong [B, maxw]
   // outputs
   float *out_q1 = nullptr, *out_q2 = nullptr, *out_l1 = nullptr, *out_l2 = nullptr, *out_lp = nullptr;
+  // CUDA graph of the S-step loop: node arguments are fixed per (S, B, hyper-parameters); what changes between calls
+  // (minibatch contents, Adam bias-correction scalars) lives in device buffers refreshed before each launch
+  long long* idx = nullptr;      // [max_steps * max_minibatch] replay rows of train_gather
+  float2* adam_tab = nullptr;    // [3][max_steps] {lr / (1 - beta1^t), sqrt(1 - beta2^t)} for policy, Q1, Q2
+  float2* h_adam_tab = nullptr;  // pinned mirror
+  cudaStream_t gs = nullptr;     // internal stream (the caller's may be the legacy default stream: not capturable)
+  cudaEvent_t ev = nullptr;
+  cudaGraphExec_t graph = nullptr;
+  b200rl_offpolicy_hparams graph_hp;
+  int graph_S = -1, graph_B = -1, graph_npol = 0, graph_launches = 0;
   std::vector<void*> allocs;
 };
 
@@ -269,10 +310,8 @@ int net_backward(b200rl_offpolicy* h, const NetBuf& nb, float* const* acts, cons
       g.B = acts[l]; g.ldb = nin;
       g.C = nb.grad + nb.w_off[l]; g.ldc = nin;
       g.M = nout; g.N = nin; g.K = rows;
+      g.dbias = nb.grad + nb.b_off[l];  // db = column sums of dZ, accumulated by the same kernel
       if (gemm<2>(g, s)) return 1;
-      colsum_kernel<<<(nout + 127) / 128, 128, 0, s>>>(dY, ldd, Y, nout, act, rows, nout, nb.grad + nb.b_off[l]);
-      B200RL_CUDA(cudaGetLastError());
-      count_launch(1);
     }
     if (l > 0 || dx_out) {
       float* dst = (l == 0) ? dx_out : pp[l & 1];
@@ -289,10 +328,8 @@ int net_backward(b200rl_offpolicy* h, const NetBuf& nb, float* const* acts, cons
   return 0;
 }
 
-int adam_net(NetBuf& nb, double lr, double b1, double b2, double eps, cudaStream_t s) {
-  nb.step += 1;
-  return b200rl_adam_step(nb.params, nb.grad, nb.m, nb.v, nb.P, nb.step, lr, b1, b2, eps, nullptr, 0, 1.0, 0.0, nullptr,
-                          nullptr, nullptr, nullptr, s);
+int adam_net(NetBuf& nb, const float2* table, int idx, double b1, double b2, double eps, cudaStream_t s) {
+  return adam_step_table(nb.params, nb.grad, nb.m, nb.v, nb.P, table, idx, b1, b2, eps, s);
 }
 
 }  // namespace
@@ -357,6 +394,11 @@ extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200r
   rc |= oalloc(h, &h->out_l1, S);
   rc |= oalloc(h, &h->out_l2, S);
   rc |= oalloc(h, &h->out_lp, S);
+  rc |= oalloc(h, &h->adam_tab, 3 * S);
+  rc |= oalloc(h, &h->idx, S * B);
+  if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_adam_tab), 3 * S * sizeof(float2)) != cudaSuccess) rc = 1;
+  if (!rc && cudaStreamCreateWithFlags(&h->gs, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
+  if (!rc && cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) rc = 1;
   if (rc) {
     b200rl_offpolicy_destroy(h);
     return 1;
@@ -367,6 +409,10 @@ extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200r
 
 extern "C" void b200rl_offpolicy_destroy(b200rl_offpolicy* h) {
   if (!h) return;
+  if (h->graph) cudaGraphExecDestroy(h->graph);
+  if (h->ev) cudaEventDestroy(h->ev);
+  if (h->gs) cudaStreamDestroy(h->gs);
+  if (h->h_adam_tab) cudaFreeHost(h->h_adam_tab);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -417,32 +463,13 @@ extern "C" int b200rl_offpolicy_get_adam(b200rl_offpolicy* h, int which, float* 
   return 0;
 }
 
-extern "C" int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S, int32_t B,
-                                      const float* obs, const float* act, const float* rew, const float* next_obs,
-                                      const float* done, const float* noise, float* q1_values, float* q2_values,
-                                      float* q1_losses, float* q2_losses, float* policy_losses,
-                                      int32_t* n_policy_updates, void* stream) {
-  B200RL_REQUIRE(h && hp && obs && act && rew && next_obs && done && q1_values && q1_losses && policy_losses &&
-                     n_policy_updates, "offpolicy_train: NULL argument");
-  B200RL_REQUIRE(S >= 0 && S <= h->cfg.max_steps && B >= 1 && B <= h->cfg.max_minibatch,
-                 "offpolicy_train: S=%d B=%d exceed the capacities", S, B);
+// Enqueue the S train steps on `s` (plain launches or under stream capture).  Everything that varies between calls
+// with the same (S, B, hyper-parameters) is read from device buffers: staged minibatches, Adam scalar tables.
+static int enqueue_steps(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int S, int B, cudaStream_t s,
+                         int* n_pol_out) {
   const bool td3 = h->cfg.n_q == 2;
-  B200RL_REQUIRE(!td3 || (q2_values && q2_losses), "offpolicy_train: TD3 needs the Q2 outputs");
-  B200RL_REQUIRE(!hp->use_target_noise || noise, "offpolicy_train: target noise requested but no noise given");
-  B200RL_REQUIRE(hp->policy_delay >= 1, "offpolicy_train: policy_delay must be >= 1");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int O = h->O, A = h->A;
-  const size_t SB = (size_t)S * B;
-  *n_policy_updates = 0;
-  if (S == 0) return 0;
-  // one host -> device upload of every minibatch of this train() call
-  B200RL_CUDA(cudaMemcpyAsync(h->obs, obs, SB * O * 4, cudaMemcpyHostToDevice, s));
-  B200RL_CUDA(cudaMemcpyAsync(h->act, act, SB * A * 4, cudaMemcpyHostToDevice, s));
-  B200RL_CUDA(cudaMemcpyAsync(h->rew, rew, SB * 4, cudaMemcpyHostToDevice, s));
-  B200RL_CUDA(cudaMemcpyAsync(h->nobs, next_obs, SB * O * 4, cudaMemcpyHostToDevice, s));
-  B200RL_CUDA(cudaMemcpyAsync(h->done, done, SB * 4, cudaMemcpyHostToDevice, s));
-  if (hp->use_target_noise) B200RL_CUDA(cudaMemcpyAsync(h->eps, noise, SB * A * 4, cudaMemcpyHostToDevice, s));
-
+  const int maxS = h->cfg.max_steps;
   NetBuf &pi = h->net[0], &q1 = h->net[1], &q2 = h->net[2], &pit = h->net[3], &q1t = h->net[4], &q2t = h->net[5];
   const int Lq = q1.d.n_layers, Lp = pi.d.n_layers;
   const int ew = 256;
@@ -497,7 +524,7 @@ extern "C" int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolic
       B200RL_CUDA(cudaGetLastError());
       count_launch(1);
       if (net_backward(h, qn, qa, h->dq, 1, B, true, nullptr, s)) return 1;
-      if (adam_net(qn, qi == 0 ? hp->q1_lr : hp->q2_lr, hp->q_beta1, hp->q_beta2, hp->q_eps, s)) return 1;
+      if (adam_net(qn, h->adam_tab + (size_t)(1 + qi) * maxS, st, hp->q_beta1, hp->q_beta2, hp->q_eps, s)) return 1;
     }
     // ---- delayed policy step + polyak (td3.py:244-263, 301-323; ddpg: every step) ----
     if (st % hp->policy_delay == 0) {
@@ -518,7 +545,7 @@ extern "C" int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolic
       // gradient w.r.t. Q1's input; its action columns are the gradient w.r.t. pi(s) (Q parameters frozen)
       if (net_backward(h, q1, qa, h->dq, 1, B, false, h->x_cat, s)) return 1;
       if (net_backward(h, pi, pa, h->x_cat + O, O + A, B, true, nullptr, s)) return 1;
-      if (adam_net(pi, hp->policy_lr, hp->policy_beta1, hp->policy_beta2, hp->policy_eps, s)) return 1;
+      if (adam_net(pi, h->adam_tab, n_pol, hp->policy_beta1, hp->policy_beta2, hp->policy_eps, s)) return 1;
       const float rho = (float)hp->polyak_rho, omr = (float)(1.0 - hp->polyak_rho);
       for (int k = 0; k < (td3 ? 3 : 2); ++k) {
         NetBuf& src = h->net[k];
@@ -530,6 +557,72 @@ extern "C" int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolic
       ++n_pol;
     }
   }
+  *n_pol_out = n_pol;
+  return 0;
+}
+
+// Runs the S steps on minibatches ALREADY staged in h->obs ... h->eps (stream h->gs) and reads the logs back.
+static int run_staged(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S, int32_t B, float* q1_values,
+                      float* q2_values, float* q1_losses, float* q2_losses, float* policy_losses,
+                      int32_t* n_policy_updates) {
+  const bool td3 = h->cfg.n_q == 2;
+  cudaStream_t s = h->gs;
+  const size_t SB = (size_t)S * B;
+
+  // Adam's step-dependent scalars for the steps of this call (torch's host-side double arithmetic), one small upload
+  const int maxS = h->cfg.max_steps;
+  const int n_pol_expected = (S + hp->policy_delay - 1) / hp->policy_delay;
+  for (int k = 0; k < n_pol_expected; ++k)
+    adam_scalars(h->net[0].step + k + 1, hp->policy_lr, hp->policy_beta1, hp->policy_beta2, &h->h_adam_tab[k].x,
+                 &h->h_adam_tab[k].y);
+  for (int qi = 0; qi < (td3 ? 2 : 1); ++qi)
+    for (int k = 0; k < S; ++k)
+      adam_scalars(h->net[1 + qi].step + k + 1, qi == 0 ? hp->q1_lr : hp->q2_lr, hp->q_beta1, hp->q_beta2,
+                   &h->h_adam_tab[(size_t)(1 + qi) * maxS + k].x, &h->h_adam_tab[(size_t)(1 + qi) * maxS + k].y);
+  B200RL_CUDA(cudaMemcpyAsync(h->adam_tab, h->h_adam_tab, 3 * (size_t)maxS * sizeof(float2), cudaMemcpyHostToDevice, s));
+
+  int n_pol = 0;
+  const char* genv = getenv("B200RL_OFFPOLICY_GRAPH");
+  const bool use_graph = !(genv != nullptr && genv[0] == '0');
+  if (!use_graph) {
+    if (enqueue_steps(h, hp, S, B, s, &n_pol)) return 1;
+  } else {
+    if (h->graph == nullptr || h->graph_S != S || h->graph_B != B || memcmp(&h->graph_hp, hp, sizeof(*hp)) != 0) {
+      if (h->graph) {
+        cudaGraphExecDestroy(h->graph);
+        h->graph = nullptr;
+      }
+      const int64_t l0 = launches_total();
+      B200RL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_steps(h, hp, S, B, s, &n_pol);
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(s, &g);
+      if (rc || ce != cudaSuccess || g == nullptr) {
+        if (g) cudaGraphDestroy(g);
+        if (!rc) set_error("offpolicy_train: stream capture failed: %s", cudaGetErrorString(ce));
+        return 1;
+      }
+      const cudaError_t ie = cudaGraphInstantiate(&h->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ie != cudaSuccess) {
+        h->graph = nullptr;
+        set_error("offpolicy_train: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        return 1;
+      }
+      h->graph_launches = (int)(launches_total() - l0);
+      count_launch(-h->graph_launches);  // counted per replay below
+      h->graph_S = S;
+      h->graph_B = B;
+      h->graph_hp = *hp;
+      h->graph_npol = n_pol;
+    }
+    n_pol = h->graph_npol;
+    B200RL_CUDA(cudaGraphLaunch(h->graph, s));
+    count_launch(h->graph_launches);
+  }
+  h->net[0].step += n_pol;
+  h->net[1].step += S;
+  if (td3) h->net[2].step += S;
   // one device -> host read of everything train() logs
   B200RL_CUDA(cudaMemcpyAsync(q1_values, h->out_q1, SB * 4, cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaMemcpyAsync(q1_losses, h->out_l1, (size_t)S * 4, cudaMemcpyDeviceToHost, s));
@@ -541,4 +634,76 @@ extern "C" int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolic
   B200RL_CUDA(cudaStreamSynchronize(s));
   *n_policy_updates = n_pol;
   return 0;
+}
+
+extern "C" int b200rl_offpolicy_train(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S, int32_t B,
+                                      const float* obs, const float* act, const float* rew, const float* next_obs,
+                                      const float* done, const float* noise, float* q1_values, float* q2_values,
+                                      float* q1_losses, float* q2_losses, float* policy_losses,
+                                      int32_t* n_policy_updates, void* stream) {
+  B200RL_REQUIRE(h && hp && obs && act && rew && next_obs && done && q1_values && q1_losses && policy_losses &&
+                     n_policy_updates, "offpolicy_train: NULL argument");
+  B200RL_REQUIRE(S >= 0 && S <= h->cfg.max_steps && B >= 1 && B <= h->cfg.max_minibatch,
+                 "offpolicy_train: S=%d B=%d exceed the capacities", S, B);
+  const bool td3 = h->cfg.n_q == 2;
+  B200RL_REQUIRE(!td3 || (q2_values && q2_losses), "offpolicy_train: TD3 needs the Q2 outputs");
+  B200RL_REQUIRE(!hp->use_target_noise || noise, "offpolicy_train: target noise requested but no noise given");
+  B200RL_REQUIRE(hp->policy_delay >= 1, "offpolicy_train: policy_delay must be >= 1");
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  cudaStream_t s = h->gs;  // everything runs on the engine's stream, ordered after the caller's
+  const int O = h->O, A = h->A;
+  const size_t SB = (size_t)S * B;
+  *n_policy_updates = 0;
+  if (S == 0) return 0;
+  B200RL_CUDA(cudaEventRecord(h->ev, user));
+  B200RL_CUDA(cudaStreamWaitEvent(s, h->ev, 0));
+  // one host -> device upload of every minibatch of this train() call
+  B200RL_CUDA(cudaMemcpyAsync(h->obs, obs, SB * O * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->act, act, SB * A * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->rew, rew, SB * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->nobs, next_obs, SB * O * 4, cudaMemcpyHostToDevice, s));
+  B200RL_CUDA(cudaMemcpyAsync(h->done, done, SB * 4, cudaMemcpyHostToDevice, s));
+  if (hp->use_target_noise) B200RL_CUDA(cudaMemcpyAsync(h->eps, noise, SB * A * 4, cudaMemcpyHostToDevice, s));
+
+
+  return run_staged(h, hp, S, B, q1_values, q2_values, q1_losses, q2_losses, policy_losses, n_policy_updates);
+}
+
+extern "C" int b200rl_offpolicy_train_gather(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S,
+                                             int32_t B, const float* d_obs, const float* d_act, const float* d_rew,
+                                             const float* d_next_obs, const float* d_done, int64_t rows,
+                                             const int64_t* idx, const float* noise, float* q1_values,
+                                             float* q2_values, float* q1_losses, float* q2_losses,
+                                             float* policy_losses, int32_t* n_policy_updates, void* stream) {
+  B200RL_REQUIRE(h && hp && d_obs && d_act && d_rew && d_next_obs && d_done && idx && q1_values && q1_losses &&
+                     policy_losses && n_policy_updates, "offpolicy_train_gather: NULL argument");
+  B200RL_REQUIRE(S >= 0 && S <= h->cfg.max_steps && B >= 1 && B <= h->cfg.max_minibatch,
+                 "offpolicy_train_gather: S=%d B=%d exceed the capacities", S, B);
+  const bool td3 = h->cfg.n_q == 2;
+  B200RL_REQUIRE(!td3 || (q2_values && q2_losses), "offpolicy_train_gather: TD3 needs the Q2 outputs");
+  B200RL_REQUIRE(!hp->use_target_noise || noise, "offpolicy_train_gather: target noise requested but no noise given");
+  B200RL_REQUIRE(hp->policy_delay >= 1, "offpolicy_train_gather: policy_delay must be >= 1");
+  const size_t SB = (size_t)S * B;
+  for (size_t i = 0; i < SB; ++i)
+    B200RL_REQUIRE(idx[i] >= 0 && idx[i] < rows, "offpolicy_train_gather: index %lld outside the %lld replay rows",
+                   (long long)idx[i], (long long)rows);
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  cudaStream_t s = h->gs;
+  const int O = h->O, A = h->A;
+  *n_policy_updates = 0;
+  if (S == 0) return 0;
+  B200RL_CUDA(cudaEventRecord(h->ev, user));
+  B200RL_CUDA(cudaStreamWaitEvent(s, h->ev, 0));
+  // the minibatches are gathered on the device from the replay columns: only the indices (and noise) cross PCIe
+  B200RL_CUDA(cudaMemcpyAsync(h->idx, idx, SB * sizeof(long long), cudaMemcpyHostToDevice, s));
+  if (hp->use_target_noise) B200RL_CUDA(cudaMemcpyAsync(h->eps, noise, SB * A * 4, cudaMemcpyHostToDevice, s));
+  const struct { const float* src; float* dst; int w; } cols[5] = {
+      {d_obs, h->obs, O}, {d_act, h->act, A}, {d_rew, h->rew, 1}, {d_next_obs, h->nobs, O}, {d_done, h->done, 1}};
+  for (const auto& c : cols) {
+    const long long n = (long long)SB * c.w;
+    gather_rows_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(c.src, h->idx, c.w, (long long)SB, c.dst);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
+  return run_staged(h, hp, S, B, q1_values, q2_values, q1_losses, q2_losses, policy_losses, n_policy_updates);
 }

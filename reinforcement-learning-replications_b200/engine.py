@@ -292,3 +292,18 @@ class OffPolicyEngine:
                                               _ptr(done), _ptr(noise), _ptr(q1v), _ptr(q2v), _ptr(l1), _ptr(l2), _ptr(lp),
                                               C.byref(npol), current_stream_handle()), "offpolicy_train")
         return dict(q1_values=q1v, q2_values=q2v, q1_losses=l1, q2_losses=l2, policy_losses=lp[:npol.value])
+
+    def train_gather(self, hp, columns, rows: int, idx, noise=None):
+        """Minibatches gathered on the device: ``columns`` = CUDA float32 tensors (obs [rows,O], act [rows,A], rew [rows],
+        next_obs [rows,O], done [rows]) of a device-resident replay buffer, ``idx`` [S,B] int64 physical rows (host)."""
+        idx = _c(idx, np.int64)
+        noise = None if noise is None else _c(noise, np.float32)
+        S, B = idx.shape
+        q1v, q2v = np.zeros((S, B), np.float32), np.zeros((S, B), np.float32)
+        l1, l2, lp = np.zeros(S, np.float32), np.zeros(S, np.float32), np.zeros(max(S, 1), np.float32)
+        npol = C.c_int32()
+        ptrs = [C.c_void_p(t.data_ptr()) for t in columns]
+        check(self.lib.b200rl_offpolicy_train_gather(self.h, C.byref(hp), S, B, *ptrs, int(rows), _ptr(idx), _ptr(noise),
+                                                     _ptr(q1v), _ptr(q2v), _ptr(l1), _ptr(l2), _ptr(lp), C.byref(npol),
+                                                     current_stream_handle()), "offpolicy_train_gather")
+        return dict(q1_values=q1v, q2_values=q2v, q1_losses=l1, q2_losses=l2, policy_losses=lp[:npol.value])

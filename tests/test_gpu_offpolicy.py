@@ -143,3 +143,50 @@ def test_train_vs_oracle_benchmark_shape(twin):
     for i, q in enumerate(q_nets):
         assert rel_err(flat(q.network), O.flatten_layers(nets[f"q{i + 1}"])) < 1e-4
     assert rel_err(flat(algo.target_policy.network), O.flatten_layers(nets["target_policy"])) < 1e-4
+
+
+def test_device_replay_gather_and_graph_replay_match_the_staged_path():
+    """b200rl_offpolicy_train_gather (replay columns in HBM, only indices uploaded) and the CUDA-graph replay of the
+    S-step loop give bit-identical results to host-staged minibatches run with plain launches."""
+    import os
+    from rl_replicas_b200.algorithms._onpolicy import describe_mlp, flat_params
+    from rl_replicas_b200.experience import Experience
+    rng = np.random.default_rng(3)
+    H, S, B = 64, 6, 32
+    mk = lambda sz: O.flatten_layers([(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+                                      for i, o in zip(sz[:-1], sz[1:])])
+    p0, q10, q20 = mk([O_DIM, H, H, A_DIM]), mk([O_DIM + A_DIM, H, H, 1]), mk([O_DIM + A_DIM, H, H, 1])
+    n = 3000
+    ex = Experience()
+    obs = rng.standard_normal((n + 1, O_DIM)).astype(np.float32)
+    ex.observations = [[obs[i] for i in range(n)]]
+    ex.actions = [[a for a in rng.uniform(-1, 1, (n, A_DIM)).astype(np.float32)]]
+    ex.rewards = [[float(x) for x in rng.standard_normal(n)]]
+    ex.dones = [[bool(x) for x in (rng.random(n) < 0.01)]]
+    ex.last_observations = [obs[n]]
+
+    def run(device_replay, graph):
+        os.environ["B200RL_OFFPOLICY_GRAPH"] = "1" if graph else "0"
+        algo, rb = build(True, H, p0, [q10, q20])
+        rb.add_experience(ex)
+        algo.use_device_replay = device_replay  # False: minibatches gathered on the host and uploaded
+        outs = []
+        for call in range(3):  # the 2nd and 3rd calls replay the captured graph
+            np.random.seed(10 + call)
+            torch.manual_seed(10 + call)
+            algo.train(rb, S, B)
+            outs.append(algo.last_train_output)
+        nets = [flat(m.network) for m in (algo.policy, algo.q_function_1, algo.q_function_2)]
+        return outs, nets
+
+    try:
+        ref_outs, ref_nets = run(False, False)
+        for dev, graph in ((True, True), (False, True), (True, False)):
+            outs, nets = run(dev, graph)
+            for a, b in zip(outs, ref_outs):
+                for k in a:
+                    np.testing.assert_array_equal(a[k], b[k])
+            for a, b in zip(nets, ref_nets):
+                np.testing.assert_array_equal(a, b)
+    finally:
+        os.environ.pop("B200RL_OFFPOLICY_GRAPH", None)
