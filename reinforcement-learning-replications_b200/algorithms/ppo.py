@@ -119,3 +119,25 @@ class PPO(OnPolicyTrainerMixin):
             "value_function_state_dict": self.value_function.network.state_dict(),
             "value_function_optimizer_state_dict": self.value_function.optimizer.state_dict(),
         }, model_path)
+
+    def load_model(self, model_path: str) -> int:
+        """Resume from a checkpoint written by ``save_model`` -- or by the reference's (same dictionary layout,
+        ref ppo.py:296-306; the shipped benchmarks/*/model.pt load as warm starts).  Restores both networks, both
+        optimizer states (Adam moments and step counts -- the next ``train`` continues the bias correction where the run
+        stopped) and ``current_total_steps``; returns the saved epoch.  The reference has no loader; a
+        Gaussian policy's ``log_std`` is not part of the checkpoint there either and keeps its constructor value."""
+        ckpt = torch.load(model_path, map_location="cpu", weights_only=False)
+        self.policy.network.load_state_dict(ckpt["policy_state_dict"])
+        self.value_function.network.load_state_dict(ckpt["value_function_state_dict"])
+        for module, key in ((self.policy, "policy_optimizer_state_dict"),
+                            (self.value_function, "value_function_optimizer_state_dict")):
+            state = ckpt.get(key)
+            if state and hasattr(module.optimizer, "load_state_dict") and state.get("state") is not None:
+                try:
+                    module.optimizer.load_state_dict(state)
+                except (ValueError, KeyError):  # e.g. TRPO's conjugate-gradient optimizer keeps no per-parameter state
+                    pass
+        if hasattr(self, "old_policy"):
+            self.old_policy.network.load_state_dict(self.policy.network.state_dict())  # ref ppo.py:183 invariant
+        self.current_total_steps = int(ckpt.get("total_steps", 0))
+        return int(ckpt.get("epoch", 0))

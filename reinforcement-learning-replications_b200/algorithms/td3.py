@@ -30,6 +30,19 @@ class _OffPolicyBase:
         tq = [self.target_q_function_1, self.target_q_function_2] if self.n_q == 2 else [self.target_q_function]
         return self._trainable(), [self.target_policy] + tq
 
+    def load_model(self, model_path: str) -> int:
+        """Resume from a checkpoint written by ``save_model`` or by the reference (same layout, ref td3.py:367-382 /
+        ddpg.py:295-314): trainable networks, their Adam states, the target networks; returns the saved epoch."""
+        ckpt = torch.load(model_path, map_location="cpu", weights_only=False)
+        names = ["policy"] + (["q_function_1", "q_function_2"] if self.n_q == 2 else ["q_function"])
+        trainable, targets = self._nets()
+        for name, module, target in zip(names, trainable, targets):
+            module.network.load_state_dict(ckpt[name + "_state_dict"])
+            module.optimizer.load_state_dict(ckpt[name + "_optimizer_state_dict"])
+            target.network.load_state_dict(ckpt["target_" + name + "_state_dict"])
+        self.current_total_steps = int(ckpt.get("total_steps", 0))
+        return int(ckpt.get("epoch", 0))
+
     def _make_targets(self):
         targets = [copy.deepcopy(m) for m in self._trainable()]
         for t in targets:

@@ -12,6 +12,8 @@ import numpy as np
 
 
 def pack_experience(experience) -> Dict[str, np.ndarray]:
+    if hasattr(experience, "packed"):  # PackedExperience: already in the engine's layout, zero copy
+        return experience.packed()
     lengths = np.asarray([len(r) for r in experience.rewards], dtype=np.int64)
     if lengths.size == 0 or np.any(lengths == 0):
         raise ValueError("experience must hold at least one episode and no empty episode")

@@ -9,7 +9,7 @@ from typing import Optional
 
 import numpy as np
 
-from ..experience import Experience
+from ..experience import Experience, PackedExperience
 
 
 class Sampler(ABC):
@@ -41,11 +41,31 @@ class BatchSampler(Sampler):
     ``is_continuous`` keeps the running observation (ref: batch_sampler.py:49-53).  An episode closes on
     terminated OR truncated (ref: :65) or when the epoch's last step is reached (cut-off, ``done`` stays False)."""
 
-    def __init__(self, env, seed: Optional[int] = None, is_continuous: bool = False):
+    def __init__(self, env, seed: Optional[int] = None, is_continuous: bool = False, packed: bool = False,
+                 pinned: bool = False):
         self.env = env
         self.seed = seed
         self.is_continuous = is_continuous
+        self.packed = packed  # write the rollout straight into the engine's contiguous layout (PackedExperience)
+        self.pinned = pinned
         self.observation: Optional[np.ndarray] = None
+
+    def _sample_packed(self, num_samples: int, policy) -> Experience:
+        """Same control flow as ``sample`` below, writing into a PackedExperience."""
+        exp: Optional[PackedExperience] = None
+        for step in range(num_samples):
+            observation = self.observation
+            action = policy.get_action_numpy(observation)
+            if exp is None:
+                exp = PackedExperience(num_samples, np.asarray(observation).size, np.asarray(action).size, self.pinned)
+            self.observation, reward, terminated, truncated, _ = self.env.step(action)
+            finished = terminated or truncated
+            exp.append_step(observation, action, reward, finished)
+            if finished or step == num_samples - 1:
+                exp.end_episode(self.observation)
+                if finished:
+                    self.observation, _ = self.env.reset()
+        return exp if exp is not None else Experience()
 
     def sample(self, num_samples: int, policy) -> Experience:
         exp = Experience()
@@ -53,6 +73,8 @@ class BatchSampler(Sampler):
             self.observation, _ = self.env.reset(seed=self.seed)
         elif not self.is_continuous:
             self.observation, _ = self.env.reset()
+        if self.packed:
+            return self._sample_packed(num_samples, policy)
         ep = _Episode()
         for step in range(num_samples):
             assert self.observation is not None

@@ -1,0 +1,67 @@
+"""PackedExperience: the contiguous rollout store gives the engine the same arrays as flattening the
+reference's nested lists, and keeps the nested-list API as views."""
+import numpy as np
+
+from rl_replicas_b200.packing import pack_experience
+from rl_replicas_b200.samplers import BatchSampler
+
+
+class _Env:
+    """Deterministic toy env (gymnasium protocol): episodes end after 7, 3, 12, ... steps (terminated) -- no physics."""
+
+    def __init__(self):
+        self.rng = np.random.default_rng(0)
+        self.t, self.length = 0, 7
+
+    def reset(self, seed=None):
+        self.t = 0
+        self.length = int(self.rng.integers(3, 13))
+        return self.rng.standard_normal(4).astype(np.float32), {}
+
+    def step(self, action):
+        self.t += 1
+        obs = (self.rng.standard_normal(4) + 0.1 * float(np.sum(action))).astype(np.float32)
+        return obs, float(self.rng.standard_normal()), self.t >= self.length, False, {}
+
+
+class _Policy:
+    def __init__(self):
+        self.rng = np.random.default_rng(5)
+
+    def get_action_numpy(self, observation):
+        return self.rng.uniform(-1, 1, 2).astype(np.float32)
+
+
+def test_packed_rollout_equals_flattened_nested_lists():
+    nested = BatchSampler(_Env(), seed=0).sample(100, _Policy())
+    packed = BatchSampler(_Env(), seed=0, packed=True).sample(100, _Policy())
+    a, b = pack_experience(nested), pack_experience(packed)
+    assert set(a) == set(b)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+        assert a[k].dtype == b[k].dtype
+    assert b["obs"].flags["C_CONTIGUOUS"] and b["obs"].base is not None  # a view of the backing store, not a copy
+    # nested-list API
+    assert packed.episode_lengths == nested.episode_lengths
+    np.testing.assert_allclose(packed.episode_returns, nested.episode_returns)
+    assert packed.episode_dones == nested.episode_dones
+    for ep_p, ep_n in zip(packed.observations, nested.observations):
+        np.testing.assert_array_equal(np.asarray(ep_p), np.asarray(ep_n))
+    np.testing.assert_array_equal(np.asarray(packed.flattened_next_observations),
+                                  np.asarray(nested.flattened_next_observations))
+    assert packed.flattened_rewards == nested.flattened_rewards and packed.flattened_dones == nested.flattened_dones
+
+
+def test_packed_experience_feeds_the_replay_buffer():
+    from rl_replicas_b200.replay_buffer import ReplayBuffer
+    nested = BatchSampler(_Env(), seed=0).sample(60, _Policy())
+    packed = BatchSampler(_Env(), seed=0, packed=True).sample(60, _Policy())
+    ra, rb = ReplayBuffer(), ReplayBuffer()
+    ra.add_experience(nested)
+    rb.add_experience(packed)
+    np.random.seed(1)
+    x = ra.sample_minibatch(32)
+    np.random.seed(1)
+    y = rb.sample_minibatch(32)
+    for k in x:
+        np.testing.assert_array_equal(x[k], y[k])
