@@ -61,6 +61,7 @@ constexpr uint32_t TM_Z1 = 0, TM_Z2 = 64, TM_OUT = 128, TM_DH2 = 160, TM_DH1 = 2
 
 struct TcArgs {
   int n_in, n_out;
+  int h1, h2;  // hidden widths (<= 64, zero-padded to the 64-wide buffers)
   int w_off[3], b_off[3], P;
   int loss, dist;
   long long n_rows;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
   float* s_bias = reinterpret_cast<float*>(sm + SM_BIAS);
   float* s_dist = reinterpret_cast<float*>(sm + SM_DIST);
   float* s_db3 = reinterpret_cast<float*>(sm + SM_DB3);
-  const int n_in = p.n_in, A_out = p.n_out;
+  const int n_in = p.n_in, A_out = p.n_out, h1 = p.h1, h2 = p.h2;
   // partial rows beyond this grid (the consumer was sized for mlp_tc2's two rows per CTA) contribute nothing
   for (int row = (int)gridDim.x + (int)blockIdx.x; row < p.total_rows; row += (int)gridDim.x) {
     if (BACKWARD)
@@ -244,15 +245,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
       *reinterpret_cast<__nv_bfloat16*>(sm + off + stride) = mb;
       *reinterpret_cast<__nv_bfloat16*>(sm + off + 2 * stride) = lb;
     };
-    for (int idx = tid; idx < 64 * n_in; idx += TC_THREADS)
+    for (int idx = tid; idx < h1 * n_in; idx += TC_THREADS)
       put(SM_W1, W_BUF, idx / n_in, idx % n_in, __ldg(p.params + p.w_off[0] + idx));
-    for (int idx = tid; idx < 64 * 64; idx += TC_THREADS)
-      put(SM_W2, W_BUF, idx >> 6, idx & 63, __ldg(p.params + p.w_off[1] + idx));
-    for (int idx = tid; idx < A_out * 64; idx += TC_THREADS)
-      put(SM_W3, W3_BUF, idx >> 6, idx & 63, __ldg(p.params + p.w_off[2] + idx));
+    for (int idx = tid; idx < h2 * h1; idx += TC_THREADS)
+      put(SM_W2, W_BUF, idx / h1, idx % h1, __ldg(p.params + p.w_off[1] + idx));
+    for (int idx = tid; idx < A_out * h2; idx += TC_THREADS)
+      put(SM_W3, W3_BUF, idx / h2, idx % h2, __ldg(p.params + p.w_off[2] + idx));
     for (int i = tid; i < 64; i += TC_THREADS) {
-      s_bias[i] = __ldg(p.params + p.b_off[0] + i);
-      s_bias[64 + i] = __ldg(p.params + p.b_off[1] + i);
+      s_bias[i] = i < h1 ? __ldg(p.params + p.b_off[0] + i) : 0.f;
+      s_bias[64 + i] = i < h2 ? __ldg(p.params + p.b_off[1] + i) : 0.f;
     }
     for (int i = tid; i < 16; i += TC_THREADS) s_bias[128 + i] = i < A_out ? __ldg(p.params + p.b_off[2] + i) : 0.f;
     if (p.dist == B200RL_DIST_GAUSSIAN)
@@ -605,29 +606,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
       for (int cb = 0; cb < 2; ++cb) {  // dW2 [64 o][64 i]
         tmem_ld32(tmem + lane_addr + TM_DW2 + 32 * cb, v);
         tmem_wait_ld();
-        if (lane < 16)
+        if (lane < 16 && m < h2)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[p.w_off[1] + m * 64 + 32 * cb + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j)
+            if (32 * cb + j < h1) dst[p.w_off[1] + m * h1 + 32 * cb + j] = __uint_as_float(v[j]);
       }
       tmem_ld32(tmem + lane_addr + TM_DW1, v);  // dW1 [64 o][32 i]
       tmem_wait_ld();
-      if (lane < 16)
+      if (lane < 16 && m < h1)
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j < n_in) dst[p.w_off[0] + m * n_in + j] = __uint_as_float(v[j]);
       uint32_t w[16];
       tmem_ld16(tmem + lane_addr + TM_DW3, w);  // dW3^T [64 i][16 o]
       tmem_wait_ld();
-      if (lane < 16)
+      if (lane < 16 && m < h2)
 #pragma unroll
         for (int a = 0; a < 15; ++a)
-          if (a < A_out) dst[p.w_off[2] + a * 64 + m] = __uint_as_float(w[a]);
+          if (a < A_out) dst[p.w_off[2] + a * h2 + m] = __uint_as_float(w[a]);
       tmem_ld16(tmem + lane_addr + TM_DB2, w);  // column 15 = sum_r dZ2[r][o]
       tmem_wait_ld();
-      if (lane < 16) dst[p.b_off[1] + m] = __uint_as_float(w[15]);
+      if (lane < 16 && m < h2) dst[p.b_off[1] + m] = __uint_as_float(w[15]);
       tmem_ld16(tmem + lane_addr + TM_DB1, w);
       tmem_wait_ld();
-      if (lane < 16) dst[p.b_off[0] + m] = __uint_as_float(w[15]);
+      if (lane < 16 && m < h1) dst[p.b_off[0] + m] = __uint_as_float(w[15]);
       // db3: fixed-order reduction of the per-row accumulators
 #pragma unroll
       for (int a = 0; a < 15; ++a) {
@@ -672,7 +674,8 @@ extern "C" int b200rl_debug_tc_timing(unsigned long long* out16) {
 #endif
 
 bool tc_shape_ok(const b200rl_mlp_desc& d) {
-  return d.n_layers == 3 && d.sizes[1] == 64 && d.sizes[2] == 64 && d.sizes[0] >= 1 && d.sizes[0] <= 32 &&
+  return d.n_layers == 3 && d.sizes[1] >= 1 && d.sizes[1] <= 64 && d.sizes[2] >= 1 && d.sizes[2] <= 64 &&
+         d.sizes[0] >= 1 && d.sizes[0] <= 32 &&
          d.sizes[3] >= 1 && d.sizes[3] <= 15 && d.hidden_act == B200RL_ACT_TANH && d.out_act == B200RL_ACT_IDENTITY;
 }
 
@@ -691,6 +694,8 @@ static int launch_mlp_tc_impl(const b200rl_mlp_loss_grad_args* a, int64_t n_glob
   k.total_rows = partial_rows;
   k.n_in = a->mlp.sizes[0];
   k.n_out = a->mlp.sizes[3];
+  k.h1 = a->mlp.sizes[1];
+  k.h2 = a->mlp.sizes[2];
   int off = 0;
   for (int l = 0; l < 3; ++l) {
     k.w_off[l] = off;

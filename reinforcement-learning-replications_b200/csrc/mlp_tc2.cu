@@ -1,7 +1,7 @@
 // mlp_tc2: second-generation tensor-core kernel for the fused MLP step (tcgen05 + TMEM, sm_100a only).
 //
 // Same contract and data flow as mlp_tc.cu / mlp_fused.cu (see mlp_fused.cu for the reference file:line map) and the
-// same shape gate (3 Linear layers, 64/64 tanh hidden, obs <= 32, out <= 15).  What changed, and why -- measured on
+// same shape gate (3 Linear layers, tanh hidden layers of width <= 64 -- zero-padded to 64 --, obs <= 32, out <= 15).  What changed, and why -- measured on
 // B200 with the per-stage clocks of tools/profile_step.py and the instruction micro-benchmark tools/tc_mma_bench.cu:
 //   * a tcgen05.mma of these small shapes costs 30..50 cycles whatever its size (instruction floor / SS-mode operand
 //     feed), so the 282 MMAs per 128-row tile of the bf16 x 3 kernel -- not the math -- set its pace.  Here every
@@ -78,6 +78,8 @@ enum { SC_X = 0, SC_G, SC_U1, SC_U2, SC_U3, SC_UH2, SC_UH1, SC_W1, SC_W2, SC_W3,
 
 struct Tc2Args {
   int n_in, n_out;
+  int h1, h2;  // hidden widths (<= 64; narrower layers are zero-padded to the 64-wide buffers, which keeps every
+               // padded activation, gradient and weight-gradient entry exactly zero)
   int w_off[3], b_off[3], P;
   int loss, dist;
   long long n_rows;
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + S2_BARS + 48);
   int* s_bad = reinterpret_cast<int*>(sm + S2_BARS + 52);
   const uint32_t bars = base + S2_BARS;  // ready[s] at +8s, chain[s] at +16+8s, off[s] at +32+8s
-  const int n_in = p.n_in, A_out = p.n_out;
+  const int n_in = p.n_in, A_out = p.n_out, h1 = p.h1, h2 = p.h2;
   bool bad = false;
 
   // ---- one-time setup: zero operand buffers; per-layer weight scales; stage W (two fp16 splits), biases ----
@@ -286,17 +288,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
   if (tid == 0) *s_bad = 0;
   {
     float m1 = 0.f, m2 = 0.f, m3 = 0.f;
-    for (int idx = tid; idx < 64 * n_in; idx += T2_THREADS) {
+    for (int idx = tid; idx < h1 * n_in; idx += T2_THREADS) {
       const float w = __ldg(p.params + p.w_off[0] + idx);
       m1 = fmaxf(m1, fabsf(w));
       if (w != w) bad = true;
     }
-    for (int idx = tid; idx < 64 * 64; idx += T2_THREADS) {
+    for (int idx = tid; idx < h2 * h1; idx += T2_THREADS) {
       const float w = __ldg(p.params + p.w_off[1] + idx);
       m2 = fmaxf(m2, fabsf(w));
       if (w != w) bad = true;
     }
-    for (int idx = tid; idx < A_out * 64; idx += T2_THREADS) {
+    for (int idx = tid; idx < A_out * h2; idx += T2_THREADS) {
       const float w = __ldg(p.params + p.w_off[2] + idx);
       m3 = fmaxf(m3, fabsf(w));
       if (w != w) bad = true;
@@ -369,15 +371,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       *reinterpret_cast<__half*>(sm + off + stride) = lb;
     };
     const float sw1 = s_scale[SC_W1], sw2 = s_scale[SC_W2], sw3 = s_scale[SC_W3];
-    for (int idx = tid; idx < 64 * n_in; idx += T2_THREADS)  // W1 stored transposed: row = input, column = output
+    for (int idx = tid; idx < h1 * n_in; idx += T2_THREADS)  // W1 stored transposed: row = input, column = output
       put(S2_W1T, T2_W1T, idx % n_in, idx / n_in, __ldg(p.params + p.w_off[0] + idx) * sw1);
-    for (int idx = tid; idx < 64 * 64; idx += T2_THREADS)
-      put(S2_W2, T2_W, idx >> 6, idx & 63, __ldg(p.params + p.w_off[1] + idx) * sw2);
-    for (int idx = tid; idx < A_out * 64; idx += T2_THREADS)
-      put(S2_W3, T2_W3, idx >> 6, idx & 63, __ldg(p.params + p.w_off[2] + idx) * sw3);
+    for (int idx = tid; idx < h2 * h1; idx += T2_THREADS)
+      put(S2_W2, T2_W, idx / h1, idx % h1, __ldg(p.params + p.w_off[1] + idx) * sw2);
+    for (int idx = tid; idx < A_out * h2; idx += T2_THREADS)
+      put(S2_W3, T2_W3, idx / h2, idx % h2, __ldg(p.params + p.w_off[2] + idx) * sw3);
     for (int i = tid; i < 64; i += T2_THREADS) {
-      s_bias[i] = __ldg(p.params + p.b_off[0] + i);
-      s_bias[64 + i] = __ldg(p.params + p.b_off[1] + i);
+      s_bias[i] = i < h1 ? __ldg(p.params + p.b_off[0] + i) : 0.f;
+      s_bias[64 + i] = i < h2 ? __ldg(p.params + p.b_off[1] + i) : 0.f;
     }
     for (int i = tid; i < 16; i += T2_THREADS) s_bias[128 + i] = i < A_out ? __ldg(p.params + p.b_off[2] + i) : 0.f;
     if (p.dist == B200RL_DIST_GAUSSIAN)
@@ -829,40 +831,45 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       const int m = 32 * (q & 1) + lane;  // feature index
       const uint32_t ta = tmem + lane_addr;
       uint32_t v[16];
-      if (part < 2) {  // dW2 [64 o][64 i]: columns 32*part .. +31
+      if (part < 2) {  // dW2 [h2 o][h1 i]: columns 32*part .. +31
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {
           const int cc = 32 * part + 16 * cb;
           tmem_ld16(ta + M2_DW2 + cc, v);
           tmem_wait_ld();
           const float u = s_scale[SC_OW2];
+          if (m < h2)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dst[p.w_off[1] + m * 64 + cc + j] = __uint_as_float(v[j]) * u;
+            for (int j = 0; j < 16; ++j)
+              if (cc + j < h1) dst[p.w_off[1] + m * h1 + cc + j] = __uint_as_float(v[j]) * u;
         }
-      } else if (part == 2) {  // dW1 [64 o][32 i] in cols 0..31, db1 in col 47
+      } else if (part == 2) {  // dW1 [h1 o][n_in i] in cols 0..31, db1 in col 47
 #pragma unroll
         for (int cb = 0; cb < 3; ++cb) {
           tmem_ld16(ta + M2_DW1 + 16 * cb, v);
           tmem_wait_ld();
-          if (cb < 2) {
-            const float u = s_scale[SC_OW1];
+          if (m < h1) {
+            if (cb < 2) {
+              const float u = s_scale[SC_OW1];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (16 * cb + j < n_in) dst[p.w_off[0] + m * n_in + 16 * cb + j] = __uint_as_float(v[j]) * u;
-          } else {
-            dst[p.b_off[0] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
+              for (int j = 0; j < 16; ++j)
+                if (16 * cb + j < n_in) dst[p.w_off[0] + m * n_in + 16 * cb + j] = __uint_as_float(v[j]) * u;
+            } else {
+              dst[p.b_off[0] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
+            }
           }
         }
-      } else {  // dW3^T [64 i][16 o] and db2 (col 15 = sum_r dZ2[r][o])
+      } else {  // dW3^T [h2 i][16 o] and db2 (col 15 = sum_r dZ2[r][o])
         tmem_ld16(ta + M2_DW3, v);
         tmem_wait_ld();
         const float u = s_scale[SC_OW3];
+        if (m < h2)
 #pragma unroll
-        for (int a = 0; a < 15; ++a)
-          if (a < A_out) dst[p.w_off[2] + a * 64 + m] = __uint_as_float(v[a]) * u;
+          for (int a = 0; a < 15; ++a)
+            if (a < A_out) dst[p.w_off[2] + a * h2 + m] = __uint_as_float(v[a]) * u;
         tmem_ld16(ta + M2_DB2, v);
         tmem_wait_ld();
-        dst[p.b_off[1] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
+        if (m < h2) dst[p.b_off[1] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
       }
       // db3: fixed-order reduction of the per-row accumulators (true scale, fp32 registers)
       if (half == 0) {
@@ -957,6 +964,8 @@ int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStrea
   Tc2Args k{};
   k.n_in = a->mlp.sizes[0];
   k.n_out = a->mlp.sizes[3];
+  k.h1 = a->mlp.sizes[1];
+  k.h2 = a->mlp.sizes[2];
   int off = 0;
   for (int l = 0; l < 3; ++l) {
     k.w_off[l] = off;

@@ -73,7 +73,9 @@ def test_scan_against_reference_golden(case):
 
 
 SHAPES = [([17, 64, 64, 6], "gaussian"), ([4, 64, 64, 2], "categorical"), ([27, 64, 64, 8], "gaussian"),
-          ([17, 64, 32, 6], "gaussian"), ([3, 16, 5], "categorical"), ([11, 64, 64, 64, 3], "gaussian")]
+          ([17, 64, 32, 6], "gaussian"),  # the reference's own benchmark recipe (run_ppo.py:28): tensor-core path, padded
+          ([9, 33, 20, 3], "categorical"), ([17, 24, 64, 6], "gaussian"),  # odd hidden widths, zero-padded to 64
+          ([3, 16, 5], "categorical"), ([11, 64, 64, 64, 3], "gaussian")]  # 2 / 4 layers: fp32 kernel
 
 
 def _net(rng, sizes):
@@ -269,3 +271,20 @@ def test_tc_mode_bf16_matches(monkeypatch):
     wide = loss_grad(sizes, O.flatten_layers(layers), obs, "mse", "none", target=ret)
     assert rel_err(fast["grad"], ref["grad"]) < TOL and rel_err(wide["grad"], ref["grad"]) < TOL
     assert rel_err(fast["grad"], wide["grad"]) < TOL
+
+
+@pytest.mark.parametrize("sizes", [[17, 64, 32, 6], [9, 33, 20, 3]])
+def test_padded_hidden_widths_on_the_wide_range_kernel(sizes, monkeypatch):
+    """Hidden layers narrower than 64 are zero-padded inside both tensor-core kernels (B200RL_TC_MODE=bf16 pins the
+    bf16 x 3 one, which is also the re-run path of the fp16 kernel)."""
+    from gpu_helpers import loss_grad
+    monkeypatch.setenv("B200RL_TC_MODE", "bf16")
+    rng = np.random.default_rng(21)
+    n = 3001
+    vs = sizes[:-1] + [1]
+    layers = _net(rng, vs)
+    obs = rng.standard_normal((n, vs[0])).astype(np.float32)
+    ret = (5 * rng.standard_normal(n)).astype(np.float32)
+    r = loss_grad(vs, O.flatten_layers(layers), obs, "mse", "none", target=ret)
+    ref = O.value_loss_and_grad(layers, obs, ret)
+    assert rel_err(r["grad"], ref["grad"]) < TOL
