@@ -337,7 +337,7 @@ def main():
                 "ms_per_fvp": ms_fvp, "fvp_per_s": 1e3 / ms_fvp, "fvp_launches": int(ts.fvp_launches),
                 "fvp_tflops_fp32": flop_fvp * E * T / (ms_fvp * 1e-3) / 1e12,
                 "accepted_ratio_index": int(ts.accepted_index), "rejected": int(ts.rejected), "kl": ts.kl,
-                "kernel": "mlp_fused_kernel<*,2> (fp32 CUDA cores: forward + tangents + metric + backward)"}
+                "kernel": "mlp_tc_fvp_kernel (tcgen05 fp16x2: forward + tangents + metric + backward, fp32 re-run predicated behind it)"}
 
     def td3_config4():
         """TD3 synthetic Hopper-shaped replay (obs 11, act 3), minibatch 256, 256-256 nets, 50 train steps per call."""

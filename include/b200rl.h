@@ -118,8 +118,8 @@ typedef struct {
                               kl_divergence(old_dist, dist) of trpo.py:167-175 (Gaussian: same log_std for both) */
   const float* direction;  /* [P] the vector v of B200RL_LOSS_FVP, same flat layout as params */
   int32_t flags;           /* B200RL_FLAG_* */
-  const float* obs_absmax; /* optional device scalar: max |obs| over the batch (range hint of the fp16 tensor-core
-                              kernel; NULL = a pre-pass computes it on every launch, see b200rl_absmax) */
+  const float* obs_absmax; /* optional device array [sizes[0]]: per-feature max |obs| over the batch (scales of the fp16
+                              tensor-core kernel; NULL = a pre-pass computes it on every launch, b200rl_absmax_cols) */
   const float* target_absmax; /* optional device scalar: max |target| (MSE backward); NULL = pre-pass */
 } b200rl_mlp_loss_grad_args;
 
@@ -128,6 +128,8 @@ int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* args, void* stream);
 /* out[0] = max |x[i]| (+inf if x holds a NaN); `out` is a device float.  Callers that launch mlp_loss_grad many times
  * over the same observations / targets compute the hints once with this. */
 int b200rl_absmax(const float* x, int64_t n, float* out, void* stream);
+/* out[c] = max_r |x[r, c]| for a row-major [rows, cols] device array, cols <= 32 (the obs_absmax hint). */
+int b200rl_absmax_cols(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
 
 /* Number of mlp_loss_grad launches (since process start) whose fp16 tensor-core pass left the fp16 range and were
  * recomputed by the wide-range bf16 kernel queued behind it.  Synchronises the device; diagnostics / tests only. */

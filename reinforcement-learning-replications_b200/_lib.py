@@ -105,6 +105,7 @@ SIGNATURES = {
                                   C.c_size_t, C.c_void_p]),
     "b200rl_mlp_loss_grad": (C.c_int, [C.POINTER(LossGradArgs), C.c_void_p]),
     "b200rl_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b200rl_absmax_cols": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "b200rl_tc_fallback_count": (C.c_int64, []),
     "b200rl_reduce_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p]),

@@ -49,7 +49,8 @@ struct b200rl_onpolicy {
   int64_t* off = nullptr;
   uint8_t* done = nullptr;
   int64_t n_rows = 0, n_ep = 0;
-  float* absmax = nullptr;   // [4] max |obs|, max |last_obs|, max |returns| (range hints of the fp16 tensor-core kernel)
+  float* absmax = nullptr;   // per-feature max |obs| [32], per-feature max |last_obs| [32], max |returns| [1]: range
+                             // hints of the fp16 tensor-core kernels
   bool hints_valid = false;  // set by the preamble, cleared whenever the batch buffers may have been rewritten
   // derived
   float *values = nullptr, *last_values = nullptr, *adv_raw = nullptr, *ret = nullptr, *old_logp = nullptr;
@@ -141,8 +142,8 @@ int launch_fused(b200rl_onpolicy* h, const b200rl_mlp_desc& mlp, int loss, int d
   a.skip_flag = skip;
   if (h->hints_valid) {
     if (obs == h->obs) a.obs_absmax = h->absmax;
-    if (obs == h->last_obs) a.obs_absmax = h->absmax + 1;
-    if (loss == B200RL_LOSS_MSE) a.target_absmax = h->absmax + 2;
+    if (obs == h->last_obs) a.obs_absmax = h->absmax + 32;
+    if (loss == B200RL_LOSS_MSE) a.target_absmax = h->absmax + 64;
   }
   return b200rl_mlp_loss_grad(&a, s);
 }
@@ -195,7 +196,7 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
   rc |= dev_alloc(h, &h->val_v, (size_t)Pv);
   rc |= dev_alloc(h, &h->partials, (size_t)2 * sms * Pmax);  // mlp_tc2 emits two partial rows per CTA
   rc |= dev_alloc(h, &h->scalar_partials, (size_t)2 * sms * B200RL_N_SCALARS);
-  rc |= dev_alloc(h, &h->absmax, 4);
+  rc |= dev_alloc(h, &h->absmax, 72);
   rc |= dev_alloc(h, &h->pol_grad, (size_t)Pp + B200RL_N_SCALARS);
   rc |= dev_alloc(h, &h->val_grad, (size_t)Pv + B200RL_N_SCALARS);
   rc |= dev_alloc(h, &h->flags, 8);
@@ -325,9 +326,11 @@ static int run_preamble(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl
                         cudaStream_t s) {
   // range hints for the fp16 tensor-core kernel: one pass over the observations per update instead of per launch
   h->hints_valid = false;
-  if (b200rl_absmax(h->obs, h->n_rows * h->obs_dim, h->absmax, s)) return 1;
-  if (b200rl_absmax(h->last_obs, h->n_ep * h->obs_dim, h->absmax + 1, s)) return 1;
-  h->hints_valid = true;
+  if (h->obs_dim <= 32) {
+    if (b200rl_absmax_cols(h->obs, h->n_rows, h->obs_dim, h->absmax, s)) return 1;
+    if (b200rl_absmax_cols(h->last_obs, h->n_ep, h->obs_dim, h->absmax + 32, s)) return 1;
+    h->hints_valid = true;
+  }
   // utils.py:60-71 compute_values: V(obs_t) for every step and V(last_observation) for every episode
   if (launch_fused(h, h->cfg.value, B200RL_LOSS_EVAL, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, h->n_rows, 0.0,
                    false, false, h->values, false, nullptr, s)) return 1;
@@ -336,7 +339,7 @@ static int run_preamble(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl
   if (b200rl_gae_scan(h->rew, h->cfg.rewards_f64, h->values, h->last_values, h->off, h->done, h->n_rows, h->n_ep,
                       hp->gamma, hp->gae_lambda, h->adv_raw, h->ret, h->adv_stats, h->scan_ws, h->scan_ws_bytes, s))
     return 1;
-  if (b200rl_absmax(h->ret, h->n_rows, h->absmax + 2, s)) return 1;
+  if (b200rl_absmax(h->ret, h->n_rows, h->absmax + 64, s)) return 1;
   // normalize_tensor (utils.py:90-92) is over the GLOBAL batch: one 3-scalar all-reduce per update
   if (ar && ar(user, h->adv_stats, 3, 1, s)) {
     set_error("allreduce callback failed (advantage statistics)");
@@ -509,6 +512,7 @@ static int launch_fvp(b200rl_onpolicy* h, const float* direction, float* out, in
   a.log_std = h->log_std;
   a.direction = direction;
   a.partials = h->partials;
+  if (h->hints_valid) a.obs_absmax = h->absmax;
   if (b200rl_mlp_loss_grad(&a, s)) return 1;
   return b200rl_reduce_partials(h->partials, nullptr, b200rl_mlp_grid(&h->cfg.policy, h->n_rows, 2), h->Pp, out,
                                 nullptr, 0, nullptr, s);

@@ -139,7 +139,13 @@ struct FusedArgs {
   float* out_full;
   const float* old_out;
   const float* direction;
+  const unsigned* run_if;  // when set: run only if *run_if == seq (re-run of a tensor-core launch that left fp16's range)
+  unsigned seq;
+  int total_rows;          // partial rows the consumer reduces (> gridDim.x when standing in for a tensor-core launch)
+  unsigned long long* rerun_counter;  // b200rl_tc_fallback_count's device counter
 };
+
+unsigned long long* tc_fallback_counter_ptr();  // mlp_tc.cu
 
 __device__ __forceinline__ float apply_act(float z, int kind) {
   if (kind == B200RL_ACT_TANH) return tanhf(z);
@@ -209,6 +215,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
   const MlpLayout& Y = p.lay;
   const int tid = threadIdx.x;
   if (p.skip_flag != nullptr && *p.skip_flag != 0) return;  // early stop: the whole launch is a no-op
+  if (p.run_if != nullptr) {
+    if (*p.run_if != p.seq) return;  // the tensor-core result stands
+    if (blockIdx.x == 0 && tid == 0 && p.rerun_counter != nullptr) atomicAdd(p.rerun_counter, 1ull);
+    for (int row = (int)gridDim.x + (int)blockIdx.x; row < p.total_rows; row += (int)gridDim.x) {
+      if (BACKWARD)
+        for (int i = tid; i < Y.P; i += MLP_THREADS) p.partials[(size_t)row * Y.P + i] = 0.f;
+      if (p.scalar_partials != nullptr && tid < B200RL_N_SCALARS) p.scalar_partials[(size_t)row * B200RL_N_SCALARS + tid] = 0.0;
+    }
+  }
   const int L = Y.L;
 
   // ---- stage the weights once per launch: W, W^T and bias ----
@@ -598,6 +613,7 @@ int tc2_grid(int64_t n_rows);
 int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s);
 // B200RL_TC_MODE=bf16 pins the bf16 x 3 kernel (A/B runs); default is the fp16 x 2 kernel with bf16 x 3 as its
 // wide-range fallback
+int tc_fvp_total_rows(const b200rl_mlp_desc& mlp, int64_t n_rows);
 static bool use_tc2() {
   const char* e = getenv("B200RL_TC_MODE");
   return !(e != nullptr && e[0] == 'b');
@@ -633,47 +649,28 @@ extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int w
     const int g = tc2_grid(n_rows);
     return g > 0 ? 2 * g : -1;
   }
+  if (with_backward == 2 && use_tc(*mlp) && use_tc2()) return tc_fvp_total_rows(*mlp, n_rows);
   MlpLayout lay;
   if (build_layout(*mlp, with_backward == 1 || with_backward == 2, &lay, with_backward == 2)) return -1;
   return fused_grid(lay, n_rows);
 }
 
-extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* stream) {
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  B200RL_REQUIRE(a != nullptr, "mlp_loss_grad: NULL args");
+namespace b200rl {
+int tc_fvp_total_rows(const b200rl_mlp_desc& mlp, int64_t n_rows);
+int launch_mlp_tc_fvp(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, int total_rows, cudaStream_t s);
+
+// the fp32 kernel, optionally as the predicated re-run of a tensor-core launch (run_if / seq / total_rows)
+static int launch_fused(const b200rl_mlp_loss_grad_args* a, const unsigned* run_if, unsigned seq, int total_rows,
+                        cudaStream_t s) {
   const bool fvp = a->loss == B200RL_LOSS_FVP;
   const bool forward_only = (a->flags & B200RL_FLAG_FORWARD_ONLY) != 0 || a->loss == B200RL_LOSS_EVAL;
   const bool backward = !forward_only;
-  B200RL_REQUIRE(!(fvp && forward_only), "mlp_loss_grad: FVP cannot be forward-only");
   FusedArgs k{};
   if (build_layout(a->mlp, backward, &k.lay, fvp)) return 2;
-  const int L = k.lay.L;
-  B200RL_REQUIRE(a->n_rows >= 0, "mlp_loss_grad: negative n_rows");
-  B200RL_REQUIRE(a->params && a->obs, "mlp_loss_grad: params/obs is NULL");
-  B200RL_REQUIRE(a->loss >= B200RL_LOSS_EVAL && a->loss <= B200RL_LOSS_FVP, "mlp_loss_grad: bad loss %d", a->loss);
-  if (a->dist == B200RL_DIST_NONE) {
-    B200RL_REQUIRE(a->loss == B200RL_LOSS_EVAL || a->loss == B200RL_LOSS_MSE,
-                   "mlp_loss_grad: dist NONE supports only EVAL / MSE");
-    B200RL_REQUIRE(k.lay.n[L] == 1, "mlp_loss_grad: value head must have one output, got %d", k.lay.n[L]);
-    B200RL_REQUIRE(a->loss != B200RL_LOSS_MSE || a->target, "mlp_loss_grad: MSE needs target");
-    B200RL_REQUIRE(!a->out_full && !a->old_out, "mlp_loss_grad: out_full / old_out need a distribution");
-  } else {
-    B200RL_REQUIRE(a->dist == B200RL_DIST_GAUSSIAN || a->dist == B200RL_DIST_CATEGORICAL, "mlp_loss_grad: bad dist");
-    B200RL_REQUIRE(a->loss != B200RL_LOSS_MSE, "mlp_loss_grad: MSE needs dist NONE");
-    B200RL_REQUIRE(fvp || a->actions, "mlp_loss_grad: actions is NULL");
-    B200RL_REQUIRE(k.lay.n[L] <= 16, "mlp_loss_grad: at most 16 action dimensions, got %d", k.lay.n[L]);
-    B200RL_REQUIRE(a->dist != B200RL_DIST_GAUSSIAN || a->log_std, "mlp_loss_grad: Gaussian needs log_std");
-    if (a->loss != B200RL_LOSS_EVAL && !fvp) B200RL_REQUIRE(a->adv_raw, "mlp_loss_grad: policy loss needs adv_raw");
-    if (a->loss == B200RL_LOSS_PPO_CLIP || a->loss == B200RL_LOSS_TRPO_SURROGATE)
-      B200RL_REQUIRE(a->old_logp, "mlp_loss_grad: PPO/TRPO loss needs old_logp");
-    if (fvp) B200RL_REQUIRE(a->direction, "mlp_loss_grad: FVP needs the direction vector");
-  }
-  if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
-  const bool needs_fp32 = fvp || a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC);
-  if (!needs_fp32 && use_tc(a->mlp)) {
-    const int64_t n_glob_tc = a->n_global > 0 ? a->n_global : a->n_rows;
-    return use_tc2() ? launch_mlp_tc2(a, n_glob_tc, s) : launch_mlp_tc(a, n_glob_tc, s);
-  }
+  k.run_if = run_if;
+  k.seq = seq;
+  k.total_rows = total_rows;
+  k.rerun_counter = run_if != nullptr ? tc_fallback_counter_ptr() : nullptr;
   const size_t smem_bytes = (size_t)k.lay.total_floats * sizeof(float);
   B200RL_REQUIRE(smem_bytes <= 227 * 1024,
                  "mlp_loss_grad: network needs %zu bytes of shared memory (> 227 KiB); too large for the fused kernel",
@@ -723,4 +720,64 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
   B200RL_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
+}
+
+int launch_fused_fallback(const b200rl_mlp_loss_grad_args* a, const unsigned* run_if, unsigned seq, int total_rows,
+                          cudaStream_t s) {
+  return launch_fused(a, run_if, seq, total_rows, s);
+}
+
+// partial rows of a tensor-core FVP launch: its own two per CTA, or the fp32 re-run's grid if that is larger
+int tc_fvp_total_rows(const b200rl_mlp_desc& mlp, int64_t n_rows) {
+  MlpLayout lay;
+  if (build_layout(mlp, true, &lay, true)) return -1;
+  const int g = tc2_grid(n_rows), f = fused_grid(lay, n_rows);
+  if (g <= 0 || f <= 0) return -1;
+  return 2 * g > f ? 2 * g : f;
+}
+}  // namespace b200rl
+
+extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200RL_REQUIRE(a != nullptr, "mlp_loss_grad: NULL args");
+  const bool fvp = a->loss == B200RL_LOSS_FVP;
+  const bool forward_only = (a->flags & B200RL_FLAG_FORWARD_ONLY) != 0 || a->loss == B200RL_LOSS_EVAL;
+  const bool backward = !forward_only;
+  B200RL_REQUIRE(!(fvp && forward_only), "mlp_loss_grad: FVP cannot be forward-only");
+  FusedArgs k{};
+  if (build_layout(a->mlp, backward, &k.lay, fvp)) return 2;
+  const int L = k.lay.L;
+  B200RL_REQUIRE(a->n_rows >= 0, "mlp_loss_grad: negative n_rows");
+  B200RL_REQUIRE(a->params && a->obs, "mlp_loss_grad: params/obs is NULL");
+  B200RL_REQUIRE(a->loss >= B200RL_LOSS_EVAL && a->loss <= B200RL_LOSS_FVP, "mlp_loss_grad: bad loss %d", a->loss);
+  if (a->dist == B200RL_DIST_NONE) {
+    B200RL_REQUIRE(a->loss == B200RL_LOSS_EVAL || a->loss == B200RL_LOSS_MSE,
+                   "mlp_loss_grad: dist NONE supports only EVAL / MSE");
+    B200RL_REQUIRE(k.lay.n[L] == 1, "mlp_loss_grad: value head must have one output, got %d", k.lay.n[L]);
+    B200RL_REQUIRE(a->loss != B200RL_LOSS_MSE || a->target, "mlp_loss_grad: MSE needs target");
+    B200RL_REQUIRE(!a->out_full && !a->old_out, "mlp_loss_grad: out_full / old_out need a distribution");
+  } else {
+    B200RL_REQUIRE(a->dist == B200RL_DIST_GAUSSIAN || a->dist == B200RL_DIST_CATEGORICAL, "mlp_loss_grad: bad dist");
+    B200RL_REQUIRE(a->loss != B200RL_LOSS_MSE, "mlp_loss_grad: MSE needs dist NONE");
+    B200RL_REQUIRE(fvp || a->actions, "mlp_loss_grad: actions is NULL");
+    B200RL_REQUIRE(k.lay.n[L] <= 16, "mlp_loss_grad: at most 16 action dimensions, got %d", k.lay.n[L]);
+    B200RL_REQUIRE(a->dist != B200RL_DIST_GAUSSIAN || a->log_std, "mlp_loss_grad: Gaussian needs log_std");
+    if (a->loss != B200RL_LOSS_EVAL && !fvp) B200RL_REQUIRE(a->adv_raw, "mlp_loss_grad: policy loss needs adv_raw");
+    if (a->loss == B200RL_LOSS_PPO_CLIP || a->loss == B200RL_LOSS_TRPO_SURROGATE)
+      B200RL_REQUIRE(a->old_logp, "mlp_loss_grad: PPO/TRPO loss needs old_logp");
+    if (fvp) B200RL_REQUIRE(a->direction, "mlp_loss_grad: FVP needs the direction vector");
+  }
+  if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
+  const int64_t n_glob_all = a->n_global > 0 ? a->n_global : a->n_rows;
+  if (fvp && use_tc(a->mlp) && use_tc2() && !(a->flags & B200RL_FLAG_NO_TC) && !a->out_full && !a->old_out) {
+    const int total = tc_fvp_total_rows(a->mlp, a->n_rows);
+    B200RL_REQUIRE(total > 0, "mlp_loss_grad: no CUDA device");
+    return launch_mlp_tc_fvp(a, n_glob_all, total, s);
+  }
+  const bool needs_fp32 = fvp || a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC);
+  if (!needs_fp32 && use_tc(a->mlp)) {
+    const int64_t n_glob_tc = a->n_global > 0 ? a->n_global : a->n_rows;
+    return use_tc2() ? launch_mlp_tc2(a, n_glob_tc, s) : launch_mlp_tc(a, n_glob_tc, s);
+  }
+  return launch_fused(a, nullptr, 0u, 0, s);
 }

@@ -749,6 +749,18 @@ int launch_mlp_tc_fallback(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, c
 
 }  // namespace b200rl
 
+namespace b200rl {
+// device address of the counter, for kernels in other translation units (no relocatable device code in this build)
+unsigned long long* tc_fallback_counter_ptr() {
+  static unsigned long long* ptr = nullptr;
+  if (ptr == nullptr) {
+    void* q = nullptr;
+    if (cudaGetSymbolAddress(&q, g_tc_fallbacks) == cudaSuccess) ptr = static_cast<unsigned long long*>(q);
+  }
+  return ptr;
+}
+}  // namespace b200rl
+
 extern "C" int64_t b200rl_tc_fallback_count(void) {
   unsigned long long v = 0;
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;

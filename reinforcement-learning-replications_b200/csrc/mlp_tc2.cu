@@ -28,6 +28,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "tc2_common.cuh"
 #include "tc_common.cuh"
 
 namespace b200rl {
@@ -40,11 +41,8 @@ constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
 constexpr int T2_THREADS = T2_EPI_THREADS + 32;
 constexpr float T2_LOG_SQRT_2PI = 0.91893853320467274178f;
 constexpr float T2_ENT_CONST = 1.4189385332046727418f;
-constexpr float T2_RANGE = 60000.f;  // |scaled value| above this (or NaN) => fall back to the bf16 x 3 kernel
-constexpr int T2_H_EXP = 14;         // activations (|H| <= 1) are stored as H * 2^14
 
 // shared-memory map (bytes from the 1024-aligned base); every operand buffer = 2 fp16 splits, 128-byte rows, SW128
-constexpr uint32_t T2_ACT = 128 * 128;      // one split of a [128][64] fp16 buffer
 constexpr uint32_t T2_SLOT = 6 * T2_ACT;    // XD, H1, H2 of one slot
 constexpr uint32_t T2_W1T = 32 * 128;       // one split of W1^T [32 in][64 out]
 constexpr uint32_t T2_W = 64 * 128;         // one split of W2 [64 out][64 in]
@@ -63,7 +61,9 @@ constexpr uint32_t S2_SCALE = S2_DB3 + 512;    // scale factors (floats)
 constexpr uint32_t S2_RED = S2_SCALE + 64;     // block reduction scratch [17 warps][4] floats
 constexpr uint32_t S2_SC = S2_RED + 320;       // [6][8 loss warps] doubles
 constexpr uint32_t S2_BARS = S2_SC + 384;      // mbarriers: ready[2], chain[2], off[2]; tmem holder; bad flag
-constexpr uint32_t S2_TOTAL = S2_BARS + 64;
+constexpr uint32_t S2_XS = S2_BARS + 64;       // per-feature observation scales 2^ex_k [32] and their inverses [32]
+constexpr uint32_t S2_ROWMAX = S2_XS + 256;    // [2 slots][128] largest scaled |obs| of each row (precision guard)
+constexpr uint32_t S2_TOTAL = S2_ROWMAX + 1024;
 constexpr uint32_t T2_SMEM_BYTES = S2_TOTAL + 1024;  // + alignment slack
 static_assert(T2_SMEM_BYTES <= 227 * 1024, "mlp_tc2 shared memory");
 
@@ -97,156 +97,11 @@ struct Tc2Args {
   float* partials;
   double* scalar_partials;
   const int* skip_flag;
-  const float* obs_absmax;     // device scalar
+  const float* obs_absmax;     // device [n_in]: per-feature max |obs|
   const float* target_absmax;  // device scalar (MSE) or NULL
   unsigned* status;            // status-ring slot of this launch
   unsigned seq;                // value to store there when the launch must be redone by the wide-range kernel
 };
-
-__device__ __forceinline__ float pow2i(int e) {  // exact 2^e for e in [-126, 127]
-  e = e < -126 ? -126 : (e > 127 ? 127 : e);
-  return __int_as_float((e + 127) << 23);
-}
-// exponent that maps the magnitude `m` into [2^12, 2^13): returns 0 for m == 0, flags non-finite m
-__device__ __forceinline__ int fit_exp(float m, bool& bad) {
-  if (!(m < INFINITY)) {
-    bad = true;
-    return 0;
-  }
-  if (!(m > 0.f)) return 0;
-  int e = 12 - ilogbf(m);
-  return e < -100 ? -100 : (e > 100 ? 100 : e);
-}
-
-__device__ __forceinline__ void split2h(float x0, float x1, uint32_t& h, uint32_t& l) {
-  const __half2 hb = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(hb);
-  const __half2 lb = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-  h = *reinterpret_cast<const uint32_t*>(&hb);
-  l = *reinterpret_cast<const uint32_t*>(&lb);
-}
-// write 8 consecutive columns (16-byte chunk `ch`) of row r into both split buffers at `buf`
-__device__ __forceinline__ void store_chunk2(uint8_t* sm, uint32_t buf, int r, int ch, const float (&x)[8]) {
-  uint4 h, l;
-  split2h(x[0], x[1], h.x, l.x);
-  split2h(x[2], x[3], h.y, l.y);
-  split2h(x[4], x[5], h.z, l.z);
-  split2h(x[6], x[7], h.w, l.w);
-  const uint32_t off = buf + (uint32_t)r * 128u + ((uint32_t)(ch ^ (r & 7)) << 4);
-  *reinterpret_cast<uint4*>(sm + off) = h;
-  *reinterpret_cast<uint4*>(sm + off + T2_ACT) = l;
-}
-// read them back as fp32 (h + l), still carrying the storage scale
-__device__ __forceinline__ void load_chunk2(const uint8_t* sm, uint32_t buf, int r, int ch, float (&x)[8]) {
-  const uint32_t off = buf + (uint32_t)r * 128u + ((uint32_t)(ch ^ (r & 7)) << 4);
-  const uint4 h = *reinterpret_cast<const uint4*>(sm + off);
-  const uint4 l = *reinterpret_cast<const uint4*>(sm + off + T2_ACT);
-  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
-    x[2 * j] = a.x + b.x;
-    x[2 * j + 1] = a.y + b.y;
-  }
-}
-__device__ __forceinline__ bool out_of_range8(const float (&x)[8]) {
-  float m = fabsf(x[0]);
-#pragma unroll
-  for (int j = 1; j < 8; ++j) m = fmaxf(m, fabsf(x[j]));  // fmaxf drops NaN, so test the sum as well
-  const float s = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
-  return !(m <= T2_RANGE) || (s != s);
-}
-
-// tanhf over 16 values, the same algorithm and constants as libdevice's (|x| < 0.6: odd polynomial; otherwise
-// 1 - 2 / (2^(2 log2(e) |x|) + 1); 1 beyond 9.01), written in phases so that the 16 special-function chains
-// (MUFU.EX2 -> MUFU.RCP, ~40 cycles of latency each) overlap instead of running one element after the other.
-__device__ __forceinline__ void tanh16(float (&z)[16]) {
-  float e[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(fabsf(z[j]) * 2.8853900432586669922f));
-#pragma unroll
-  for (int j = 0; j < 16; ++j) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(e[j] + 1.f));
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float x = z[j], a = fabsf(x), x2 = x * x;
-    float big = fmaf(e[j], -2.f, 1.f);
-    big = a >= 9.010913848876953125f ? 1.f : big;
-    big = copysignf(big, x);
-    float p = fmaf(x2, 0.01573968306183815f, -0.052303962409496307373f);
-    p = fmaf(x2, p, 0.1331529766321182251f);
-    p = fmaf(x2, p, -0.33332768082618713379f);
-    p = fmaf(x2, p, 0.f);
-    z[j] = a >= 0.60000002384185791016f ? big : fmaf(x, p, x);
-  }
-}
-
-__device__ __forceinline__ void t2_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-
-// Instruction descriptor, kind::f16 with fp16 operands (format 0), fp32 accumulate (fields as in tc_common.cuh)
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
-struct Op2 {  // warp-uniform operand description: descriptor halves, low-word step per split and per k-step
-  uint32_t lo, hi, split_step, k_step;
-};
-__device__ __forceinline__ Op2 op2_kmajor(uint32_t addr, uint32_t split_bytes) {
-  const uint64_t d = make_smem_desc_sw128(addr, 16, 1024);
-  return Op2{(uint32_t)d, (uint32_t)(d >> 32), split_bytes >> 4, 32u >> 4};
-}
-// K along the rows; `atom_stride` = byte distance between 64-element atoms along M/N (the next split buffer when the
-// operand is read with M = 128 "stacked")
-__device__ __forceinline__ Op2 op2_mnmajor(uint32_t addr, uint32_t atom_stride, uint32_t split_bytes) {
-  const uint64_t d = make_smem_desc_sw128(addr, atom_stride, 1024);
-  return Op2{(uint32_t)d, (uint32_t)(d >> 32), split_bytes >> 4, 2048u >> 4};
-}
-__device__ __forceinline__ Op2 op2_at(Op2 o, uint32_t byte_off) {  // same view, `byte_off` further (slot select)
-  o.lo += byte_off >> 4;
-  return o;
-}
-// Issue path: fully unrolled with compile-time k-step offsets, every operand derived from warp-uniform values
-// (shared-memory window offsets, kernel parameters, vote results) -- measured 100 -> 74 cycles per MMA on B200.
-// chain product: (h,l) + (l,h) + (h,h), smallest terms first; overwrites D
-template <int KSTEPS>
-__device__ __forceinline__ void issue_chain3(uint32_t d_tmem, uint32_t idesc, const Op2 a, const Op2 b) {
-  constexpr int TI[3] = {0, 1, 0};
-  constexpr int TJ[3] = {1, 0, 0};
-#pragma unroll
-  for (int t = 0; t < 3; ++t)
-#pragma unroll
-    for (int k = 0; k < KSTEPS; ++k)
-      umma_f16_elect2(d_tmem, a.lo + TI[t] * a.split_step + k * a.k_step, a.hi,
-                      b.lo + TJ[t] * b.split_step + k * b.k_step, b.hi, idesc, (t | k) ? 1u : 0u);
-}
-// stacked product: A covers both of its splits along M; B split l (optional) then h
-template <int KSTEPS, int B_SPLITS>
-__device__ __forceinline__ void issue_stacked(uint32_t d_tmem, uint32_t idesc, bool accumulate_first,
-                                              const Op2 a, const Op2 b) {
-#pragma unroll
-  for (int sp = B_SPLITS - 1; sp >= 0; --sp)
-#pragma unroll
-    for (int k = 0; k < KSTEPS; ++k)
-      umma_f16_elect2(d_tmem, a.lo + k * a.k_step, a.hi, b.lo + sp * b.split_step + k * b.k_step, b.hi, idesc,
-                      (sp != B_SPLITS - 1 || k != 0 || accumulate_first) ? 1u : 0u);
-}
 
 #ifdef B200RL_TC_TIMING
 __device__ unsigned long long g_tc2_t[24];
@@ -286,10 +141,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
   // ---- one-time setup: zero operand buffers; per-layer weight scales; stage W (two fp16 splits), biases ----
   for (uint32_t i = tid; i < S2_OPERANDS_END / 16; i += T2_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) *s_bad = 0;
+  // Observation features are scaled one by one (MuJoCo-style observations mix magnitudes): X_s[:,k] = X[:,k] 2^ex_k
+  // with the feature's own max at [2^12, 2^13), and the inverse factor is folded into column k of W1 -- exact.
+  float* s_xs = reinterpret_cast<float*>(sm + S2_XS);
+  float* s_rowmax = reinterpret_cast<float*>(sm + S2_ROWMAX);
+  if (tid < 32) {
+    bool bx = false;
+    const int e = tid < n_in ? fit_exp(__ldg(p.obs_absmax + tid), bx) : 0;
+    s_xs[tid] = pow2i(e);
+    s_xs[32 + tid] = pow2i(-e);
+    if (bx) bad = true;
+  }
+  for (int i = tid; i < 2 * 128; i += T2_THREADS) s_rowmax[i] = 0.f;
+  __syncthreads();
   {
     float m1 = 0.f, m2 = 0.f, m3 = 0.f;
     for (int idx = tid; idx < h1 * n_in; idx += T2_THREADS) {
-      const float w = __ldg(p.params + p.w_off[0] + idx);
+      const float w = __ldg(p.params + p.w_off[0] + idx) * s_xs[32 + idx % n_in];
       m1 = fmaxf(m1, fabsf(w));
       if (w != w) bad = true;
     }
@@ -327,7 +195,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     }
     bool b0 = false;
     const int ew1 = fit_exp(m1, b0), ew2 = fit_exp(m2, b0), ew3 = fit_exp(m3, b0);
-    const int ex = fit_exp(__ldg(p.obs_absmax), b0);
     // gradient scale: park typical |dLoss/dOut| * 2^eg near 2^3 (outliers stay far below the fp16 limit)
     int eg = 0;
     if (BACKWARD) {
@@ -345,9 +212,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       eg = 3 + ilogbf(p.n_glob_f) - ilogbf(typ);
       eg = eg < -100 ? -100 : (eg > 100 ? 100 : eg);
     }
-    s_scale[SC_X] = pow2i(ex);
     s_scale[SC_G] = pow2i(eg);
-    s_scale[SC_U1] = pow2i(-(ex + ew1));
+    s_scale[SC_U1] = pow2i(-ew1);
     s_scale[SC_U2] = pow2i(-(T2_H_EXP + ew2));
     s_scale[SC_U3] = pow2i(-(T2_H_EXP + ew3));
     s_scale[SC_UH2] = pow2i(-ew3);
@@ -357,7 +223,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     s_scale[SC_W3] = pow2i(ew3);
     s_scale[SC_OW3] = pow2i(-(T2_H_EXP + eg));
     s_scale[SC_OW2] = pow2i(-(T2_H_EXP + eg));
-    s_scale[SC_OW1] = pow2i(-(ex + eg));
+    s_scale[SC_OW1] = pow2i(-eg);  // times 2^-ex_k of the column, applied when the accumulator is read
     s_scale[SC_OB] = pow2i(-eg);
     if (b0) *s_bad = 1;
   }
@@ -372,7 +238,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     };
     const float sw1 = s_scale[SC_W1], sw2 = s_scale[SC_W2], sw3 = s_scale[SC_W3];
     for (int idx = tid; idx < h1 * n_in; idx += T2_THREADS)  // W1 stored transposed: row = input, column = output
-      put(S2_W1T, T2_W1T, idx % n_in, idx / n_in, __ldg(p.params + p.w_off[0] + idx) * sw1);
+      put(S2_W1T, T2_W1T, idx % n_in, idx / n_in, (__ldg(p.params + p.w_off[0] + idx) * s_xs[32 + idx % n_in]) * sw1);
     for (int idx = tid; idx < h2 * h1; idx += T2_THREADS)
       put(S2_W2, T2_W, idx / h1, idx % h1, __ldg(p.params + p.w_off[1] + idx) * sw2);
     for (int idx = tid; idx < A_out * h2; idx += T2_THREADS)
@@ -521,7 +387,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     const int c0 = 32 * half;  // this warp's 32 columns of a 64-column epilogue
     const uint32_t bar_ready = bars + 8 * slot, bar_chain = bars + 16 + 8 * slot, bar_off = bars + 32 + 8 * slot;
     uint32_t ph_chain = 0, ph_off = 0;
-    const float sX = s_scale[SC_X], sG = s_scale[SC_G];
+    const float sG = s_scale[SC_G];
     const float sH = pow2i(T2_H_EXP);
 
     float adv_mean = 0.f, adv_std = 1.f;  // normalize_tensor (utils.py:90-92): mean, UNBIASED std, no epsilon
@@ -605,11 +471,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         }
         first = false;
         T2_T(12);
+        float rmax = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          x0[j] *= sX;
-          x1[j] *= sX;
+          x0[j] *= s_xs[16 * half + j];
+          x1[j] *= s_xs[16 * half + 8 + j];
+          rmax = fmaxf(rmax, fmaxf(fabsf(x0[j]), fabsf(x1[j])));
         }
+        atomicMax(reinterpret_cast<int*>(s_rowmax + slot * 128 + r), __float_as_int(rmax));  // >= 0: int order
         if (out_of_range8(x0) || out_of_range8(x1)) bad = true;
         store_chunk2(sm, so + S2_XD, r, 2 * half, x0);
         store_chunk2(sm, so + S2_XD, r, 2 * half + 1, x1);
@@ -651,6 +520,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
 
       // ---- E3: distribution / loss epilogue, one row per thread (warps 0..3 of the slot) ----
       if (half == 0) {
+        {  // precision guard: a row whose every feature sits 2^17 below its column's maximum has lost the l-splits
+          const float rm = s_rowmax[slot * 128 + r];
+          s_rowmax[slot * 128 + r] = 0.f;
+          if (valid && rm > 0.f && rm < 0.03125f) bad = true;
+        }
         uint32_t o[16];
         tmem_ld16(tz + M2_OUT, o);
         tmem_wait_ld();
@@ -853,7 +727,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
               const float u = s_scale[SC_OW1];
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (16 * cb + j < n_in) dst[p.w_off[0] + m * n_in + 16 * cb + j] = __uint_as_float(v[j]) * u;
+                if (16 * cb + j < n_in)
+                  dst[p.w_off[0] + m * n_in + 16 * cb + j] = (__uint_as_float(v[j]) * u) * s_xs[32 + 16 * cb + j];
             } else {
               dst[p.b_off[0] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
             }
@@ -928,17 +803,68 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // m >= 0: int order
 }
 
+// per-column max |x| of a row-major [rows, cols] array (cols <= 32): the per-feature observation scales
+__global__ void __launch_bounds__(256) absmax_cols_kernel(const float* __restrict__ x, long long rows, int cols,
+                                                          float* out) {
+  const int c = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  float m = 0.f;
+  bool nan = false;
+  if (c < cols)
+    for (long long r = (long long)blockIdx.x * 8 + sub; r < rows; r += (long long)gridDim.x * 8) {
+      const float v = x[r * cols + c];
+      m = fmaxf(m, fabsf(v));
+      nan |= (v != v);
+    }
+  if (nan) m = INFINITY;
+  if (c < cols && m > 0.f) atomicMax(reinterpret_cast<int*>(out + c), __float_as_int(m));
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
 namespace {
 constexpr int STATUS_SLOTS = 1024;
 struct Tc2State {
   unsigned* status = nullptr;  // [STATUS_SLOTS]
-  float* scratch = nullptr;    // [STATUS_SLOTS][2] absmax pre-pass results
+  float* scratch = nullptr;    // [STATUS_SLOTS][40] absmax pre-pass results: 32 observation features, then the target
   std::atomic<unsigned> seq{1};
   bool configured = false;
 };
 Tc2State g_tc2;
 }  // namespace
+
+// next status-ring slot (shared by every fp16 tensor-core launch: mlp_tc2, mlp_tc_fvp)
+int tc2_take_slot(unsigned** status, unsigned* seq, float** scratch) {
+  if (!g_tc2.configured) {
+    B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.status), STATUS_SLOTS * sizeof(unsigned)));
+    B200RL_CUDA(cudaMemset(g_tc2.status, 0, STATUS_SLOTS * sizeof(unsigned)));
+    B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.scratch), STATUS_SLOTS * 40 * sizeof(float)));
+    B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+    B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+    g_tc2.configured = true;
+  }
+  *seq = g_tc2.seq.fetch_add(1);
+  const unsigned slot = *seq % STATUS_SLOTS;
+  *status = g_tc2.status + slot;
+  *scratch = g_tc2.scratch + 40 * slot;
+  return 0;
+}
+
+int launch_absmax(const float* x, long long n, float* out, cudaStream_t s) {
+  if (n > 0) {
+    absmax_kernel<<<(int)std::min<long long>((n + 255) / 256, 2LL * 148), 256, 0, s>>>(x, n, out);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
+  return 0;
+}
+
+int launch_absmax_cols(const float* x, long long rows, int cols, float* out, cudaStream_t s) {
+  if (rows > 0 && cols > 0) {
+    absmax_cols_kernel<<<(int)std::min<long long>((rows + 7) / 8, 4LL * 148), 256, 0, s>>>(x, rows, cols, out);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
+  return 0;
+}
 
 int tc2_grid(int64_t n_rows) {
   const int64_t tiles = (n_rows + T2_ROWS - 1) / T2_ROWS;
@@ -951,16 +877,10 @@ int launch_mlp_tc_fallback(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, c
                            int partial_rows, cudaStream_t s);
 
 int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s) {
-  if (!g_tc2.configured) {
-    B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.status), STATUS_SLOTS * sizeof(unsigned)));
-    B200RL_CUDA(cudaMemset(g_tc2.status, 0, STATUS_SLOTS * sizeof(unsigned)));
-    B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.scratch), STATUS_SLOTS * 2 * sizeof(float)));
-    B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
-    B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
-    g_tc2.configured = true;
-  }
-  const unsigned seq = g_tc2.seq.fetch_add(1);
-  const unsigned slot = seq % STATUS_SLOTS;
+  unsigned* status_slot = nullptr;
+  unsigned seq = 0;
+  float* scratch = nullptr;
+  if (tc2_take_slot(&status_slot, &seq, &scratch)) return 1;
   Tc2Args k{};
   k.n_in = a->mlp.sizes[0];
   k.n_out = a->mlp.sizes[3];
@@ -993,27 +913,24 @@ int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStrea
   k.partials = a->partials;
   k.scalar_partials = a->scalar_partials;
   k.skip_flag = a->skip_flag;
-  k.status = g_tc2.status + slot;
+  k.status = status_slot;
   k.seq = seq;
   const bool backward = a->loss != B200RL_LOSS_EVAL;
   int launches = 0;
   // scale hints: use the caller's, else run the pre-pass (correct for any caller; the engine passes hints)
-  float* scratch = g_tc2.scratch + 2 * slot;
   const bool need_obs = a->obs_absmax == nullptr;
   const bool need_tgt = backward && a->loss == B200RL_LOSS_MSE && a->target_absmax == nullptr;
-  if (need_obs || need_tgt) B200RL_CUDA(cudaMemsetAsync(scratch, 0, 2 * sizeof(float), s));
+  if (need_obs || need_tgt) B200RL_CUDA(cudaMemsetAsync(scratch, 0, 40 * sizeof(float), s));
   if (need_obs) {
-    const long long n = (long long)a->n_rows * k.n_in;
-    absmax_kernel<<<(int)std::min<long long>((n + 255) / 256, 2LL * 148), 256, 0, s>>>(a->obs, n, scratch);
-    ++launches;
+    if (launch_absmax_cols(a->obs, a->n_rows, k.n_in, scratch, s)) return 1;
   }
   if (need_tgt) {
     absmax_kernel<<<(int)std::min<long long>((a->n_rows + 255) / 256, 2LL * 148), 256, 0, s>>>(a->target, a->n_rows,
-                                                                                              scratch + 1);
+                                                                                              scratch + 32);
     ++launches;
   }
   k.obs_absmax = need_obs ? scratch : a->obs_absmax;
-  k.target_absmax = need_tgt ? scratch + 1 : a->target_absmax;
+  k.target_absmax = need_tgt ? scratch + 32 : a->target_absmax;
   const int grid = tc2_grid(a->n_rows);
   B200RL_REQUIRE(grid > 0, "mlp_tc2: no CUDA device");
   if (backward)
@@ -1023,7 +940,7 @@ int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStrea
   B200RL_CUDA(cudaGetLastError());
   count_launch(launches + 1);
   // wide-range re-run, predicated on this launch's status slot (a few microseconds when it does not fire)
-  return launch_mlp_tc_fallback(a, n_glob, g_tc2.status + slot, seq, 2 * grid, s);
+  return launch_mlp_tc_fallback(a, n_glob, status_slot, seq, 2 * grid, s);
 }
 
 }  // namespace b200rl
@@ -1033,6 +950,14 @@ extern "C" int b200rl_debug_tc2_timing(unsigned long long* out16) {
   return (int)cudaMemcpyFromSymbol(out16, b200rl::g_tc2_t, sizeof(unsigned long long) * 24);
 }
 #endif
+
+extern "C" int b200rl_absmax_cols(const float* x, int64_t rows, int32_t cols, float* out, void* stream) {
+  using namespace b200rl;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  B200RL_REQUIRE(x != nullptr && out != nullptr && rows >= 0 && cols >= 1 && cols <= 32, "absmax_cols: bad argument");
+  B200RL_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), s));
+  return launch_absmax_cols(x, rows, cols, out, s);
+}
 
 extern "C" int b200rl_absmax(const float* x, int64_t n, float* out, void* stream) {
   using namespace b200rl;

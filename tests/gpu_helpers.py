@@ -79,3 +79,28 @@ def adam_step(params, grad, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
                                None, None, None, stream()), "adam_step")
     torch.cuda.synchronize()
     return dp.cpu().numpy(), dm.cpu().numpy(), dv.cpu().numpy()
+
+
+def fvp(sizes, flat, obs, dist, direction, log_std=None, hidden_act="tanh"):
+    """One Fisher-vector product launch (B200RL_LOSS_FVP) + the fixed-order reduction: returns F v (no damping)."""
+    lib = _lib.load()
+    a = LossGradArgs()
+    a.mlp = MlpDesc.make(sizes, hidden_act, "identity")
+    a.loss, a.dist = LOSS["fvp"], DIST[dist]
+    n = obs.shape[0]
+    a.n_rows, a.n_global = n, 0
+    P = int(lib.b200rl_mlp_param_count(a.mlp))
+    grid = lib.b200rl_mlp_grid(a.mlp, n, 2)
+    assert grid > 0
+    keep = dict(params=dev(flat, np.float32), obs=dev(obs, np.float32), direction=dev(direction, np.float32))
+    if log_std is not None:
+        keep["log_std"] = dev(log_std, np.float32)
+    partials = torch.full((grid * P,), float("nan"), dtype=torch.float32, device="cuda")  # every row must be written
+    for k, t in keep.items():
+        setattr(a, k, t.data_ptr())
+    a.partials = partials.data_ptr()
+    check(lib.b200rl_mlp_loss_grad(C.byref(a), stream()), "mlp_loss_grad(fvp)")
+    out = torch.zeros(P + N_SCALARS, dtype=torch.float32, device="cuda")
+    check(lib.b200rl_reduce_partials(p(partials), None, grid, P, p(out), None, 0, None, stream()), "reduce_partials")
+    torch.cuda.synchronize()
+    return out[:P].cpu().numpy()

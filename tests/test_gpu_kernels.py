@@ -288,3 +288,28 @@ def test_padded_hidden_widths_on_the_wide_range_kernel(sizes, monkeypatch):
     r = loss_grad(vs, O.flatten_layers(layers), obs, "mse", "none", target=ret)
     ref = O.value_loss_and_grad(layers, obs, ret)
     assert rel_err(r["grad"], ref["grad"]) < TOL
+
+
+def test_tc2_mixed_feature_magnitudes_and_row_outlier():
+    """Per-feature observation scales: features spanning 1e-3 .. 1e3 keep full precision on the fp16 path; a single row
+    1e6 times larger than the rest would silently cost every other row its l-splits -- the precision guard sends that
+    launch to the wide-range kernel instead."""
+    from gpu_helpers import loss_grad
+    rng = np.random.default_rng(12)
+    n, sizes = 6000, [17, 64, 64, 1]
+    feat = (10.0 ** rng.uniform(-3, 3, 17)).astype(np.float32)
+    layers = _net(rng, sizes)
+    layers[0] = ((layers[0][0] / feat[None, :]).astype(np.float32), layers[0][1])
+    obs = (rng.standard_normal((n, 17)) * feat[None, :]).astype(np.float32)
+    ret = (5 * rng.standard_normal(n)).astype(np.float32)
+    before = _fallbacks()
+    r = loss_grad(sizes, O.flatten_layers(layers), obs, "mse", "none", target=ret)
+    assert _fallbacks() == before
+    ref = O.value_loss_and_grad(layers, obs, ret)
+    assert rel_err(r["grad"], ref["grad"]) < TOL
+    obs2 = obs.copy()
+    obs2[11] *= 1e6
+    r2 = loss_grad(sizes, O.flatten_layers(layers), obs2, "mse", "none", target=ret)
+    assert _fallbacks() == before + 1
+    ref2 = O.value_loss_and_grad(layers, obs2, ret)
+    assert rel_err(r2["grad"], ref2["grad"]) < TOL

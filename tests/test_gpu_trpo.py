@@ -98,3 +98,69 @@ def test_trpo_vs_oracle_and_rejection():
         np.testing.assert_array_equal(flat(t2.policy.network), g["policy_flat0"])
     else:
         assert t2.last_trpo_stats.kl <= 1e-9
+
+
+@pytest.mark.parametrize("sizes,dist", [([27, 64, 64, 8], "gaussian"), ([4, 64, 64, 2], "categorical"),
+                                        ([17, 64, 32, 6], "gaussian"), ([9, 33, 20, 3], "categorical")])
+@pytest.mark.parametrize("n", [50, 4097, 20011])
+@pytest.mark.parametrize("v_scale", [1e-3, 1.0, 300.0])
+def test_fvp_tensor_core_kernel_matches_oracle(sizes, dist, n, v_scale):
+    """mlp_tc_fvp (forward + tangents + metric + backward on the tensor cores) against the numpy oracle's F v, for
+    directions of very different magnitude (CG iterates span orders of magnitude); the fp32 re-run must not fire."""
+    from gpu_helpers import fvp
+    from rl_replicas_b200 import _lib
+    rng = np.random.default_rng(n + sizes[0])
+    layers = [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), 0.1 * rng.standard_normal(o).astype(np.float32))
+              for i, o in zip(sizes[:-1], sizes[1:])]
+    flat_p = O.flatten_layers(layers)
+    obs = rng.standard_normal((n, sizes[0])).astype(np.float32)
+    log_std = np.full(sizes[-1], -0.5, np.float32) if dist == "gaussian" else None
+    v = (v_scale * rng.standard_normal(flat_p.size)).astype(np.float32)
+    before = int(_lib.load().b200rl_tc_fallback_count())
+    got = fvp(sizes, flat_p, obs, dist, v, log_std)
+    assert int(_lib.load().b200rl_tc_fallback_count()) == before
+    want = O.fisher_vector_product(layers, dist, log_std, obs, v, damping=0.0)
+    assert rel_err(got, want) < 1e-5
+
+
+def test_fvp_row_outlier_is_redone_in_fp32():
+    """One transition whose observation is 1e6 times the others drags every feature's scale up: all other rows lose
+    their l-splits.  The precision guard notices (row max 2^17 below the column max) and the fp32 kernel redoes it."""
+    from gpu_helpers import fvp
+    from rl_replicas_b200 import _lib
+    rng = np.random.default_rng(4)
+    sizes, n = [27, 64, 64, 8], 3000
+    layers = [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+              for i, o in zip(sizes[:-1], sizes[1:])]
+    flat_p = O.flatten_layers(layers)
+    obs = rng.standard_normal((n, 27)).astype(np.float32)
+    obs[5] *= 1e6
+    log_std = np.full(8, -0.5, np.float32)
+    v = rng.standard_normal(flat_p.size).astype(np.float32)
+    before = int(_lib.load().b200rl_tc_fallback_count())
+    got = fvp(sizes, flat_p, obs, "gaussian", v, log_std)
+    want = O.fisher_vector_product(layers, "gaussian", log_std, obs, v, damping=0.0)
+    assert int(_lib.load().b200rl_tc_fallback_count()) == before + 1
+    assert rel_err(got, want) < 1e-5
+
+
+def test_fvp_mixed_feature_magnitudes_stay_on_the_tensor_cores():
+    """MuJoCo-style observations: features spanning 1e-3 .. 1e3.  Per-feature scales keep all of them at full
+    precision; no re-run."""
+    from gpu_helpers import fvp
+    from rl_replicas_b200 import _lib
+    rng = np.random.default_rng(5)
+    sizes, n = [27, 64, 64, 8], 5000
+    feat = (10.0 ** rng.uniform(-3, 3, 27)).astype(np.float32)
+    layers = [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+              for i, o in zip(sizes[:-1], sizes[1:])]
+    layers[0] = ((layers[0][0] / feat[None, :]).astype(np.float32), layers[0][1])  # first layer undoes the feature scale
+    flat_p = O.flatten_layers(layers)
+    obs = (rng.standard_normal((n, 27)) * feat[None, :]).astype(np.float32)
+    log_std = np.full(8, -0.5, np.float32)
+    v = rng.standard_normal(flat_p.size).astype(np.float32)
+    before = int(_lib.load().b200rl_tc_fallback_count())
+    got = fvp(sizes, flat_p, obs, "gaussian", v, log_std)
+    assert int(_lib.load().b200rl_tc_fallback_count()) == before
+    want = O.fisher_vector_product(layers, "gaussian", log_std, obs, v, damping=0.0)
+    assert rel_err(got, want) < 1e-5
