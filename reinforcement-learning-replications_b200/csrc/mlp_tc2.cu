@@ -13,9 +13,11 @@
 //     MN-major operand sits one leading-byte-offset further, i.e. in the next split buffer).  101 MMAs per tile.
 //   * with one tile in flight the epilogue warps spent 43% of their time on mbarriers (ncu source view): the
 //     MMA -> tanh -> MMA chain is latency bound.  Two fp16 splits instead of three bf16 ones make TWO tiles fit in
-//     shared memory (2 x 96 KB), so the CTA runs two independent tile pipelines ("slots", 8 epilogue warps each)
-//     that share the MMA-issuing warp, the tensor pipe and the gradient accumulators in tensor memory: while one
-//     slot waits for its MMAs the other one runs its epilogue.
+//     shared memory (2 x 96 KB), so two tiles ("slots") are in flight per CTA.  All 16 epilogue warps work on one
+//     epilogue job at a time, alternating between the slots in a fixed order, so the MMAs a job hands to the issuer
+//     run under the other slot's next job; the issuer follows the same fixed order (no polling, the slot is a
+//     compile-time constant, K back-to-back MMAs go out as one asm block: ~3 instructions per MMA -- it shares its
+//     scheduler with four epilogue warps and was the bottleneck at 11).
 // fp16 has a narrow exponent range: the scales come from the data (max |W| per layer computed per CTA, max |obs| and
 // max |target| from a pre-pass or the caller) and every converted value is range-checked.  A launch that sees a
 // value outside +-60000 after scaling raises its slot in a status ring and the host has already queued the
@@ -26,6 +28,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc2_common.cuh"
@@ -56,11 +59,11 @@ constexpr uint32_t S2_W3 = S2_W2 + 2 * T2_W;
 constexpr uint32_t S2_OPERANDS_END = S2_W3 + 2 * T2_W3;
 constexpr uint32_t S2_BIAS = S2_OPERANDS_END;  // b1[64] b2[64] b3[16] floats
 constexpr uint32_t S2_DIST = S2_BIAS + 640;    // var[16], log_scale[16], 1/(2 var)[16], 1/var[16] floats
-constexpr uint32_t S2_DB3 = S2_DIST + 256;     // [8 loss warps][16] floats
-constexpr uint32_t S2_SCALE = S2_DB3 + 512;    // scale factors (floats)
+constexpr uint32_t S2_DB3 = S2_DIST + 256;     // [16 warps][16] floats: running sum_r dOut[r][a] per warp
+constexpr uint32_t S2_SCALE = S2_DB3 + 1024;   // scale factors (floats)
 constexpr uint32_t S2_RED = S2_SCALE + 64;     // block reduction scratch [17 warps][4] floats
-constexpr uint32_t S2_SC = S2_RED + 320;       // [6][8 loss warps] doubles
-constexpr uint32_t S2_BARS = S2_SC + 384;      // mbarriers: ready[2], chain[2], off[2]; tmem holder; bad flag
+constexpr uint32_t S2_SC = S2_RED + 320;       // [16 warps][6] doubles: running scalar sums per warp
+constexpr uint32_t S2_BARS = S2_SC + 768;      // mbarriers: ready[2], chain[2], off[2]; tmem holder; bad flag
 constexpr uint32_t S2_XS = S2_BARS + 64;       // per-feature observation scales 2^ex_k [32] and their inverses [32]
 constexpr uint32_t S2_ROWMAX = S2_XS + 256;    // [2 slots][128] largest scaled |obs| of each row (precision guard)
 constexpr uint32_t S2_TOTAL = S2_ROWMAX + 1024;
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
   }
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bars + 8 * s, T2_SLOT_THREADS);  // ready[s]: every epilogue thread of the slot arrives
+      mbar_init(bars + 8 * s, T2_EPI_THREADS);   // ready[s]: every epilogue thread arrives once per job of slot s
       mbar_init(bars + 16 + 8 * s, 1);           // chain[s]: tcgen05.commit
       mbar_init(bars + 32 + 8 * s, 1);           // off[s]:   tcgen05.commit
     }
@@ -302,39 +305,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
               W3_K = op2_kmajor(ub + S2_W3, T2_W3), W2_M = op2_mnmajor(ub + S2_W2, 64 * 128, T2_W),
               W3_M = op2_mnmajor(ub + S2_W3, 16 * 128, T2_W3);
     bool acc_dw3 = false, acc_dw2 = false, acc_dw1 = false;  // the first product into an accumulator overwrites it
-    long long left[2] = {(cta_tiles + 1) / 2 * STAGES, cta_tiles / 2 * STAGES};
-    int st[2] = {0, 0};
-    int acc_done[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // accumulating stages issued so far, per stage and slot
-    uint32_t par[2] = {0u, 0u};
-    int s = 0;
-#ifdef B200RL_TC_TIMING
-    unsigned long long iacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long ilast = clock64();
-#endif
-    while (left[0] + left[1] > 0) {
-      // serve whichever slot has its stage inputs ready (the vote makes the predicate provably warp-uniform)
-      if (left[s] == 0 || !__all_sync(0xffffffffu, mbar_test(ubar + 8 * s, par[s]))) {
-        s ^= 1;
-        continue;
-      }
-      // The gradient accumulators are shared by the slots and fp32 addition is not associative: products that
-      // accumulate (stages 3..5) are issued in TILE order, whatever order the slots become ready in, so that a launch
-      // is bit-reproducible.  Slot s's j-th tile is the CTA's tile 2j + s.
-      if (BACKWARD && st[s] >= 3) {
-        const int x = st[s] - 3;
-        if (acc_done[x][s ^ 1] < acc_done[x][s] + s) {
-          s ^= 1;
-          continue;
-        }
-        ++acc_done[x][s];
-      }
-      par[s] ^= 1u;
-      --left[s];
+    uint32_t par0 = 0u, par1 = 0u;
+    // The epilogue pool runs its jobs in a fixed order -- (slot 0, stage) then (slot 1, stage) -- and so does the
+    // issuer: no polling, the slot is a compile-time constant of each call (descriptor arithmetic folds into
+    // immediates on a uniform base), and products that accumulate into the shared gradient accumulators are issued in
+    // tile order, which makes a launch bit-reproducible.
+    auto serve = [&](auto slot_tag, const int stage) {
+      constexpr int S = decltype(slot_tag)::value;
+      constexpr uint32_t so = (uint32_t)S * T2_SLOT;
+      const uint32_t tz = ut + (uint32_t)S * M2_SLOT;
+      const uint32_t bar_chain = ubar + 16 + 8 * S, bar_off = ubar + 32 + 8 * S;
+      uint32_t& par = S == 0 ? par0 : par1;
+      mbar_wait(ubar + 8 * S, par);  // every epilogue thread has delivered its share of the stage inputs
+      par ^= 1u;
       tc_fence_after_sync();
-      const uint32_t so = (uint32_t)s * T2_SLOT, tz = ut + (uint32_t)s * M2_SLOT;
-      const uint32_t bar_chain = ubar + 16 + 8 * s, bar_off = ubar + 32 + 8 * s;
-      const int stage = st[s];
-      st[s] = stage + 1 == STAGES ? 0 : stage + 1;
       if (stage == 0) {  // Z1 = X W1^T
         issue_chain3<2>(tz + M2_Z1, I_128_64_KM, op2_at(XD_K, so), W1T_M);
         umma_commit_elect(bar_chain);
@@ -365,30 +349,36 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         umma_commit_elect(bar_off);
       }
       __syncwarp();
-#ifdef B200RL_TC_TIMING
-      {
-        const long long n = clock64();
-        iacc[stage] += (unsigned long long)(n - ilast);  // issuing (incl. back-pressure from the MMA queue)
-        ilast = n;
+    };
+    for (long long kp = 0; kp < cta_tiles; kp += 2) {
+#pragma unroll 1
+      for (int stage = 0; stage < STAGES; ++stage) {
+        serve(std::integral_constant<int, 0>{}, stage);
+        if (kp + 1 < cta_tiles) serve(std::integral_constant<int, 1>{}, stage);
       }
-#endif
     }
-#ifdef B200RL_TC_TIMING
-    if (lane == 0 && blockIdx.x == 0 && BACKWARD)
-      for (int i = 0; i < 8; ++i) g_tc2_t[16 + i] = iacc[i];
-#endif
   } else {
-    // =============================== epilogue warps: two slots of 8 ==================================
-    const int slot = warp >> 3, q = warp & 3, half = (warp >> 2) & 1;
+    // =============================== epilogue warps: one pool of 16 ===================================
+    // Two tiles ("slots") are in flight, but the epilogue warps are NOT bound to a slot: all 16 work on one epilogue
+    // job at a time (16 columns each: 4 warps per TMEM lane quadrant), alternating between the slots in a fixed order
+    //   (slot 0, E0) (slot 1, E0) (slot 0, E1) (slot 1, E1) ... (slot 1, E5) | next pair of tiles
+    // so the MMAs a job hands to the issuer run under the OTHER slot's next job.  (Binding 8 warps to each slot left
+    // every epilogue latency bound -- 8 warps cannot fill the SM's issue slots -- and made both slots wait for their
+    // MMAs at the same time; measured 0.45 ms vs this scheme's figure in profiles/.)  The one-row-per-thread loss
+    // job needs only 4 warps; it rotates over the four column groups from tile to tile and the other 12 warps move on.
+    const int q = warp & 3, part = warp >> 2;
     const int r = 32 * q + lane;                          // row of the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;  // this warp's TMEM lane quadrant
-    const uint32_t tz = tmem + lane_addr + (uint32_t)slot * M2_SLOT;
-    const uint32_t so = (uint32_t)slot * T2_SLOT;
-    const int c0 = 32 * half;  // this warp's 32 columns of a 64-column epilogue
-    const uint32_t bar_ready = bars + 8 * slot, bar_chain = bars + 16 + 8 * slot, bar_off = bars + 32 + 8 * slot;
-    uint32_t ph_chain = 0, ph_off = 0;
+    const int cs = 16 * part;                             // this warp's 16 columns of a 64-column epilogue
+    uint32_t ph_chain0 = 0, ph_chain1 = 0, ph_off0 = 0, ph_off1 = 0;
+    bool first0 = true, first1 = true;
     const float sG = s_scale[SC_G];
     const float sH = pow2i(T2_H_EXP);
+    float* s_db3w = s_db3 + warp * 16;                       // this warp's running sum_r dOut[r][a]
+    double* s_scw = s_sc + warp * 6;                         // this warp's running scalar sums
+    if (lane < 16) s_db3w[lane] = 0.f;
+    if (lane < 6) s_scw[lane] = 0.0;
+    __syncwarp();
 
     float adv_mean = 0.f, adv_std = 1.f;  // normalize_tensor (utils.py:90-92): mean, UNBIASED std, no epsilon
     if (p.adv_stats != nullptr) {
@@ -398,26 +388,64 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       adv_std = (float)sqrt((s2 - cnt * mean * mean) / (cnt - 1.0));
     }
     const float adv_inv_std = 1.f / adv_std;
-    double sc[6] = {0, 0, 0, 0, 0, 0};
-    float db3[15];
-#pragma unroll
-    for (int a = 0; a < 15; ++a) db3[a] = 0.f;
 
-    auto epi_arrive = [&]() {  // -> issuer: "this thread's share of the slot's next stage inputs is in shared memory"
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(bar_ready);
-    };
-    auto wait_chain = [&]() {
-      mbar_wait(bar_chain, ph_chain);
-      ph_chain ^= 1u;
-      tc_fence_after_sync();
-    };
-    // tanh layer epilogue: Z (TMEM) * unscale + bias -> tanh -> [fp32 copy back to TMEM for tanh'] + fp16 splits
-    auto act_epilogue = [&](uint32_t tm_col, const float* bias, float unscale, uint32_t dst_buf, bool keep_fp32) {
+#ifdef B200RL_TC_TIMING
+    unsigned long long tacc[16];
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+    long long tlast = clock64();
+#endif
+    auto job = [&](const int slot, const int stage, const long long k) {
+      const uint32_t tz = tmem + lane_addr + (uint32_t)slot * M2_SLOT;
+      const uint32_t so = (uint32_t)slot * T2_SLOT;
+      const uint32_t bar_ready = bars + 8 * slot, bar_chain = bars + 16 + 8 * slot, bar_off = bars + 32 + 8 * slot;
+      const long long tile = blockIdx.x + k * gridDim.x;
+      const long long row = tile * T2_ROWS + r;
+      const bool valid = row < p.n_rows;
+      const bool loss_warp = part == (int)(k & 3);  // rotates: every warp does the loss job of one tile in four
+      auto arrive = [&]() {  // -> issuer: "this thread's share of the slot's next stage inputs is in shared memory"
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        mbar_arrive(bar_ready);
+      };
+      auto wait_chain = [&]() {
+        T2_T(2 * stage + 1);  // work since the last mark belongs to the previous job's tail (arrive)
+        uint32_t& ph = slot == 0 ? ph_chain0 : ph_chain1;
+        mbar_wait(bar_chain, ph);
+        ph ^= 1u;
+        tc_fence_after_sync();
+        T2_T(2 * stage);  // wait
+      };
+      if (stage == 0) {
+        // ---- E0: observations (global fp32 -> scaled fp16 splits, cols 0..31 of XD; 8 columns per thread) ----
+        float x[8];
+        const float* src = p.obs + row * n_in + 8 * part;
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {  // 16 columns at a time keeps the live register set small
-        const int cs = c0 + 16 * sub;
+        for (int j = 0; j < 8; ++j) x[j] = (valid && 8 * part + j < n_in) ? __ldg(src + j) : 0.f;
+        bool& first = slot == 0 ? first0 : first1;
+        if (BACKWARD && !first) {  // the slot's previous tile: dW1 still reads XD and H1 (dZ1)
+          uint32_t& ph = slot == 0 ? ph_off0 : ph_off1;
+          mbar_wait(bar_off, ph);
+          ph ^= 1u;
+          tc_fence_after_sync();
+        }
+        first = false;
+        float rmax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          x[j] *= s_xs[8 * part + j];
+          rmax = fmaxf(rmax, fabsf(x[j]));
+        }
+        atomicMax(reinterpret_cast<int*>(s_rowmax + slot * 128 + r), __float_as_int(rmax));  // >= 0: int order
+        if (out_of_range8(x)) bad = true;
+        store_chunk2(sm, so + S2_XD, r, part, x);
+        arrive();
+      } else if (stage == 1 || stage == 2) {
+        // ---- E1 / E2: Z (TMEM) * unscale + bias -> tanh -> [fp32 back to TMEM for tanh'] + fp16 splits ----
+        wait_chain();
+        const uint32_t tm_col = stage == 1 ? M2_Z1 : M2_ZB;
+        const float* bias = stage == 1 ? s_bias : s_bias + 64;
+        const float unscale = s_scale[stage == 1 ? SC_U1 : SC_U2];
+        const uint32_t dst = so + (stage == 1 ? S2_H1 : S2_H2);
         uint32_t v[16];
         tmem_ld16(tz + tm_col + cs, v);
         tmem_wait_ld();
@@ -432,257 +460,206 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
           v[j] = __float_as_uint(z[j]);
         }
         if (nan_probe != nan_probe) bad = true;  // |tanh| <= 1: only a NaN pre-activation can break the range
-        if (keep_fp32) t2_tmem_st16(tz + tm_col + cs, v);
+        if (BACKWARD && stage == 1) t2_tmem_st16(tz + tm_col + cs, v);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[8 * ch + j]) * sH;
-          store_chunk2(sm, so + dst_buf, r, (cs >> 3) + ch, x);
+          store_chunk2(sm, dst, r, (cs >> 3) + ch, x);
         }
-      }
-      if (keep_fp32) tmem_wait_st();
-    };
-
-#ifdef B200RL_TC_TIMING
-    unsigned long long tacc[16];
-    for (int i = 0; i < 16; ++i) tacc[i] = 0;
-    long long tlast = clock64();
-#endif
-    bool first = true;
-    for (long long k = slot; k < cta_tiles; k += 2) {
-      const long long tile = blockIdx.x + k * gridDim.x;
-      const long long row = tile * T2_ROWS + r;
-      const bool valid = row < p.n_rows;
-
-      // ---- E0: observations (global fp32 -> scaled fp16 splits, cols 0..31 of XD; 16 columns per thread) ----
-      {
-        float x0[8], x1[8];
-        const float* src = p.obs + row * n_in + 16 * half;
+        if (BACKWARD && stage == 1) tmem_wait_st();
+        arrive();
+      } else if (stage == 3) {
+        // ---- E3: distribution / loss epilogue, one row per thread, on this tile's loss warps ----
+        float pf_act[15], pf_adv = 0.f, pf_old = 0.f, pf_tgt = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          x0[j] = (valid && 16 * half + j < n_in) ? __ldg(src + j) : 0.f;
-          x1[j] = (valid && 16 * half + 8 + j < n_in) ? __ldg(src + 8 + j) : 0.f;
+        for (int a = 0; a < 15; ++a) pf_act[a] = 0.f;
+        if (loss_warp && valid) {  // loss inputs of this row: issue the loads before waiting for F3
+          if (p.dist == B200RL_DIST_GAUSSIAN) {
+#pragma unroll
+            for (int a = 0; a < 15; ++a)
+              if (a < A_out) pf_act[a] = __ldg(p.actions + row * A_out + a);
+          } else if (p.dist == B200RL_DIST_CATEGORICAL) {
+            pf_act[0] = __ldg(p.actions + row);
+          }
+          if (p.loss != B200RL_LOSS_EVAL && p.adv_raw != nullptr) pf_adv = __ldg(p.adv_raw + row);
+          if (p.old_logp != nullptr) pf_old = __ldg(p.old_logp + row);
+          if (p.loss == B200RL_LOSS_MSE) pf_tgt = __ldg(p.target + row);
         }
-        if (BACKWARD && !first) {  // the slot's previous tile: dW1 still reads XD and H1 (dZ1)
-          mbar_wait(bar_off, ph_off);
-          ph_off ^= 1u;
-          tc_fence_after_sync();
-        }
-        first = false;
-        T2_T(12);
-        float rmax = 0.f;
+        wait_chain();  // every warp consumes the phase (a skipped parity wait could not be told from a completed one)
+        if (loss_warp) {
+          {  // precision guard: a row whose every feature sits 2^17 below its column's maximum has lost the l-splits
+            const float rm = s_rowmax[slot * 128 + r];
+            s_rowmax[slot * 128 + r] = 0.f;
+            if (valid && rm > 0.f && rm < 0.03125f) bad = true;
+          }
+          uint32_t o[16];
+          tmem_ld16(tz + M2_OUT, o);
+          tmem_wait_ld();
+          float out[16], dout[16];
+          double sc[6] = {0, 0, 0, 0, 0, 0};
+          const float u3 = s_scale[SC_U3];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          x0[j] *= s_xs[16 * half + j];
-          x1[j] *= s_xs[16 * half + 8 + j];
-          rmax = fmaxf(rmax, fmaxf(fabsf(x0[j]), fabsf(x1[j])));
-        }
-        atomicMax(reinterpret_cast<int*>(s_rowmax + slot * 128 + r), __float_as_int(rmax));  // >= 0: int order
-        if (out_of_range8(x0) || out_of_range8(x1)) bad = true;
-        store_chunk2(sm, so + S2_XD, r, 2 * half, x0);
-        store_chunk2(sm, so + S2_XD, r, 2 * half + 1, x1);
-      }
-      T2_T(0);
-      epi_arrive();
-      wait_chain();  // F1
-      T2_T(1);
-      act_epilogue(M2_Z1, s_bias, s_scale[SC_U1], S2_H1, BACKWARD);
-      T2_T(2);
-      epi_arrive();
-      wait_chain();  // F2
-      T2_T(3);
-      act_epilogue(M2_ZB, s_bias + 64, s_scale[SC_U2], S2_H2, false);
-      T2_T(4);
-      epi_arrive();
-
-      // loss inputs of this row: issue the loads before waiting for F3
-      float pf_act[15], pf_adv = 0.f, pf_old = 0.f, pf_tgt = 0.f;
-#pragma unroll
-      for (int a = 0; a < 15; ++a) pf_act[a] = 0.f;
-      if (half == 0 && valid) {
-        if (p.dist == B200RL_DIST_GAUSSIAN) {
-#pragma unroll
-          for (int a = 0; a < 15; ++a)
-            if (a < A_out) pf_act[a] = __ldg(p.actions + row * A_out + a);
-        } else if (p.dist == B200RL_DIST_CATEGORICAL) {
-          pf_act[0] = __ldg(p.actions + row);
-        }
-        if (p.loss != B200RL_LOSS_EVAL && p.adv_raw != nullptr) pf_adv = __ldg(p.adv_raw + row);
-        if (p.old_logp != nullptr) pf_old = __ldg(p.old_logp + row);
-        if (p.loss == B200RL_LOSS_MSE) pf_tgt = __ldg(p.target + row);
-      } else if (half == 1) {  // idle during the loss epilogue: pull the slot's next observations towards L2
-        const long long nrow = row + 2 * (long long)gridDim.x * T2_ROWS;
-        if (nrow < p.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obs + nrow * n_in));
-      }
-      wait_chain();  // F3
-      T2_T(5);
-
-      // ---- E3: distribution / loss epilogue, one row per thread (warps 0..3 of the slot) ----
-      if (half == 0) {
-        {  // precision guard: a row whose every feature sits 2^17 below its column's maximum has lost the l-splits
-          const float rm = s_rowmax[slot * 128 + r];
-          s_rowmax[slot * 128 + r] = 0.f;
-          if (valid && rm > 0.f && rm < 0.03125f) bad = true;
-        }
-        uint32_t o[16];
-        tmem_ld16(tz + M2_OUT, o);
-        tmem_wait_ld();
-        float out[16], dout[16];
-        const float u3 = s_scale[SC_U3];
-#pragma unroll
-        for (int a = 0; a < 16; ++a) {
-          out[a] = fmaf(__uint_as_float(o[a]), u3, s_bias[128 + a]);
-          dout[a] = 0.f;
-        }
-        if (valid) {
-          float coef = 0.f, term = 0.f, lp = 0.f, ent = 0.f;
-          if (p.dist == B200RL_DIST_NONE) {
-            const float vout = out[0];
-            if (p.row_out) p.row_out[row] = vout;
-            if (p.loss == B200RL_LOSS_MSE) {  // ppo.py:282-287
-              const float diff = vout - pf_tgt;
-              term = diff * diff;
-              dout[0] = (2.f * diff) * p.inv_n;
-            }
-            sc[0] += (double)term;
-            sc[5] += 1.0;
-          } else {
-            float dlp[16];
-#pragma unroll
-            for (int a = 0; a < 16; ++a) dlp[a] = 0.f;
-            if (p.dist == B200RL_DIST_GAUSSIAN) {
-#pragma unroll
-              for (int a = 0; a < 15; ++a)
-                if (a < A_out) {
-                  const float lsc = s_dist[16 + a];
-                  const float d = pf_act[a] - out[a];
-                  lp += -(d * d) * s_dist[32 + a] - lsc - T2_LOG_SQRT_2PI;  // torch Normal.log_prob
-                  ent += T2_ENT_CONST + lsc;                                // torch Normal.entropy
-                  dlp[a] = d * s_dist[48 + a];
-                }
+          for (int a = 0; a < 16; ++a) {
+            out[a] = fmaf(__uint_as_float(o[a]), u3, s_bias[128 + a]);
+            dout[a] = 0.f;
+          }
+          if (valid) {
+            float coef = 0.f, term = 0.f, lp = 0.f, ent = 0.f;
+            if (p.dist == B200RL_DIST_NONE) {
+              const float vout = out[0];
+              if (p.row_out) p.row_out[row] = vout;
+              if (p.loss == B200RL_LOSS_MSE) {  // ppo.py:282-287
+                const float diff = vout - pf_tgt;
+                term = diff * diff;
+                dout[0] = (2.f * diff) * p.inv_n;
+              }
+              sc[0] = (double)term;
+              sc[5] = 1.0;
             } else {
-              float m = out[0];
+              float dlp[16];
 #pragma unroll
-              for (int a = 1; a < 15; ++a)
-                if (a < A_out) m = fmaxf(m, out[a]);
-              float se = 0.f;
+              for (int a = 0; a < 16; ++a) dlp[a] = 0.f;
+              if (p.dist == B200RL_DIST_GAUSSIAN) {
 #pragma unroll
-              for (int a = 0; a < 15; ++a)
-                if (a < A_out) se += expf(out[a] - m);
-              const float lse = m + logf(se);
-              const int ai = (int)pf_act[0];  // value.long()
+                for (int a = 0; a < 15; ++a)
+                  if (a < A_out) {
+                    const float lsc = s_dist[16 + a];
+                    const float d = pf_act[a] - out[a];
+                    lp += -(d * d) * s_dist[32 + a] - lsc - T2_LOG_SQRT_2PI;  // torch Normal.log_prob
+                    ent += T2_ENT_CONST + lsc;                                // torch Normal.entropy
+                    dlp[a] = d * s_dist[48 + a];
+                  }
+              } else {
+                float m = out[0];
 #pragma unroll
-              for (int a = 0; a < 15; ++a)
-                if (a < A_out) {
-                  const float lg = out[a] - lse;
-                  const float pa = expf(lg);
-                  ent -= lg * pa;
-                  if (a == ai) lp = lg;
-                  dlp[a] = (a == ai ? 1.f : 0.f) - pa;
-                }
+                for (int a = 1; a < 15; ++a)
+                  if (a < A_out) m = fmaxf(m, out[a]);
+                float se = 0.f;
+#pragma unroll
+                for (int a = 0; a < 15; ++a)
+                  if (a < A_out) se += expf(out[a] - m);
+                const float lse = m + logf(se);
+                const int ai = (int)pf_act[0];  // value.long()
+#pragma unroll
+                for (int a = 0; a < 15; ++a)
+                  if (a < A_out) {
+                    const float lg = out[a] - lse;
+                    const float pa = expf(lg);
+                    ent -= lg * pa;
+                    if (a == ai) lp = lg;
+                    dlp[a] = (a == ai ? 1.f : 0.f) - pa;
+                  }
+              }
+              if (p.row_out) p.row_out[row] = lp;
+              float adv = 0.f, oldlp = 0.f;
+              if (p.loss != B200RL_LOSS_EVAL) {
+                adv = pf_adv;
+                if (p.adv_stats != nullptr) adv = (adv - adv_mean) * adv_inv_std;  // utils.py:91
+              }
+              if (p.old_logp != nullptr) oldlp = pf_old;
+              if (p.loss == B200RL_LOSS_PPO_CLIP) {  // ppo.py:245-255
+                const float ratio = expf(lp - oldlp);
+                const float s1 = ratio * adv;
+                const float s2 = fminf(fmaxf(ratio, p.clip_lo), p.clip_hi) * adv;
+                term = -fminf(s1, s2);
+                const bool pass = adv >= 0.f ? (ratio <= p.clip_hi) : (ratio >= p.clip_lo);
+                coef = pass ? (-p.inv_n * adv) * ratio : 0.f;
+              } else if (p.loss == B200RL_LOSS_VPG) {  // vpg.py:203
+                term = -(lp * adv);
+                coef = -p.inv_n * adv;
+              } else if (p.loss == B200RL_LOSS_TRPO_SURROGATE) {  // trpo.py:161-163
+                const float ratio = expf(lp - oldlp);
+                term = -(ratio * adv);
+                coef = (-p.inv_n * adv) * ratio;
+              }
+#pragma unroll
+              for (int a = 0; a < 15; ++a) dout[a] = coef * dlp[a];
+              sc[0] = (double)term;
+              if (p.old_logp != nullptr) sc[1] = (double)(oldlp - lp);
+              sc[2] = (double)ent;
+              sc[3] = (double)lp;
+              sc[4] = (double)lp * (double)lp;
+              sc[5] = 1.0;
             }
-            if (p.row_out) p.row_out[row] = lp;
-            float adv = 0.f, oldlp = 0.f;
-            if (p.loss != B200RL_LOSS_EVAL) {
-              adv = pf_adv;
-              if (p.adv_stats != nullptr) adv = (adv - adv_mean) * adv_inv_std;  // utils.py:91
-            }
-            if (p.old_logp != nullptr) oldlp = pf_old;
-            if (p.loss == B200RL_LOSS_PPO_CLIP) {  // ppo.py:245-255
-              const float ratio = expf(lp - oldlp);
-              const float s1 = ratio * adv;
-              const float s2 = fminf(fmaxf(ratio, p.clip_lo), p.clip_hi) * adv;
-              term = -fminf(s1, s2);
-              const bool pass = adv >= 0.f ? (ratio <= p.clip_hi) : (ratio >= p.clip_lo);
-              coef = pass ? (-p.inv_n * adv) * ratio : 0.f;
-            } else if (p.loss == B200RL_LOSS_VPG) {  // vpg.py:203
-              term = -(lp * adv);
-              coef = -p.inv_n * adv;
-            } else if (p.loss == B200RL_LOSS_TRPO_SURROGATE) {  // trpo.py:161-163
-              const float ratio = expf(lp - oldlp);
-              term = -(ratio * adv);
-              coef = (-p.inv_n * adv) * ratio;
-            }
+          }
+          // scalar sums of this tile: warp tree, then this warp's running total (fixed order => reproducible)
+          if (p.scalar_partials != nullptr) {
 #pragma unroll
-            for (int a = 0; a < 15; ++a) dout[a] = coef * dlp[a];
-            sc[0] += (double)term;
-            if (p.old_logp != nullptr) sc[1] += (double)(oldlp - lp);
-            sc[2] += (double)ent;
-            sc[3] += (double)lp;
-            sc[4] += (double)lp * (double)lp;
-            sc[5] += 1.0;
+            for (int kk = 0; kk < 6; ++kk) {
+              const double t = warp_sum(sc[kk]);
+              if (lane == 0) s_scw[kk] += t;
+            }
+          }
+          if (BACKWARD) {
+#pragma unroll
+            for (int a = 0; a < 15; ++a) {
+              float t = dout[a];
+#pragma unroll
+              for (int o2 = 16; o2 > 0; o2 >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o2);
+              if (lane == 0 && a < A_out) s_db3w[a] += t;
+            }
+            float x0[8], x1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              x0[j] = dout[j] * sG;
+              x1[j] = j < 7 ? dout[8 + j] * sG : 1.0f;  // ones column (col 47): db1 / db2 fall out of the dW products
+            }
+            if (out_of_range8(x0) || out_of_range8(x1)) bad = true;
+            store_chunk2(sm, so + S2_XD, r, 4, x0);  // cols 32..39
+            store_chunk2(sm, so + S2_XD, r, 5, x1);  // cols 40..47
           }
         }
-        if (BACKWARD) {
-          float x0[8], x1[8];
+        if (BACKWARD) arrive();
+      } else if (stage == 4) {
+        // ---- E4: dZ2 (scaled) = dH2_acc * 2^-ew3 * (1 - H2^2), H2 re-read from its fp16 splits, written in place ----
+        wait_chain();  // dH2 (and dW3: H2 may be overwritten now)
+        const float unscale = s_scale[SC_UH2], hh = pow2i(-2 * T2_H_EXP);
+        uint32_t g[16];
+        tmem_ld16(tz + M2_ZB + cs, g);
+        tmem_wait_ld();
 #pragma unroll
-          for (int a = 0; a < 15; ++a) db3[a] += dout[a];
+        for (int ch = 0; ch < 2; ++ch) {
+          float x[8];
+          load_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * fmaf(-(x[j] * hh), x[j], 1.f);
+          if (out_of_range8(x)) bad = true;
+          store_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
+        }
+        arrive();
+      } else {
+        // ---- E5: dZ1 (scaled) = dH1_acc * 2^-ew2 * (1 - H1^2), H1 kept as fp32 in tensor memory, written over H1 ----
+        wait_chain();  // dH1 (and dW2 / db2: H1 may be overwritten now)
+        const float unscale = s_scale[SC_UH1];
+        uint32_t g[16], h[16];
+        tmem_ld16(tz + M2_ZB + cs, g);
+        tmem_ld16(tz + M2_Z1 + cs, h);
+        tmem_wait_ld();
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            x0[j] = dout[j] * sG;
-            x1[j] = j < 7 ? dout[8 + j] * sG : 1.0f;  // ones column (col 47): db1 / db2 fall out of the dW products
+            const float hv = __uint_as_float(h[8 * ch + j]);
+            x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * (1.f - hv * hv);
           }
-          if (out_of_range8(x0) || out_of_range8(x1)) bad = true;
-          store_chunk2(sm, so + S2_XD, r, 4, x0);  // cols 32..39
-          store_chunk2(sm, so + S2_XD, r, 5, x1);  // cols 40..47
+          if (out_of_range8(x)) bad = true;
+          store_chunk2(sm, so + S2_H1, r, (cs >> 3) + ch, x);
         }
+        arrive();  // -> dW1 / db1, completion tracked by bar_off
       }
-      T2_T(6);
-      if (BACKWARD) {
-        epi_arrive();
-        wait_chain();  // dH2 (and dW3: H2 may be overwritten now)
-        T2_T(7);
-        // dZ2 (scaled) = dH2_acc * 2^-ew3 * (1 - H2^2), H2 re-read from its fp16 splits, written in place
-        {
-          const float unscale = s_scale[SC_UH2], hh = pow2i(-2 * T2_H_EXP);
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int cs = c0 + 16 * sub;
-            uint32_t g[16];
-            tmem_ld16(tz + M2_ZB + cs, g);
-            tmem_wait_ld();
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              float x[8];
-              load_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * fmaf(-(x[j] * hh), x[j], 1.f);
-              if (out_of_range8(x)) bad = true;
-              store_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
-            }
-          }
-        }
-        T2_T(8);
-        epi_arrive();
-        wait_chain();  // dH1 (and dW2 / db2: H1 may be overwritten now)
-        T2_T(9);
-        // dZ1 (scaled) = dH1_acc * 2^-ew2 * (1 - H1^2), H1 kept as fp32 in tensor memory, written over H1
-        {
-          const float unscale = s_scale[SC_UH1];
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int cs = c0 + 16 * sub;
-            uint32_t g[16], h[16];
-            tmem_ld16(tz + M2_ZB + cs, g);
-            tmem_ld16(tz + M2_Z1 + cs, h);
-            tmem_wait_ld();
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-              float x[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float hv = __uint_as_float(h[8 * ch + j]);
-                x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * (1.f - hv * hv);
-              }
-              if (out_of_range8(x)) bad = true;
-              store_chunk2(sm, so + S2_H1, r, (cs >> 3) + ch, x);
-            }
-          }
-        }
-        T2_T(10);
-        epi_arrive();  // -> dW1 / db1, completion tracked by bar_off
+    };
+
+    constexpr int NSTAGE = BACKWARD ? 6 : 4;  // forward only: E0, E1, E2 and the loss job (no arrival after it)
+    for (long long kp = 0; kp < cta_tiles; kp += 2) {
+#pragma unroll 1
+      for (int stage = 0; stage < NSTAGE; ++stage) {
+        job(0, stage, kp);
+        T2_T(2 * stage + 1);
+        if (kp + 1 < cta_tiles) job(1, stage, kp + 1);
+        T2_T(2 * stage + 1);
       }
     }
 #ifdef B200RL_TC_TIMING
@@ -691,16 +668,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
 #endif
 
     // ---- per-CTA results ----
-    if (BACKWARD && !first) {  // this slot's last dW1 (slots that had no tile never armed the barrier)
-      mbar_wait(bar_off, ph_off);
-      tc_fence_after_sync();
+    if (BACKWARD) {  // the last dW1 of each slot that had a tile
+      if (!first0) {
+        mbar_wait(bars + 32, ph_off0);
+        tc_fence_after_sync();
+      }
+      if (!first1) {
+        mbar_wait(bars + 40, ph_off1);
+        tc_fence_after_sync();
+      }
     }
     tc_fence_before_sync();
-    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // both slots: every MMA of the CTA has retired
+    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // every MMA of the CTA has retired
     tc_fence_after_sync();
     if (BACKWARD) {
       // stacked accumulators: lanes 0..63 = h-split half (partial row 2b), lanes 64..127 = l-split half (row 2b+1)
-      const int part = warp >> 2;  // 0..3: which accumulator columns this warp moves
       float* dst = p.partials + ((size_t)blockIdx.x * 2 + (q >> 1)) * p.P;
       const int m = 32 * (q & 1) + lane;  // feature index
       const uint32_t ta = tmem + lane_addr;
@@ -746,35 +728,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         tmem_wait_ld();
         if (m < h2) dst[p.b_off[1] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
       }
-      // db3: fixed-order reduction of the per-row accumulators (true scale, fp32 registers)
-      if (half == 0) {
-#pragma unroll
-        for (int a = 0; a < 15; ++a) {
-          float s = db3[a];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (lane == 0) s_db3[(slot * 4 + q) * 16 + a] = s;
-        }
-      }
     }
-    if (p.scalar_partials != nullptr && half == 0) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double v = warp_sum(sc[k]);
-        if (lane == 0) s_sc[k * 8 + slot * 4 + q] = v;
-      }
-    }
-    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-    if (BACKWARD && tid < A_out) {
-      float s = 0.f;
-      for (int w8 = 0; w8 < 8; ++w8) s += s_db3[w8 * 16 + tid];
-      p.partials[((size_t)blockIdx.x * 2) * p.P + p.b_off[2] + tid] = s;
+    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // every warp's running sums are final
+    if (BACKWARD && tid < A_out) {  // db3: the 16 per-warp totals in warp order
+      float t = 0.f;
+      for (int w = 0; w < T2_EPI_WARPS; ++w) t += s_db3[w * 16 + tid];
+      p.partials[((size_t)blockIdx.x * 2) * p.P + p.b_off[2] + tid] = t;
       p.partials[((size_t)blockIdx.x * 2 + 1) * p.P + p.b_off[2] + tid] = 0.f;
     }
     if (p.scalar_partials != nullptr && tid < B200RL_N_SCALARS) {
       double t = 0.0;
       if (tid < 6)
-        for (int w8 = 0; w8 < 8; ++w8) t += s_sc[tid * 8 + w8];
+        for (int w = 0; w < T2_EPI_WARPS; ++w) t += s_sc[w * 6 + tid];
       p.scalar_partials[((size_t)blockIdx.x * 2) * B200RL_N_SCALARS + tid] = t;
       p.scalar_partials[((size_t)blockIdx.x * 2 + 1) * B200RL_N_SCALARS + tid] = 0.0;
     }

@@ -98,8 +98,9 @@ class ReplayBuffer:
         if self._capacity == 0:
             raise ValueError("device_columns: the buffer is empty")
         if self._dev is None:
-            self._dev = tuple(torch.empty(self._cols[k].shape, dtype=torch.float32, device="cuda") for k in self.COLUMNS)
-            self._dev_dirty = [(0, self._capacity)]
+            self._dev = tuple(torch.zeros(self._cols[k].shape, dtype=torch.float32, device="cuda") for k in self.COLUMNS)
+            first = min(self.current_size, self._capacity - self._head)  # the rows that hold data, wrap-around aware
+            self._dev_dirty = [(self._head, first)] + ([(0, self.current_size - first)] if first < self.current_size else [])
         for start, count in self._dev_dirty:
             for k, d in zip(self.COLUMNS, self._dev):
                 host = np.ascontiguousarray(self._cols[k][start:start + count], dtype=np.float32)
