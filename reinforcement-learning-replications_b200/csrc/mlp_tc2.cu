@@ -656,10 +656,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     for (long long kp = 0; kp < cta_tiles; kp += 2) {
 #pragma unroll 1
       for (int stage = 0; stage < NSTAGE; ++stage) {
-        job(0, stage, kp);
-        T2_T(2 * stage + 1);
-        if (kp + 1 < cta_tiles) job(1, stage, kp + 1);
-        T2_T(2 * stage + 1);
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {  // one copy of the job code: it is large and the I-cache is not
+          if (kp + slot < cta_tiles) job(slot, stage, kp + slot);
+          T2_T(2 * stage + 1);
+        }
       }
     }
 #ifdef B200RL_TC_TIMING
