@@ -397,12 +397,15 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
         store_chunk2(sm, SF_XD, r, 2 * half, x0);
         store_chunk2(sm, SF_XD, r, 2 * half + 1, x1);
       }
-      epi_arrive();
-      wait_chain();
-      layer_epilogue(MF_Z1, s_bias, s_vb, s_scale[FS_U1], s_scale[FS_UT1], s_scale[FS_T1], SF_H1, SF_T1, true);
-      epi_arrive();
-      wait_chain();
-      layer_epilogue(MF_ZB, s_bias + 64, s_vb + 64, s_scale[FS_U2], s_scale[FS_UT2], s_scale[FS_T2], SF_H2, SF_T2, false);
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {  // one copy of the (large) layer epilogue: instruction-cache pressure
+        epi_arrive();
+        wait_chain();
+        layer_epilogue(layer == 0 ? MF_Z1 : MF_ZB, s_bias + 64 * layer, s_vb + 64 * layer,
+                       s_scale[layer == 0 ? FS_U1 : FS_U2], s_scale[layer == 0 ? FS_UT1 : FS_UT2],
+                       s_scale[layer == 0 ? FS_T1 : FS_T2], layer == 0 ? SF_H1 : SF_H2, layer == 0 ? SF_T1 : SF_T2,
+                       layer == 0);
+      }
       epi_arrive();
       wait_chain();
       // ---- metric epilogue: dOut = M (J v) / N, one row per thread ----
