@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
   }
   if (FVP) {
     for (int l = 0; l < L; ++l) {
-      const int nin = Y.n[l], nout = Y.n[l + 1];
+      const int nin = Y.n[l];
       float* vt = smem + Y.s_vt[l];
       for (int idx = tid; idx < nin * Y.ld[l + 1]; idx += MLP_THREADS) vt[idx] = 0.f;
     }

@@ -37,9 +37,7 @@
 namespace b200rl {
 
 constexpr int T2_ROWS = 128;
-constexpr int T2_SLOT_WARPS = 8;
-constexpr int T2_SLOT_THREADS = T2_SLOT_WARPS * 32;
-constexpr int T2_EPI_WARPS = 2 * T2_SLOT_WARPS;
+constexpr int T2_EPI_WARPS = 16;  // one pool: 4 warps per TMEM lane quadrant, 16 columns each
 constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
 constexpr int T2_THREADS = T2_EPI_THREADS + 32;
 constexpr float T2_LOG_SQRT_2PI = 0.91893853320467274178f;
@@ -811,15 +809,6 @@ int tc2_take_slot(unsigned** status, unsigned* seq, float** scratch) {
   const unsigned slot = *seq % STATUS_SLOTS;
   *status = g_tc2.status + slot;
   *scratch = g_tc2.scratch + 40 * slot;
-  return 0;
-}
-
-int launch_absmax(const float* x, long long n, float* out, cudaStream_t s) {
-  if (n > 0) {
-    absmax_kernel<<<(int)std::min<long long>((n + 255) / 256, 2LL * 148), 256, 0, s>>>(x, n, out);
-    B200RL_CUDA(cudaGetLastError());
-    count_launch(1);
-  }
   return 0;
 }
 

@@ -132,19 +132,6 @@ __global__ void __launch_bounds__(GTHREADS) gemm_kernel(const GemmArgs g) {
   }
 }
 
-// db[n] = sum_rows dY[r][n] * act'(Y[r][n])
-__global__ void colsum_kernel(const float* dY, int ldd, const float* Y, int ldy, int act, int rows, int N, float* out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    float d = dY[(size_t)r * ldd + n];
-    if (Y) d *= op_act_prime(Y[(size_t)r * ldy + n], act);
-    s += d;
-  }
-  out[n] = s;
-}
-
 // X[r] = [obs[r] | act[r]]  (q_function.py:30 torch.cat([observation, action], -1))
 __global__ void concat_kernel(const float* obs, int O, const float* act, int lda, int A, int rows, float* X) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
