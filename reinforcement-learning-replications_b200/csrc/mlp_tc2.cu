@@ -304,6 +304,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
               W3_M = op2_mnmajor(ub + S2_W3, 16 * 128, T2_W3);
     bool acc_dw3 = false, acc_dw2 = false, acc_dw1 = false;  // the first product into an accumulator overwrites it
     uint32_t par0 = 0u, par1 = 0u;
+#ifdef B200RL_TC_TIMING
+    unsigned long long iacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     // The epilogue pool runs its jobs in a fixed order -- (slot 0, stage) then (slot 1, stage) -- and so does the
     // issuer: no polling, the slot is a compile-time constant of each call (descriptor arithmetic folds into
     // immediates on a uniform base), and products that accumulate into the shared gradient accumulators are issued in
@@ -314,9 +317,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
       const uint32_t tz = ut + (uint32_t)S * M2_SLOT;
       const uint32_t bar_chain = ubar + 16 + 8 * S, bar_off = ubar + 32 + 8 * S;
       uint32_t& par = S == 0 ? par0 : par1;
+#ifdef B200RL_TC_TIMING
+      long long it0 = clock64();
+#endif
       mbar_wait(ubar + 8 * S, par);  // every epilogue thread has delivered its share of the stage inputs
       par ^= 1u;
       tc_fence_after_sync();
+#ifdef B200RL_TC_TIMING
+      long long it1 = clock64();
+      iacc[6] += (unsigned long long)(it1 - it0);
+#endif
       if (stage == 0) {  // Z1 = X W1^T
         issue_chain3<2>(tz + M2_Z1, I_128_64_KM, op2_at(XD_K, so), W1T_M);
         umma_commit_elect(bar_chain);
@@ -347,6 +357,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         umma_commit_elect(bar_off);
       }
       __syncwarp();
+#ifdef B200RL_TC_TIMING
+      iacc[stage] += (unsigned long long)(clock64() - it1);
+#endif
     };
     for (long long kp = 0; kp < cta_tiles; kp += 2) {
 #pragma unroll 1
@@ -355,6 +368,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         if (kp + 1 < cta_tiles) serve(std::integral_constant<int, 1>{}, stage);
       }
     }
+#ifdef B200RL_TC_TIMING
+    if (lane == 0 && blockIdx.x == 0 && BACKWARD)
+      for (int i = 0; i < 8; ++i) g_tc2_t[16 + i] = iacc[i];
+#endif
   } else {
     // =============================== epilogue warps: one pool of 16 ===================================
     // Two tiles ("slots") are in flight, but the epilogue warps are NOT bound to a slot: all 16 work on one epilogue
