@@ -1,3 +1,4 @@
 from .batch_sampler import BatchSampler, Sampler
+from .vector_sampler import VectorSampler
 
-__all__ = ["Sampler", "BatchSampler"]
+__all__ = ["Sampler", "BatchSampler", "VectorSampler"]

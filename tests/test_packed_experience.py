@@ -65,3 +65,34 @@ def test_packed_experience_feeds_the_replay_buffer():
     y = rb.sample_minibatch(32)
     for k in x:
         np.testing.assert_array_equal(x[k], y[k])
+
+
+def test_vector_sampler_lockstep_rollouts_have_the_single_env_structure():
+    """VectorSampler: E toy environments in lock step, one batched policy call per step.  With a
+    deterministic policy each environment's rollout must equal what a BatchSampler produces on a twin environment."""
+    from rl_replicas_b200.samplers import VectorSampler
+
+    class Det:
+        def get_action_numpy(self, observation):
+            o = np.asarray(observation, np.float32)
+            return np.tanh(o[..., :2] * 0.5).astype(np.float32)  # batch-transparent
+
+    class SeededEnv(_Env):
+        def __init__(self, seed):
+            super().__init__()
+            self.rng = np.random.default_rng(seed)
+
+    n_env, per_env = 3, 40
+    vec = VectorSampler([SeededEnv(10 + e) for e in range(n_env)]).sample(n_env * per_env, Det())
+    packed = pack_experience(vec)
+    assert packed["obs"].shape == (n_env * per_env, 4) and packed["ep_offsets"][-1] == n_env * per_env
+    row = 0
+    for e in range(n_env):
+        single = pack_experience(BatchSampler(SeededEnv(10 + e)).sample(per_env, Det()))
+        n = single["obs"].shape[0]
+        np.testing.assert_array_equal(packed["obs"][row:row + n], single["obs"])
+        np.testing.assert_array_equal(packed["act"][row:row + n], single["act"])
+        np.testing.assert_array_equal(packed["rew"][row:row + n], single["rew"])
+        row += n
+    assert row == n_env * per_env
+    assert sum(vec.episode_lengths) == n_env * per_env and len(vec.episode_dones) == len(vec.episode_lengths)
