@@ -389,11 +389,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     bool first0 = true, first1 = true;
     const float sG = s_scale[SC_G];
     const float sH = pow2i(T2_H_EXP);
-    float* s_db3w = s_db3 + warp * 16;                       // this warp's running sum_r dOut[r][a]
-    double* s_scw = s_sc + warp * 6;                         // this warp's running scalar sums
-    if (lane < 16) s_db3w[lane] = 0.f;
-    if (lane < 6) s_scw[lane] = 0.0;
-    __syncwarp();
+    // per-thread running sums over the rows this thread handled as a loss thread (one tile in four): reduced once, in
+    // a fixed order, at the end of the kernel -- a warp reduction per tile would put ~130 dependent shuffles on the
+    // latency-bound loss job
+    double sc[6] = {0, 0, 0, 0, 0, 0};
+    float db3[15];
+#pragma unroll
+    for (int a = 0; a < 15; ++a) db3[a] = 0.f;
 
     float adv_mean = 0.f, adv_std = 1.f;  // normalize_tensor (utils.py:90-92): mean, UNBIASED std, no epsilon
     if (p.adv_stats != nullptr) {
@@ -513,7 +515,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
           tmem_ld16(tz + M2_OUT, o);
           tmem_wait_ld();
           float out[16], dout[16];
-          double sc[6] = {0, 0, 0, 0, 0, 0};
           const float u3 = s_scale[SC_U3];
 #pragma unroll
           for (int a = 0; a < 16; ++a) {
@@ -530,8 +531,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
                 term = diff * diff;
                 dout[0] = (2.f * diff) * p.inv_n;
               }
-              sc[0] = (double)term;
-              sc[5] = 1.0;
+              sc[0] += (double)term;
+              sc[5] += 1.0;
             } else {
               float dlp[16];
 #pragma unroll
@@ -591,30 +592,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
               }
 #pragma unroll
               for (int a = 0; a < 15; ++a) dout[a] = coef * dlp[a];
-              sc[0] = (double)term;
-              if (p.old_logp != nullptr) sc[1] = (double)(oldlp - lp);
-              sc[2] = (double)ent;
-              sc[3] = (double)lp;
-              sc[4] = (double)lp * (double)lp;
-              sc[5] = 1.0;
-            }
-          }
-          // scalar sums of this tile: warp tree, then this warp's running total (fixed order => reproducible)
-          if (p.scalar_partials != nullptr) {
-#pragma unroll
-            for (int kk = 0; kk < 6; ++kk) {
-              const double t = warp_sum(sc[kk]);
-              if (lane == 0) s_scw[kk] += t;
+              sc[0] += (double)term;
+              if (p.old_logp != nullptr) sc[1] += (double)(oldlp - lp);
+              sc[2] += (double)ent;
+              sc[3] += (double)lp;
+              sc[4] += (double)lp * (double)lp;
+              sc[5] += 1.0;
             }
           }
           if (BACKWARD) {
 #pragma unroll
-            for (int a = 0; a < 15; ++a) {
-              float t = dout[a];
-#pragma unroll
-              for (int o2 = 16; o2 > 0; o2 >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o2);
-              if (lane == 0 && a < A_out) s_db3w[a] += t;
-            }
+            for (int a = 0; a < 15; ++a) db3[a] += dout[a];
             float x0[8], x1[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -745,7 +733,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         if (m < h2) dst[p.b_off[1] + m] = __uint_as_float(v[15]) * s_scale[SC_OB];
       }
     }
-    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // every warp's running sums are final
+    // per-thread sums -> per-warp sums (tree) -> the 16 warps in order (below): fixed order => reproducible
+    if (BACKWARD) {
+#pragma unroll
+      for (int a = 0; a < 15; ++a) {
+        float t = db3[a];
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o2);
+        if (lane == 0) s_db3[warp * 16 + a] = t;
+      }
+    }
+    if (p.scalar_partials != nullptr) {
+#pragma unroll
+      for (int kk = 0; kk < 6; ++kk) {
+        const double t = warp_sum(sc[kk]);
+        if (lane == 0) s_sc[warp * 6 + kk] = t;
+      }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // every warp's sums are in shared memory
     if (BACKWARD && tid < A_out) {  // db3: the 16 per-warp totals in warp order
       float t = 0.f;
       for (int w = 0; w < T2_EPI_WARPS; ++w) t += s_db3[w * 16 + tid];
