@@ -418,7 +418,11 @@ def main():
             "roofline": {"kernel": "mlp_tc2_kernel<true> (tcgen05 fp16x2 policy fwd+loss+bwd, one launch per policy step; "
                                    "timed with the predicated wide-range re-run queued behind it)",
                          "bound": "tensor", "achieved": tf_pol, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": tf_pol / pk["tf_sust"], "traffic": None,
+                         "frac": tf_pol / pk["tf_sust"],
+                         "traffic": 105.9e6 if (E, T) == (1024, 1000) else None,
+                         "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of one ncu "
+                                         "--set full capture at this shape (profiles/r01_tc2_summary.md section 5; "
+                                         "algorithmic 100 B x 1.024 M rows = 102.4 MB)",
                          "note": f"fp32-equivalent algorithmic FLOPs ({FLOP_POLICY_STEP}/row) over the CUDA-event "
                                  f"launch time; peak = 16-bit dense sustained GEMM ({pk['src']}); the kernel executes 3 fp16 MMAs per "
                                  f"logical fp32 product",
@@ -430,7 +434,9 @@ def main():
                               "bytes_per_transition": 20, "ms_per_launch": ms_scan_pair,
                               "note": "16.4 MB problem: launch-latency bound at this size (SURVEY 7.3-3)"},
             "roofline_scan_large": {"kernel": "gae_scan_episode_kernel<double>", "bound": "hbm", "achieved": gbs_big,
-                                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_big / pk["hbm"], "traffic": None,
+                                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_big / pk["hbm"], "traffic": 1.269e9,
+                                    "traffic_note": "ncu --set full, profiles/r01_tc2_summary.md section 5 "
+                                                    "(algorithmic 1.311 GB)",
                                     "transitions": n_big, "bytes_per_transition": 20, "ms_per_launch": ms_big,
                                     "note": "65536 episodes x 1000 steps: 1.31 GB of algorithmic traffic (> L2)"},
             "update_flops_per_transition": FLOP_PER_TRANSITION,

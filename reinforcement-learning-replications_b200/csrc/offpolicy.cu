@@ -224,9 +224,13 @@ struct b200rl_offpolicy {
   // staged minibatches [S,B,*]
   float *obs = nullptr, *act = nullptr, *rew = nullptr, *nobs = nullptr, *done = nullptr, *eps = nullptr;
   // per-step workspace
-  float* acts[3][B200RL_MAX_LAYERS + 1];  // three activation stacks [B, width]: 0 scratch/target, 1 Q, 2 policy
+  float* acts[5][B200RL_MAX_LAYERS + 1];  // activation stacks [B, width]: 0 scratch/target (Q1 side), 1 Q1, 2 policy,
+                                          // 3 target Q2, 4 Q2 (the twin critic runs on a second stream)
   float *x_cat = nullptr, *x_cat2 = nullptr, *qt1 = nullptr, *qt2 = nullptr, *y = nullptr, *dq = nullptr;
   float *dbuf0 = nullptr, *dbuf1 = nullptr;  // gradient ping-pong [B, maxw]
+  float *dbuf2 = nullptr, *dbuf3 = nullptr, *dq2 = nullptr;  // the same for the twin critic's branch
+  cudaStream_t s2 = nullptr;                // side stream of the twin critic (forked / joined with events)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // outputs
   float *out_q1 = nullptr, *out_q2 = nullptr, *out_l1 = nullptr, *out_l2 = nullptr, *out_lp = nullptr;
   // CUDA graph of the S-step loop: node arguments are fixed per (S, B, hyper-parameters); what changes between calls
@@ -282,11 +286,11 @@ int net_forward(const NetBuf& nb, float* const* acts, int rows, cudaStream_t s) 
 // backward: dOut = gradient w.r.t. the network OUTPUT (after the output activation) [rows, nL] with ld ld_dout.
 // want_param_grads: write nb.grad (flat).  dx_out (optional): gradient w.r.t. the input [rows, n0].
 int net_backward(b200rl_offpolicy* h, const NetBuf& nb, float* const* acts, const float* dOut, int ld_dout, int rows,
-                 bool want_param_grads, float* dx_out, cudaStream_t s) {
+                 bool want_param_grads, float* dx_out, cudaStream_t s, bool twin_branch = false) {
   const int L = nb.d.n_layers;
   const float* dY = dOut;
   int ldd = ld_dout;
-  float* pp[2] = {h->dbuf0, h->dbuf1};
+  float* pp[2] = {twin_branch ? h->dbuf2 : h->dbuf0, twin_branch ? h->dbuf3 : h->dbuf1};
   for (int l = L - 1; l >= 0; --l) {
     const int nout = nb.d.sizes[l + 1], nin = nb.d.sizes[l];
     const int act = (l == L - 1) ? nb.d.out_act : nb.d.hidden_act;
@@ -366,7 +370,7 @@ extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200r
   rc |= oalloc(h, &h->nobs, S * B * O);
   rc |= oalloc(h, &h->done, S * B);
   rc |= oalloc(h, &h->eps, S * B * A);
-  for (int k = 0; k < 3; ++k)
+  for (int k = 0; k < 5; ++k)
     for (int l = 0; l <= B200RL_MAX_LAYERS; ++l) rc |= oalloc(h, &h->acts[k][l], B * (size_t)maxw);
   rc |= oalloc(h, &h->x_cat, B * (size_t)(O + A));
   rc |= oalloc(h, &h->x_cat2, B * (size_t)(O + A));
@@ -376,6 +380,9 @@ extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200r
   rc |= oalloc(h, &h->dq, B);
   rc |= oalloc(h, &h->dbuf0, B * (size_t)maxw);
   rc |= oalloc(h, &h->dbuf1, B * (size_t)maxw);
+  rc |= oalloc(h, &h->dbuf2, B * (size_t)maxw);
+  rc |= oalloc(h, &h->dbuf3, B * (size_t)maxw);
+  rc |= oalloc(h, &h->dq2, B);
   rc |= oalloc(h, &h->out_q1, S * B);
   rc |= oalloc(h, &h->out_q2, S * B);
   rc |= oalloc(h, &h->out_l1, S);
@@ -386,6 +393,9 @@ extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200r
   if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_adam_tab), 3 * S * sizeof(float2)) != cudaSuccess) rc = 1;
   if (!rc && cudaStreamCreateWithFlags(&h->gs, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
   if (!rc && cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) rc = 1;
+  if (!rc && cudaStreamCreateWithFlags(&h->s2, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
+  if (!rc && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = 1;
+  if (!rc && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) rc = 1;
   if (rc) {
     b200rl_offpolicy_destroy(h);
     return 1;
@@ -398,6 +408,9 @@ extern "C" void b200rl_offpolicy_destroy(b200rl_offpolicy* h) {
   if (!h) return;
   if (h->graph) cudaGraphExecDestroy(h->graph);
   if (h->ev) cudaEventDestroy(h->ev);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->s2) cudaStreamDestroy(h->s2);
   if (h->gs) cudaStreamDestroy(h->gs);
   if (h->h_adam_tab) cudaFreeHost(h->h_adam_tab);
   for (void* p : h->allocs) cudaFree(p);
@@ -486,11 +499,18 @@ static int enqueue_steps(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp
     tq[0] = h->x_cat2;
     for (int l = 1; l < Lq; ++l) tq[l] = h->acts[0][l];
     tq[Lq] = h->qt1;
-    if (net_forward(q1t, tq, B, s)) return 1;
-    if (td3) {
-      tq[Lq] = h->qt2;
-      if (net_forward(q2t, tq, B, s)) return 1;
+    if (td3) {  // the twin target critic runs concurrently on the side stream (its own activation stack)
+      B200RL_CUDA(cudaEventRecord(h->ev_fork, s));
+      B200RL_CUDA(cudaStreamWaitEvent(h->s2, h->ev_fork, 0));
+      float* tq2[B200RL_MAX_LAYERS + 1];
+      tq2[0] = h->x_cat2;
+      for (int l = 1; l < Lq; ++l) tq2[l] = h->acts[3][l];
+      tq2[Lq] = h->qt2;
+      if (net_forward(q2t, tq2, B, h->s2)) return 1;
+      B200RL_CUDA(cudaEventRecord(h->ev_join, h->s2));
     }
+    if (net_forward(q1t, tq, B, s)) return 1;
+    if (td3) B200RL_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
     td_target_kernel<<<(B + ew - 1) / ew, ew, 0, s>>>(s_rew, s_done, h->qt1, td3 ? h->qt2 : nullptr, (float)hp->gamma, B,
                                                       h->y);
     B200RL_CUDA(cudaGetLastError());
@@ -500,19 +520,27 @@ static int enqueue_steps(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp
     concat_kernel<<<(B * (O + A) + ew - 1) / ew, ew, 0, s>>>(s_obs, O, s_act, A, A, B, h->x_cat);
     B200RL_CUDA(cudaGetLastError());
     count_launch(1);
-    for (int qi = 0; qi < (td3 ? 2 : 1); ++qi) {
+    if (td3) {
+      B200RL_CUDA(cudaEventRecord(h->ev_fork, s));
+      B200RL_CUDA(cudaStreamWaitEvent(h->s2, h->ev_fork, 0));
+    }
+    for (int qi = (td3 ? 1 : 0); qi >= 0; --qi) {  // twin critic first: it goes to the side stream, Q1 stays on `s`
       NetBuf& qn = qi == 0 ? q1 : q2;
+      cudaStream_t qs = qi == 0 ? s : h->s2;
+      float* dq = qi == 0 ? h->dq : h->dq2;
       float* qa[B200RL_MAX_LAYERS + 1];
       qa[0] = h->x_cat;
-      for (int l = 1; l <= Lq; ++l) qa[l] = h->acts[1][l];
-      if (net_forward(qn, qa, B, s)) return 1;
-      q_loss_kernel<<<1, 1024, 0, s>>>(qa[Lq], h->y, B, h->dq, (qi == 0 ? h->out_l1 : h->out_l2) + st,
-                                       (qi == 0 ? h->out_q1 : h->out_q2) + (size_t)st * B);
+      for (int l = 1; l <= Lq; ++l) qa[l] = h->acts[qi == 0 ? 1 : 4][l];
+      if (net_forward(qn, qa, B, qs)) return 1;
+      q_loss_kernel<<<1, 1024, 0, qs>>>(qa[Lq], h->y, B, dq, (qi == 0 ? h->out_l1 : h->out_l2) + st,
+                                        (qi == 0 ? h->out_q1 : h->out_q2) + (size_t)st * B);
       B200RL_CUDA(cudaGetLastError());
       count_launch(1);
-      if (net_backward(h, qn, qa, h->dq, 1, B, true, nullptr, s)) return 1;
-      if (adam_net(qn, h->adam_tab + (size_t)(1 + qi) * maxS, st, hp->q_beta1, hp->q_beta2, hp->q_eps, s)) return 1;
+      if (net_backward(h, qn, qa, dq, 1, B, true, nullptr, qs, qi != 0)) return 1;
+      if (adam_net(qn, h->adam_tab + (size_t)(1 + qi) * maxS, st, hp->q_beta1, hp->q_beta2, hp->q_eps, qs)) return 1;
+      if (qi != 0) B200RL_CUDA(cudaEventRecord(h->ev_join, h->s2));
     }
+    if (td3) B200RL_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
     // ---- delayed policy step + polyak (td3.py:244-263, 301-323; ddpg: every step) ----
     if (st % hp->policy_delay == 0) {
       float* pa[B200RL_MAX_LAYERS + 1];
