@@ -1,8 +1,9 @@
 // mlp_tc2: second-generation tensor-core kernel for the fused MLP step (tcgen05 + TMEM, sm_100a only).
 //
 // Same contract and data flow as mlp_tc.cu / mlp_fused.cu (see mlp_fused.cu for the reference file:line map) and the
-// same shape gate (3 Linear layers, tanh hidden layers of width <= 64 -- zero-padded to 64 --, obs <= 32, out <= 15).  What changed, and why -- measured on
-// B200 with the per-stage clocks of tools/profile_step.py and the instruction micro-benchmark tools/tc_mma_bench.cu:
+// same shape gate (3 Linear layers, tanh hidden layers of width <= 64 -- zero-padded to 64 --, obs <= 32, out <= 15).
+// What changed, and why -- measured on B200 with the per-stage clocks of tools/profile_step.py and the instruction
+// micro-benchmark tools/tc_mma_bench.cu:
 //   * a tcgen05.mma of these small shapes costs 30..50 cycles whatever its size (instruction floor / SS-mode operand
 //     feed), so the 282 MMAs per 128-row tile of the bf16 x 3 kernel -- not the math -- set its pace.  Here every
 //     fp32 operand is split into TWO fp16 values x*2^e = h + l (22 mantissa bits, 3.0e-7 worst-case relative error

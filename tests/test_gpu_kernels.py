@@ -313,3 +313,27 @@ def test_tc2_mixed_feature_magnitudes_and_row_outlier():
     assert _fallbacks() == before + 1
     ref2 = O.value_loss_and_grad(layers, obs2, ret)
     assert rel_err(r2["grad"], ref2["grad"]) < TOL
+
+
+def test_absmax_helpers():
+    """b200rl_absmax / b200rl_absmax_cols: the range hints of the fp16 kernels (a NaN makes the result +inf, which the
+    kernels turn into a wide-range re-run)."""
+    import ctypes as C
+    import torch
+    from rl_replicas_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((5000, 17)) * 10.0 ** rng.uniform(-3, 3, 17)).astype(np.float32)
+    d = torch.from_numpy(x).cuda()
+    out = torch.full((32,), -1.0, device="cuda")
+    st = int(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.b200rl_absmax_cols(C.c_void_p(d.data_ptr()), 5000, 17, C.c_void_p(out.data_ptr()), st), "absmax_cols")
+    np.testing.assert_array_equal(out[:17].cpu().numpy(), np.abs(x).max(axis=0))
+    one = torch.zeros(1, device="cuda")
+    _lib.check(lib.b200rl_absmax(C.c_void_p(d.data_ptr()), x.size, C.c_void_p(one.data_ptr()), st), "absmax")
+    assert float(one.item()) == float(np.abs(x).max())
+    x[123, 4] = np.nan
+    d = torch.from_numpy(x).cuda()
+    _lib.check(lib.b200rl_absmax_cols(C.c_void_p(d.data_ptr()), 5000, 17, C.c_void_p(out.data_ptr()), st), "absmax_cols")
+    got = out[:17].cpu().numpy()
+    assert np.isinf(got[4]) and np.isfinite(np.delete(got, 4)).all()

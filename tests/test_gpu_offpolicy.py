@@ -190,3 +190,20 @@ def test_device_replay_gather_and_graph_replay_match_the_staged_path():
                 np.testing.assert_array_equal(a, b)
     finally:
         os.environ.pop("B200RL_OFFPOLICY_GRAPH", None)
+
+
+def test_train_gather_rejects_indices_outside_the_replay_columns():
+    from rl_replicas_b200._lib import B200RLError
+    rng = np.random.default_rng(0)
+    H = 32
+    mk = lambda sz: O.flatten_layers([(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+                                      for i, o in zip(sz[:-1], sz[1:])])
+    algo, rb = build(True, H, mk([O_DIM, H, H, A_DIM]), [mk([O_DIM + A_DIM, H, H, 1]), mk([O_DIM + A_DIM, H, H, 1])])
+    eng = algo._ensure_engine(2, 8)
+    rows = 100
+    cols = (torch.zeros(rows, O_DIM, device="cuda"), torch.zeros(rows, A_DIM, device="cuda"), torch.zeros(rows, device="cuda"),
+            torch.zeros(rows, O_DIM, device="cuda"), torch.zeros(rows, device="cuda"))
+    idx = np.zeros((2, 8), np.int64)
+    idx[1, 3] = rows  # one past the end
+    with pytest.raises(B200RLError, match="outside"):
+        eng.train_gather(algo._hparams(True, 2), cols, rows, idx, np.zeros((2, 8, A_DIM), np.float32))
