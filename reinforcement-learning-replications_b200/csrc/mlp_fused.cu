@@ -748,6 +748,15 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
   if (build_layout(a->mlp, backward, &k.lay, fvp)) return 2;
   const int L = k.lay.L;
   B200RL_REQUIRE(a->n_rows >= 0, "mlp_loss_grad: negative n_rows");
+  if (a->n_rows == 0) {  // an empty shard (data-parallel ranks may hold none): every partial row is zero
+    const int rows = b200rl_mlp_grid(&a->mlp, 0, fvp ? 2 : (backward ? 1 : ((a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC)) ? 3 : 0)));
+    B200RL_REQUIRE(rows > 0, "mlp_loss_grad: no CUDA device");
+    if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
+    if (backward) B200RL_CUDA(cudaMemsetAsync(a->partials, 0, (size_t)rows * k.lay.P * sizeof(float), s));
+    if (a->scalar_partials)
+      B200RL_CUDA(cudaMemsetAsync(a->scalar_partials, 0, (size_t)rows * B200RL_N_SCALARS * sizeof(double), s));
+    return 0;
+  }
   B200RL_REQUIRE(a->params && a->obs, "mlp_loss_grad: params/obs is NULL");
   B200RL_REQUIRE(a->loss >= B200RL_LOSS_EVAL && a->loss <= B200RL_LOSS_FVP, "mlp_loss_grad: bad loss %d", a->loss);
   if (a->dist == B200RL_DIST_NONE) {

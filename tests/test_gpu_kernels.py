@@ -337,3 +337,17 @@ def test_absmax_helpers():
     _lib.check(lib.b200rl_absmax_cols(C.c_void_p(d.data_ptr()), 5000, 17, C.c_void_p(out.data_ptr()), st), "absmax_cols")
     got = out[:17].cpu().numpy()
     assert np.isinf(got[4]) and np.isfinite(np.delete(got, 4)).all()
+
+
+@pytest.mark.parametrize("loss", ["eval", "mse"])
+def test_empty_launch_contributes_zeros(loss):
+    """n_rows = 0 (an empty data-parallel shard): every partial row and scalar is zero, nothing is read."""
+    from gpu_helpers import loss_grad
+    rng = np.random.default_rng(3)
+    sizes = [17, 64, 64, 1]
+    layers = _net(rng, sizes)
+    obs = np.zeros((0, 17), np.float32)
+    r = loss_grad(sizes, O.flatten_layers(layers), obs, loss, "none", target=np.zeros(0, np.float32) if loss == "mse" else None)
+    assert not r["scalars"].any()
+    if loss == "mse":
+        assert not r["grad"].any()
