@@ -248,8 +248,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     for (int i = tid; i < 64; i += T2_THREADS) {
       s_bias[i] = i < h1 ? __ldg(p.params + p.b_off[0] + i) : 0.f;
       s_bias[64 + i] = i < h2 ? __ldg(p.params + p.b_off[1] + i) : 0.f;
+      if (!(fabsf(s_bias[i]) < INFINITY) || !(fabsf(s_bias[64 + i]) < INFINITY)) bad = true;
     }
-    for (int i = tid; i < 16; i += T2_THREADS) s_bias[128 + i] = i < A_out ? __ldg(p.params + p.b_off[2] + i) : 0.f;
+    for (int i = tid; i < 16; i += T2_THREADS) {
+      s_bias[128 + i] = i < A_out ? __ldg(p.params + p.b_off[2] + i) : 0.f;
+      if (!(fabsf(s_bias[128 + i]) < INFINITY)) bad = true;
+    }
     if (p.dist == B200RL_DIST_GAUSSIAN)
       for (int a = tid; a < A_out; a += T2_THREADS) {
         const float scale = expf(__ldg(p.log_std + a));  // gaussian_policy.py:34
@@ -259,6 +263,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         s_dist[48 + a] = 1.f / (scale * scale);
       }
   }
+  if (bad) *s_bad = 1;  // non-finite bias
+  bad = false;
   if (warp == T2_EPI_WARPS) {
     tmem_alloc(smem_u32(s_tmem), 512);
     tmem_relinquish();
@@ -447,14 +453,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
           tc_fence_after_sync();
         }
         first = false;
-        float rmax = 0.f;
+        float rmax = 0.f, nan_probe = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           x[j] *= s_xs[8 * part + j];
-          rmax = fmaxf(rmax, fabsf(x[j]));
+          rmax = fmaxf(rmax, fabsf(x[j]));  // drops NaNs ...
+          nan_probe += x[j];                // ... so they are caught here
         }
         atomicMax(reinterpret_cast<int*>(s_rowmax + slot * 128 + r), __float_as_int(rmax));  // >= 0: int order
-        if (out_of_range8(x)) bad = true;
+        if (!(rmax <= T2_RANGE) || nan_probe != nan_probe) bad = true;
         store_chunk2(sm, so + S2_XD, r, part, x);
         arrive();
       } else if (stage == 1 || stage == 2) {
@@ -470,14 +477,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         float z[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[j] = fmaf(__uint_as_float(v[j]), unscale, bias[cs + j]);
-        tanh16(z);
-        float nan_probe = 0.f;
+        tanh16(z);  // |tanh| <= 1, and Z is finite: observations, weights and biases were all checked
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          nan_probe += z[j];
-          v[j] = __float_as_uint(z[j]);
-        }
-        if (nan_probe != nan_probe) bad = true;  // |tanh| <= 1: only a NaN pre-activation can break the range
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(z[j]);
         if (BACKWARD && stage == 1) t2_tmem_st16(tz + tm_col + cs, v);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
           load_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * fmaf(-(x[j] * hh), x[j], 1.f);
-          if (out_of_range8(x)) bad = true;
+          if (too_large8(x)) bad = true;
           store_chunk2(sm, so + S2_H2, r, (cs >> 3) + ch, x);
         }
         arrive();
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
             const float hv = __uint_as_float(h[8 * ch + j]);
             x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * (1.f - hv * hv);
           }
-          if (out_of_range8(x)) bad = true;
+          if (too_large8(x)) bad = true;
           store_chunk2(sm, so + S2_H1, r, (cs >> 3) + ch, x);
         }
         arrive();  // -> dW1 / db1, completion tracked by bar_off

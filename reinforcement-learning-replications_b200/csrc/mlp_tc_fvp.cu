@@ -217,8 +217,12 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
       for (int i = tid; i < 64; i += FV_THREADS) {
         bias[i] = i < h1 ? __ldg(src + p.b_off[0] + i) : 0.f;
         bias[64 + i] = i < h2 ? __ldg(src + p.b_off[1] + i) : 0.f;
+        if (!(fabsf(bias[i]) < INFINITY) || !(fabsf(bias[64 + i]) < INFINITY)) bad = true;
       }
-      for (int i = tid; i < 16; i += FV_THREADS) bias[128 + i] = i < A_out ? __ldg(src + p.b_off[2] + i) : 0.f;
+      for (int i = tid; i < 16; i += FV_THREADS) {
+        bias[128 + i] = i < A_out ? __ldg(src + p.b_off[2] + i) : 0.f;
+        if (!(fabsf(bias[128 + i]) < INFINITY)) bad = true;
+      }
     }
     if (p.dist == B200RL_DIST_GAUSSIAN)
       for (int a = tid; a < 16; a += FV_THREADS) {
@@ -226,6 +230,8 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
         s_ivar[a] = 1.f / (scale * scale);
       }
   }
+  if (bad) *s_bad = 1;  // non-finite bias
+  bad = false;
   if (warp == FV_EPI_WARPS) {
     tmem_alloc(smem_u32(s_tmem), 512);
     tmem_relinquish();
@@ -340,14 +346,9 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
         float z[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[j] = fmaf(__uint_as_float(v[j]), unscale, bias[cs + j]);
-        tanh16(z);
-        float nan_probe = 0.f;
+        tanh16(z);  // Z is finite: observations, weights and biases were all checked
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          nan_probe += z[j];
-          v[j] = __float_as_uint(z[j]);
-        }
-        if (nan_probe != nan_probe) bad = true;
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(z[j]);
         if (keep_fp32) t2_tmem_st16(tz + tm_z + cs, v);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * fmaf(-(x[j] * hh), x[j], 1.f);
-            if (out_of_range8(x)) bad = true;
+            if (too_large8(x)) bad = true;
             store_chunk2(sm, SF_H2, r, (cs >> 3) + ch, x);
           }
         }
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
               const float hv = __uint_as_float(h[8 * ch + j]);
               x[j] = (__uint_as_float(g[8 * ch + j]) * unscale) * (1.f - hv * hv);
             }
-            if (out_of_range8(x)) bad = true;
+            if (too_large8(x)) bad = true;
             store_chunk2(sm, SF_H1, r, (cs >> 3) + ch, x);
           }
         }
