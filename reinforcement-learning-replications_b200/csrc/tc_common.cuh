@@ -23,6 +23,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // the loop re-arms it.  `spin_guard` bounds the total wait so a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+#pragma unroll 1  // inlined at ~20 sites of the tensor-core kernels: keep the spin loop small (instruction cache)
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile(
         "{\n\t"
