@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs p) {
   if (p.run_if != nullptr && *p.run_if != p.seq) return;    // the fp16 kernel's result stands
   if (p.run_if != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_tc_fallbacks, 1ull);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches need no vote
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
   uint8_t* sm = smem_raw + (base - raw);

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
   extern __shared__ uint8_t smem_raw[];
   if (p.skip_flag != nullptr && *p.skip_flag != 0) return;  // early stop: whole launch is a no-op
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches need no vote
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
   uint8_t* sm = smem_raw + (base - raw);
@@ -318,9 +319,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     // issuer: no polling, the slot is a compile-time constant of each call (descriptor arithmetic folds into
     // immediates on a uniform base), and products that accumulate into the shared gradient accumulators are issued in
     // tile order, which makes a launch bit-reproducible.
-    auto serve = [&](auto slot_tag, const int stage) {
-      constexpr int S = decltype(slot_tag)::value;
-      constexpr uint32_t so = (uint32_t)S * T2_SLOT;
+    auto serve = [&](const int S, const int stage) {
+      const uint32_t so = (uint32_t)S * T2_SLOT;
       const uint32_t tz = ut + (uint32_t)S * M2_SLOT;
       const uint32_t bar_chain = ubar + 16 + 8 * S, bar_off = ubar + 32 + 8 * S;
       uint32_t& par = S == 0 ? par0 : par1;
@@ -371,8 +371,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     for (long long kp = 0; kp < cta_tiles; kp += 2) {
 #pragma unroll 1
       for (int stage = 0; stage < STAGES; ++stage) {
-        serve(std::integral_constant<int, 0>{}, stage);
-        if (kp + 1 < cta_tiles) serve(std::integral_constant<int, 1>{}, stage);
+#pragma unroll 1
+        for (int S = 0; S < 2; ++S)
+          if (kp + S < cta_tiles) serve(S, stage);
       }
     }
 #ifdef B200RL_TC_TIMING
