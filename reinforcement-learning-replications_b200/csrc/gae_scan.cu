@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) gae_scan_kernel(const ScanArg
   __shared__ double s_carry[2];
   __shared__ double s_red[2][SCAN_CONSUMERS / 32];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform role branch
   const int G = gridDim.x, c = blockIdx.x, T = p.num_tiles;
   const long long n = p.n;
   const int n_mine = (T - 1 - c) / G + 1;  // host guarantees G <= T
@@ -524,7 +525,8 @@ constexpr int EP_STAGES = 4;  // chunks in flight per warp (cp.async ring)
 template <typename RewT>
 __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const ScanArgs p, double2* ep_partial) {
   extern __shared__ __align__(16) unsigned char ep_smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: episode loops and bounds stay uniform
   const long long n_warps = (long long)gridDim.x * EP_WARPS;
   const RewT* __restrict__ rew = static_cast<const RewT*>(p.rew);
   double lp_r = 1.0, lp_a = 1.0;  // gamma^(8*(31-lane)): coefficient of the incoming carry for this lane
