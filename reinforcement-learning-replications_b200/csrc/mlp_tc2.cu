@@ -16,9 +16,11 @@
 //     MMA -> tanh -> MMA chain is latency bound.  Two fp16 splits instead of three bf16 ones make TWO tiles fit in
 //     shared memory (2 x 96 KB), so two tiles ("slots") are in flight per CTA.  All 16 epilogue warps work on one
 //     epilogue job at a time, alternating between the slots in a fixed order, so the MMAs a job hands to the issuer
-//     run under the other slot's next job; the issuer follows the same fixed order (no polling, the slot is a
-//     compile-time constant, K back-to-back MMAs go out as one asm block: ~3 instructions per MMA -- it shares its
-//     scheduler with four epilogue warps and was the bottleneck at 11).
+//     run under the other slot's next job; the issuer follows the same fixed order (no polling; K back-to-back MMAs
+//     go out as one asm block).  The warp index is read through __shfl_sync so that ptxas can prove the role branch
+//     warp-uniform: the issue path then stays in the uniform datapath (~6 instructions per MMA instead of 22 with a
+//     vote + R2UR moves around every MMA) -- the issuer shares its scheduler with four epilogue warps, and those
+//     four set the pace of every job.
 // fp16 has a narrow exponent range: the scales come from the data (max |W| per layer computed per CTA, max |obs| and
 // max |target| from a pre-pass or the caller) and every converted value is range-checked.  A launch that sees a
 // value outside +-60000 after scaling raises its slot in a status ring and the host has already queued the
@@ -316,9 +318,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     unsigned long long iacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     // The epilogue pool runs its jobs in a fixed order -- (slot 0, stage) then (slot 1, stage) -- and so does the
-    // issuer: no polling, the slot is a compile-time constant of each call (descriptor arithmetic folds into
-    // immediates on a uniform base), and products that accumulate into the shared gradient accumulators are issued in
-    // tile order, which makes a launch bit-reproducible.
+    // issuer: no polling (the slot only offsets the uniform descriptor bases: one copy of the issue code), and
+    // products that accumulate into the shared gradient accumulators are issued in tile order, which makes a launch
+    // bit-reproducible.
     auto serve = [&](const int S, const int stage) {
       const uint32_t so = (uint32_t)S * T2_SLOT;
       const uint32_t tz = ut + (uint32_t)S * M2_SLOT;
