@@ -233,12 +233,16 @@ class DDPG(_OffPolicyBase):
 
 
 def _make_eval_env(env):
-    """gym.make(env.spec.id) when gymnasium is importable (ref td3.py:76); otherwise evaluation reuses ``env``."""
+    """gym.make(env.spec.id) when gymnasium knows the environment (ref td3.py:76); otherwise an independent copy of
+    ``env`` -- evaluation must not step the environment the sampler is in the middle of an episode with."""
     try:
         import gymnasium as gym
         return gym.make(env.spec.id)
     except Exception:
-        return env
+        try:
+            return copy.deepcopy(env)
+        except Exception:
+            return env
 
 
 def _learn(self, num_epochs, batch_size, minibatch_size, num_start_steps, num_steps_before_update, num_train_steps,
