@@ -1,6 +1,7 @@
 // On-policy update engine: device-resident batch + flat parameters + Adam state, and the whole per-epoch update
 // (the reference's PPO.train / VPG.train, /root/reference/src/rl_replicas/algorithms/ppo.py:139-223, vpg.py:127-192)
 // as a host-sync-free stream of kernel launches.  See include/b200rl.h for the C ABI.
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -10,7 +11,7 @@
 namespace b200rl {
 
 static thread_local std::string g_error;
-static int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};  // engines of different host threads count into it
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -20,8 +21,8 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
   g_error = buf;
 }
-void count_launch(int n) { g_launches += n; }
-int64_t launches_total() { return g_launches; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launches_total() { return g_launches.load(std::memory_order_relaxed); }
 
 int device_sm_count() {
   int dev = 0, sms = 0;

@@ -818,22 +818,32 @@ struct Tc2State {
   unsigned* status = nullptr;  // [STATUS_SLOTS]
   float* scratch = nullptr;    // [STATUS_SLOTS][40] absmax pre-pass results: 32 observation features, then the target
   std::atomic<unsigned> seq{1};
-  bool configured = false;
 };
 Tc2State g_tc2;
+
+int tc2_configure() {  // once per process (one process drives one GPU): status ring, scratch, shared-memory opt-in
+  B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.status), STATUS_SLOTS * sizeof(unsigned)));
+  B200RL_CUDA(cudaMemset(g_tc2.status, 0, STATUS_SLOTS * sizeof(unsigned)));
+  B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.scratch), STATUS_SLOTS * 40 * sizeof(float)));
+  B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+  B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
+  return 0;
+}
 }  // namespace
 
-// next status-ring slot (shared by every fp16 tensor-core launch: mlp_tc2, mlp_tc_fvp)
+// next status-ring slot (shared by every fp16 tensor-core launch: mlp_tc2, mlp_tc_fvp).  A launch that must be redone
+// stores its own sequence number in its slot and the predicated re-run queued right behind it on the same stream
+// compares for equality, so a stale value from an earlier user of the slot can never fire it (0 is never handed out:
+// the ring starts zeroed).
 int tc2_take_slot(unsigned** status, unsigned* seq, float** scratch) {
-  if (!g_tc2.configured) {
-    B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.status), STATUS_SLOTS * sizeof(unsigned)));
-    B200RL_CUDA(cudaMemset(g_tc2.status, 0, STATUS_SLOTS * sizeof(unsigned)));
-    B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_tc2.scratch), STATUS_SLOTS * 40 * sizeof(float)));
-    B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
-    B200RL_CUDA(cudaFuncSetAttribute(mlp_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2_SMEM_BYTES));
-    g_tc2.configured = true;
+  static const int configured = tc2_configure();  // thread-safe one-time initialisation
+  if (configured != 0) {
+    set_error("mlp_tc2: the one-time device setup (status ring, shared-memory opt-in) failed earlier in this process");
+    return 1;
   }
-  *seq = g_tc2.seq.fetch_add(1);
+  do {
+    *seq = g_tc2.seq.fetch_add(1);
+  } while (*seq == 0u);
   const unsigned slot = *seq % STATUS_SLOTS;
   *status = g_tc2.status + slot;
   *scratch = g_tc2.scratch + 40 * slot;
