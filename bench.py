@@ -107,6 +107,10 @@ def cpu_reference_run(steps, warmup, n_envs=64, horizon=1000):
     n_envs x horizon transitions, the same 80 + 80 full-batch steps (throughput is size-independent to first order)."""
     import torch
     from oracle import onpolicy as O, torch_port as T
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is meant to use the host's cores
+    want = max(torch.get_num_threads(), (os.cpu_count() or 2) // 2)
+    if want != torch.get_num_threads():
+        torch.set_num_threads(want)
     pl, vl, log_std = make_nets()
     b = make_batch(n_envs, horizon, pl, seed=0)
     n = n_envs * horizon
