@@ -66,7 +66,7 @@ def _worker(rank, world, port, out):
 
 
 def test_dp_decomposition_world2_gloo():
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # fork() from a multi-threaded pytest process can deadlock
     out = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
