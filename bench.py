@@ -13,6 +13,9 @@ Workload at N GPUs: 1024 envs x 1000 steps PER GPU (BASELINE configs[1]; configs
   e2e   : same through the public API, PPO.train_packed(host batch): pinned-host -> device copies of the batch,
           parameter/optimizer-state upload, the update, and the device -> host read-back of parameters,
           optimizer state and the logged scalars, all inside the timed region.
+
+Only the two CPU legs (`cpu_baseline` of the default run, `--impl reference`) import `oracle/`; the measured arm builds its
+learners and synthetic data from `rl_replicas_b200.synthetic` alone.
 """
 from __future__ import annotations
 
@@ -166,9 +169,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import onpolicy as O  # only for the cpu_baseline leg and to flatten the initial nets
     from rl_replicas_b200 import _lib
-    from test_gpu_ppo import build as build_algo
+    from rl_replicas_b200 import synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -195,10 +197,8 @@ def main():
     h2d = sum(pinned[k].nbytes for k in pinned) + 2 * (5702 * 4 * 3 + 5377 * 4 * 3) // 2 + 5702 * 4 + ACT * 4
     d2h = (5702 + 5377) * 4 * 3 + 13 * 8
 
-    ppo = build_algo(POLICY_SIZES, VALUE_SIZES, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std,
-                     num_policy_gradients=N_POLICY, num_value_gradients=N_VALUE, max_kl_divergence=float("inf"),
-                     distributed=distributed)
-    ppo.metrics_manager = None
+    ppo = synthetic.onpolicy_learner("ppo", pl, vl, log_std, num_policy_gradients=N_POLICY, num_value_gradients=N_VALUE,
+                                     max_kl_divergence=float("inf"), distributed=distributed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -301,20 +301,14 @@ def main():
     # ---------------- BASELINE configs 3 and 4 (rank 0 only; reported as extra fields, not the headline) ----------------
     def trpo_config3():
         """TRPO synthetic Ant-shaped obs(27) act(8), 1024 envs x 1000 steps, CG iters 10 (11 FVPs), 80 value steps."""
-        import types
-        from rl_replicas_b200 import synthetic
-        from test_gpu_trpo import build_trpo
         rng = np.random.default_rng(1)
         ps, vs = [27, 64, 64, 8], [27, 64, 64, 1]
         mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
                          for i, o in zip(sz[:-1], sz[1:])]
         pl2, vl2 = mk(ps), mk(vs)
-        g = {"policy_sizes": ps, "value_sizes": vs, "policy_flat0": O.flatten_layers(pl2),
-             "value_flat0": O.flatten_layers(vl2), "log_std": np.full(8, -0.5, np.float32)}
-        trpo = build_trpo(g, num_value_gradients=N_VALUE)
-        trpo.metrics_manager = None
+        trpo = synthetic.onpolicy_learner("trpo", pl2, vl2, np.full(8, -0.5, np.float32), num_value_gradients=N_VALUE)
         b = synthetic.fixed_batch(E, T, 27, 8, seed=9, frac_not_done=0.1,
-                                  mean_fn=lambda o: O.mlp_forward(pl2, o)[0])
+                                  mean_fn=lambda o: synthetic.numpy_mlp(pl2, o))
         for _ in range(2):
             trpo.train_packed(b)
         torch.cuda.synchronize()
@@ -346,14 +340,12 @@ def main():
     def td3_config4():
         """TD3 synthetic Hopper-shaped replay (obs 11, act 3), minibatch 256, 256-256 nets, 50 train steps per call."""
         from rl_replicas_b200.experience import Experience
-        from test_gpu_offpolicy import build as build_off
         rng = np.random.default_rng(2)
         H = 256
         mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
                          for i, o in zip(sz[:-1], sz[1:])]
         PSz, QSz = [11, H, H, 3], [14, H, H, 1]
-        algo, rb = build_off(True, H, O.flatten_layers(mk(PSz)), [O.flatten_layers(mk(QSz)), O.flatten_layers(mk(QSz))])
-        algo.metrics_manager = None
+        algo, rb = synthetic.offpolicy_learner(True, mk(PSz), [mk(QSz), mk(QSz)])
         n_rb = 100000  # sampling cost does not depend on the buffer size; 1 M Python-list entries only cost host RAM/time
         ex = Experience()
         obs_rb = rng.standard_normal((n_rb + 1, 11)).astype(np.float32)

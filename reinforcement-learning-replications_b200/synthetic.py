@@ -88,3 +88,83 @@ def to_experience_lists(batch: Dict[str, np.ndarray], discrete: bool):
     return dict(observations=observations, actions=actions, rewards=rewards, last_observations=last_observations,
                 dones=dones, episode_returns=[float(sum(r)) for r in rewards],
                 episode_lengths=[len(r) for r in rewards])
+
+
+# ---- learners on given parameters (bench.py, tools/): plain (W [out, in], b [out]) numpy pairs per layer ------------
+def flatten_layers(layers) -> np.ndarray:
+    """[(W, b), ...] -> the flat f32 parameter vector in torch's ``parameters()`` order (W row-major, then b)."""
+    return np.concatenate([np.concatenate([np.asarray(w, np.float32).reshape(-1), np.asarray(b, np.float32).reshape(-1)])
+                           for w, b in layers])
+
+
+def numpy_mlp(layers, x: np.ndarray, hidden: str = "tanh") -> np.ndarray:
+    """Forward pass on the host, used to draw on-policy-like synthetic actions around the initial policy's mean."""
+    h = np.asarray(x, np.float32)
+    for i, (w, b) in enumerate(layers):
+        h = h @ np.asarray(w, np.float32).T + np.asarray(b, np.float32)
+        if i < len(layers) - 1:
+            h = np.tanh(h) if hidden == "tanh" else np.maximum(h, 0.0)
+    return h
+
+
+def _mlp_from_layers(layers, hidden_activation, output_activation):
+    import torch
+    from .networks import MLP
+    sizes = [int(np.asarray(layers[0][0]).shape[1])] + [int(np.asarray(w).shape[0]) for w, _ in layers]
+    net = MLP(sizes, hidden_activation, output_activation)
+    linears = [m for m in net.network if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for lin, (w, b) in zip(linears, layers):
+            lin.weight.copy_(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)))
+            lin.bias.copy_(torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)))
+    return net
+
+
+def onpolicy_learner(algo: str, policy_layers, value_layers, log_std: Optional[np.ndarray] = None, **hparams):
+    """PPO / VPG / TRPO on the given initial parameters (Gaussian policy when ``log_std`` is given, else categorical),
+    with the recipes' optimizers (Adam 3e-4 / 1e-3, conjugate gradient for TRPO), no env, no sampler, no logging."""
+    import torch
+    from .algorithms import PPO, TRPO, VPG
+    from .optimizers import ConjugateGradientOptimizer
+    from .policies import CategoricalPolicy, GaussianPolicy
+    from .value_function import ValueFunction
+    pnet = _mlp_from_layers(policy_layers, torch.nn.Tanh, torch.nn.Identity)
+    vnet = _mlp_from_layers(value_layers, torch.nn.Tanh, torch.nn.Identity)
+    popt = (ConjugateGradientOptimizer(pnet.parameters()) if algo == "trpo"
+            else torch.optim.Adam(pnet.parameters(), lr=3e-4))
+    if log_std is not None:
+        policy = GaussianPolicy(pnet, popt, torch.nn.Parameter(torch.from_numpy(np.asarray(log_std, dtype=np.float32))))
+    else:
+        policy = CategoricalPolicy(pnet, popt)
+    value_function = ValueFunction(vnet, torch.optim.Adam(vnet.parameters(), lr=1e-3))
+    learner = {"ppo": PPO, "vpg": VPG, "trpo": TRPO}[algo](policy, value_function, None, None, **hparams)
+    learner.metrics_manager = None
+    learner.current_total_steps = 0
+    return learner
+
+
+def offpolicy_learner(twin: bool, policy_layers, q_layers_list):
+    """TD3 (``twin``) / DDPG on the given initial parameters with an empty ReplayBuffer; returns (learner, buffer)."""
+    import types
+    import torch
+    from .algorithms import DDPG, TD3
+    from .policies import DeterministicPolicy, RandomPolicy
+    from .q_function import QFunction
+    from .replay_buffer import ReplayBuffer
+    pnet = _mlp_from_layers(policy_layers, torch.nn.ReLU, torch.nn.Tanh)
+    act_dim = int(np.asarray(policy_layers[-1][0]).shape[0])
+    policy = DeterministicPolicy(pnet, torch.optim.Adam(pnet.parameters(), lr=1e-3))
+    critics = []
+    for layers in q_layers_list:
+        qnet = _mlp_from_layers(layers, torch.nn.ReLU, torch.nn.Identity)
+        critics.append(QFunction(qnet, torch.optim.Adam(qnet.parameters(), lr=1e-3)))
+    env = types.SimpleNamespace(action_space=types.SimpleNamespace(high=np.ones(act_dim, np.float32), shape=(act_dim,)),
+                                spec=types.SimpleNamespace(id="synthetic"))
+    buffer = ReplayBuffer()
+    if twin:
+        learner = TD3(policy, RandomPolicy(None), critics[0], critics[1], env, None, buffer, None)
+    else:
+        learner = DDPG(policy, RandomPolicy(None), critics[0], env, None, buffer, None)
+    learner.metrics_manager = None
+    learner.current_total_steps = 0
+    return learner, buffer

@@ -49,3 +49,32 @@ def test_metrics_manager_prints_every_scalar_and_keeps_tensorboard_optional(tmp_
     assert out == ["epoch: 3       ", "policy/loss: -0.0123 "]  # the reference's "{}: {:<8.3g}" lines
     if mm.tensorboard_writer is not None:  # TensorBoard installed: an event file under <log_dir>/tensorboard
         assert any(f.startswith("events.out.tfevents") for f in os.listdir(os.path.join(tmp_path, "tensorboard")))
+
+
+def test_synthetic_learners_hold_the_given_parameters():
+    """bench.py builds its learners from plain (W, b) pairs through rl_replicas_b200.synthetic (no oracle import on the
+    measured arm): the flat order is torch's parameters() order and the recipes' optimizers are attached."""
+    import numpy as np
+
+    from rl_replicas_b200 import synthetic
+    from rl_replicas_b200.optimizers import ConjugateGradientOptimizer
+    rng = np.random.default_rng(0)
+    mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32), rng.standard_normal(o).astype(np.float32))
+                     for i, o in zip(sz[:-1], sz[1:])]
+    pl, vl = mk([5, 64, 32, 3]), mk([5, 64, 32, 1])
+    vec = lambda m: torch.nn.utils.parameters_to_vector(m.parameters()).detach().numpy()
+    ppo = synthetic.onpolicy_learner("ppo", pl, vl, np.full(3, -0.5, np.float32), num_policy_gradients=2)
+    assert np.array_equal(vec(ppo.policy.network), synthetic.flatten_layers(pl))
+    assert np.array_equal(vec(ppo.value_function.network), synthetic.flatten_layers(vl))
+    assert ppo.num_policy_gradients == 2 and ppo.policy.optimizer.defaults["lr"] == 3e-4
+    assert np.array_equal(vec(ppo.old_policy.network), synthetic.flatten_layers(pl))
+    trpo = synthetic.onpolicy_learner("trpo", pl, vl)  # no log_std: categorical
+    assert isinstance(trpo.policy.optimizer, ConjugateGradientOptimizer) and type(trpo.policy).__name__ == "CategoricalPolicy"
+    x = rng.standard_normal((4, 5)).astype(np.float32)
+    np.testing.assert_allclose(synthetic.numpy_mlp(pl, x), ppo.policy.network(torch.from_numpy(x)).detach().numpy(),
+                               rtol=1e-5, atol=1e-5)
+    td3, buffer = synthetic.offpolicy_learner(True, mk([4, 16, 16, 2]), [mk([6, 16, 16, 1]), mk([6, 16, 16, 1])])
+    assert type(td3).__name__ == "TD3" and td3.replay_buffer is buffer
+    assert np.array_equal(vec(td3.target_policy.network), vec(td3.policy.network))
+    ddpg, _ = synthetic.offpolicy_learner(False, mk([4, 16, 16, 2]), [mk([6, 16, 16, 1])])
+    assert type(ddpg).__name__ == "DDPG"
