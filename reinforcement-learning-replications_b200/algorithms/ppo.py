@@ -120,13 +120,15 @@ class PPO(OnPolicyTrainerMixin):
             "value_function_optimizer_state_dict": self.value_function.optimizer.state_dict(),
         }, model_path)
 
-    def load_model(self, model_path: str) -> int:
+    def load_model(self, model_path: str, trust_checkpoint: bool = False) -> int:
         """Resume from a checkpoint written by ``save_model`` -- or by the reference's (same dictionary layout,
         ref ppo.py:296-306; the shipped benchmarks/*/model.pt load as warm starts).  Restores both networks, both
         optimizer states (Adam moments and step counts -- the next ``train`` continues the bias correction where the run
         stopped) and ``current_total_steps``; returns the saved epoch.  The reference has no loader; a
-        Gaussian policy's ``log_std`` is not part of the checkpoint there either and keeps its constructor value."""
-        ckpt = torch.load(model_path, map_location="cpu", weights_only=False)
+        Gaussian policy's ``log_std`` is not part of the checkpoint there either and keeps its constructor value.
+        The file is read with ``weights_only=True`` (tensors, numbers and optimizer state dictionaries -- everything
+        ``save_model`` writes); ``trust_checkpoint=True`` allows arbitrary pickles for legacy files you trust."""
+        ckpt = torch.load(model_path, map_location="cpu", weights_only=not trust_checkpoint)
         self.policy.network.load_state_dict(ckpt["policy_state_dict"])
         self.value_function.network.load_state_dict(ckpt["value_function_state_dict"])
         for module, key in ((self.policy, "policy_optimizer_state_dict"),

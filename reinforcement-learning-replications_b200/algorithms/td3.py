@@ -30,10 +30,10 @@ class _OffPolicyBase:
         tq = [self.target_q_function_1, self.target_q_function_2] if self.n_q == 2 else [self.target_q_function]
         return self._trainable(), [self.target_policy] + tq
 
-    def load_model(self, model_path: str) -> int:
+    def load_model(self, model_path: str, trust_checkpoint: bool = False) -> int:
         """Resume from a checkpoint written by ``save_model`` or by the reference (same layout, ref td3.py:367-382 /
         ddpg.py:295-314): trainable networks, their Adam states, the target networks; returns the saved epoch."""
-        ckpt = torch.load(model_path, map_location="cpu", weights_only=False)
+        ckpt = torch.load(model_path, map_location="cpu", weights_only=not trust_checkpoint)
         names = ["policy"] + (["q_function_1", "q_function_2"] if self.n_q == 2 else ["q_function"])
         trainable, targets = self._nets()
         for name, module, target in zip(names, trainable, targets):

@@ -160,6 +160,10 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
   B200RL_REQUIRE(cfg->value.sizes[cfg->value.n_layers] == 1, "onpolicy_create: value network must have one output");
   B200RL_REQUIRE(cfg->dist == B200RL_DIST_GAUSSIAN || cfg->dist == B200RL_DIST_CATEGORICAL,
                  "onpolicy_create: dist must be GAUSSIAN or CATEGORICAL");
+  // log_std and the loss epilogues are sized for 16 action dimensions (set_log_std would otherwise write past them)
+  B200RL_REQUIRE(cfg->dist != B200RL_DIST_GAUSSIAN || cfg->policy.sizes[cfg->policy.n_layers] <= 16,
+                 "onpolicy_create: a Gaussian policy supports at most 16 action dimensions, got %d",
+                 cfg->policy.sizes[cfg->policy.n_layers]);
   const int sms = device_sm_count();
   B200RL_REQUIRE(sms > 0, "onpolicy_create: no CUDA device (%s)", cudaGetErrorString(cudaGetLastError()));
   b200rl_onpolicy* h = new b200rl_onpolicy();

@@ -64,10 +64,15 @@ class PackedExperience(Experience):
     available as views built on demand, so code written against ``Experience`` keeps working.
     ``pinned=True`` allocates the arrays in page-locked memory (one DMA per column to the GPU)."""
 
-    def __init__(self, capacity: int, observation_size: int, action_size: int, pinned: bool = False):
+    def __init__(self, capacity: int, observation_size: int, action_size: int, pinned: bool = False,
+                 scalar_actions: bool = False):
+        """``scalar_actions=True`` (or ``action_size=0``): actions are 0-d values (Discrete spaces: the index a
+        CategoricalPolicy samples); ``packed()["act"]`` is then ``[N]`` as the engine's categorical path expects,
+        and the ``actions`` view holds 0-d entries like the reference's lists."""
         self.episode_returns, self.episode_lengths = [], []  # the five trajectory fields are views (properties below)
         self.capacity, self._n, self._start = int(capacity), 0, 0
-        self._o, self._a = int(observation_size), int(action_size)
+        self._o = int(observation_size)
+        self._a = 0 if scalar_actions else int(action_size)
 
         def alloc(shape, dtype):
             if pinned:
@@ -101,6 +106,22 @@ class PackedExperience(Experience):
         self._last.append(np.asarray(last_observation, dtype=np.float32).reshape(-1).copy())
         self.episode_returns.append(float(self._rew[begin:self._n].sum()) if episode_return is None else episode_return)
         self.episode_lengths.append(self._n - begin)
+
+    def append_episode(self, observations, actions, rewards, dones, last_observation) -> None:
+        """A whole episode at once: ``[L,O]`` / ``[L,A]`` (or ``[L]``) / ``[L]`` / ``[L]`` arrays, one slice copy per
+        column (what a vectorised sampler flushes; ``append_step`` per transition is a Python call per row)."""
+        n = len(rewards)
+        i = self._n
+        if n == 0:
+            raise ValueError("append_episode: the episode is empty")
+        if i + n > self.capacity:
+            raise IndexError("PackedExperience is full")
+        self._obs[i:i + n] = np.asarray(observations, dtype=np.float32).reshape(n, -1)
+        self._act[i:i + n] = np.asarray(actions, dtype=np.float32).reshape(n, -1)
+        self._rew[i:i + n] = rewards
+        self._done[i:i + n] = dones
+        self._n = i + n
+        self.end_episode(last_observation)
 
     # ---- consumer side: what the engine uploads (views, no copy) ----
     def packed(self):

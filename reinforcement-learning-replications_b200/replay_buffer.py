@@ -82,9 +82,16 @@ class ReplayBuffer:
             if first < n:
                 col[:n - first] = arr[first:]
         self.current_size += n
-        self._dev_dirty.append((start, first))
-        if first < n:
-            self._dev_dirty.append((0, n - first))
+        if self._dev is not None:  # no mirror yet: its first build uploads everything anyway
+            self._dev_dirty.append((start, first))
+            if first < n:
+                self._dev_dirty.append((0, n - first))
+            if len(self._dev_dirty) > 256:  # many small appends between two train() calls: one full refresh is cheaper
+                self._dev_dirty = self._live_ranges()
+
+    def _live_ranges(self) -> List:
+        first = min(self.current_size, self._capacity - self._head)  # the rows that hold data, wrap-around aware
+        return [(self._head, first)] + ([(0, self.current_size - first)] if first < self.current_size else [])
 
     # ---- device mirror: the columns as float32 CUDA tensors, refreshed incrementally ----
     def physical_rows(self, logical: np.ndarray) -> np.ndarray:
@@ -99,8 +106,7 @@ class ReplayBuffer:
             raise ValueError("device_columns: the buffer is empty")
         if self._dev is None:
             self._dev = tuple(torch.zeros(self._cols[k].shape, dtype=torch.float32, device="cuda") for k in self.COLUMNS)
-            first = min(self.current_size, self._capacity - self._head)  # the rows that hold data, wrap-around aware
-            self._dev_dirty = [(self._head, first)] + ([(0, self.current_size - first)] if first < self.current_size else [])
+            self._dev_dirty = self._live_ranges()
         for start, count in self._dev_dirty:
             for k, d in zip(self.COLUMNS, self._dev):
                 host = np.ascontiguousarray(self._cols[k][start:start + count], dtype=np.float32)

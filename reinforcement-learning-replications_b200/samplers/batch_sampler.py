@@ -57,7 +57,8 @@ class BatchSampler(Sampler):
             observation = self.observation
             action = policy.get_action_numpy(observation)
             if exp is None:
-                exp = PackedExperience(num_samples, np.asarray(observation).size, np.asarray(action).size, self.pinned)
+                exp = PackedExperience(num_samples, np.asarray(observation).size, np.asarray(action).size, self.pinned,
+                                       scalar_actions=np.asarray(action).ndim == 0)
             self.observation, reward, terminated, truncated, _ = self.env.step(action)
             finished = terminated or truncated
             exp.append_step(observation, action, reward, finished)

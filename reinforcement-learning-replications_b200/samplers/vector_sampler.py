@@ -70,12 +70,11 @@ class VectorSampler(Sampler):
                     last_obs[e].append(np.asarray(self.observations[e], np.float32).reshape(-1).copy())
                     if finished:
                         self.observations[e], _ = env.reset()
-        exp = PackedExperience(num_samples, obs_dim, act_dim, self.pinned)
-        for e in range(n_env):
+        exp = PackedExperience(num_samples, obs_dim, act_dim, self.pinned, scalar_actions=np.asarray(probe[0]).ndim == 0)
+        for e in range(n_env):  # one block copy per episode (ref batch_sampler.py:66-78 closes episodes one by one)
             begin = 0
             for end, last in zip(ends[e], last_obs[e]):
-                for t in range(begin, end):
-                    exp.append_step(obs_buf[e, t], act_buf[e, t], rew_buf[e, t], done_buf[e, t])
-                exp.end_episode(last)
+                exp.append_episode(obs_buf[e, begin:end], act_buf[e, begin:end], rew_buf[e, begin:end],
+                                   done_buf[e, begin:end], last)
                 begin = end
         return exp

@@ -96,3 +96,29 @@ def test_vector_sampler_lockstep_rollouts_have_the_single_env_structure():
         row += n
     assert row == n_env * per_env
     assert sum(vec.episode_lengths) == n_env * per_env and len(vec.episode_dones) == len(vec.episode_lengths)
+
+
+class _DiscretePolicy:
+    def __init__(self):
+        self.rng = np.random.default_rng(7)
+
+    def get_action_numpy(self, observation):
+        o = np.asarray(observation)
+        if o.ndim == 2:  # batched call of the VectorSampler
+            return self.rng.integers(0, 3, o.shape[0])
+        return np.asarray(self.rng.integers(0, 3))  # 0-d, like CategoricalPolicy.get_action_numpy on one observation
+
+
+def test_packed_rollout_with_scalar_actions_has_the_categorical_layout():
+    """Discrete action spaces: the reference's lists hold 0-d actions and the engine's categorical path wants
+    act [N] -- the packed store must produce exactly what flattening the nested lists produces."""
+    from rl_replicas_b200.samplers import VectorSampler
+    nested = BatchSampler(_Env(), seed=0).sample(50, _DiscretePolicy())
+    packed = BatchSampler(_Env(), seed=0, packed=True).sample(50, _DiscretePolicy())
+    a, b = pack_experience(nested), pack_experience(packed)
+    assert a["act"].shape == (50,) and b["act"].shape == (50,)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    assert np.asarray(packed.actions[0][0]).ndim == 0
+    vec = pack_experience(VectorSampler([_Env(), _Env()]).sample(40, _DiscretePolicy()))
+    assert vec["act"].shape == (40,) and vec["act"].dtype == np.float32
