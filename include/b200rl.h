@@ -259,8 +259,34 @@ int b200rl_onpolicy_fvp(b200rl_onpolicy* h, const float* host_v, float* host_out
  *       "policy_params","old_policy_params","value_params" */
 int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr, int64_t* count, int32_t* dtype);
 
-/* Whole path through HOST buffers (what `e2e` in bench.py times): H2D batch + parameters/Adam state, update, D2H. */
+/* Per-launch scalar sums of the LAST update, as read back by it (host copy, no device work): out[slot][k], k as in
+ * b200rl_mlp_loss_grad_args.scalar_partials, already summed over CTAs (and ranks).  PPO: slot i = forward pass of
+ * policy step i (so slot i+1, k=1, divided by the row count is the approximate KL after step i, ppo.py:176-178; slot
+ * K = the forward-only pass after the last step), slots K+1.. = value steps (k=0: sum of squared errors).
+ * *n_slots = slots available; at most max_slots are copied. */
+int b200rl_onpolicy_scalar_history(b200rl_onpolicy* h, double* out, int32_t max_slots, int32_t* n_slots);
+
+/* Profiling hook (not on the product path): runs ONE named stage of the update on the loaded batch -- "values",
+ * "preamble", "scan", "old_logp", "policy_grad", "policy_grad_kernel", "value_grad", "value_grad_kernel", "fvp" --
+ * so that bench.py can time single kernels with CUDA events and ncu can capture them.  Asynchronous.
+ * Note: the fp16 tensor-core kernels keep one status ring per PROCESS on the device that was current at their first
+ * launch: one process drives one GPU (the torchrun / one-rank-per-GPU model of SURVEY 8e). */
 int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, const b200rl_ppo_hparams* hp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stand-alone helpers behind rl_replicas.utils' public functions, for callers that use them outside train()
+ * (device pointers; float64 where the reference computes in float64).
+ *   b200rl_discounted_cumsum: out[t] = x[t] + discount * out[t+1]            ref: utils.py:14-28 (scipy lfilter, f64)
+ *   b200rl_gae_f64: delta[t] = rewards[t] + gamma*values[t+1] - values[t], t < n (rewards / values hold n+1 entries),
+ *                   out = discounted_cumsum(delta, gamma*gae_lambda)          ref: utils.py:31-44
+ *   b200rl_normalize: out = (x - mean(x)) / std(x), unbiased std, no epsilon  ref: utils.py:90-92
+ *   b200rl_polyak: target = f32(rho)*target + f32(1-rho)*param                ref: utils.py:47-57
+ * ------------------------------------------------------------------------------------------------------------ */
+int b200rl_discounted_cumsum(const double* x, int64_t n, double discount, double* out, void* stream);
+int b200rl_gae_f64(const double* rewards, const double* values, int64_t n, double gamma, double gae_lambda, double* out,
+                   void* stream);
+int b200rl_normalize(const float* x, int64_t n, float* out, void* stream);
+int b200rl_polyak(float* target, const float* param, int64_t n, double rho, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Off-policy update engine (DDPG / TD3): the reference's `train(replay_buffer, num_train_steps, minibatch_size)`

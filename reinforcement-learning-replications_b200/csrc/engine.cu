@@ -68,6 +68,7 @@ struct b200rl_onpolicy {
   float *pol_grad = nullptr, *val_grad = nullptr;  // [P + N_SCALARS]
   double* slots = nullptr;                         // [n_slots][N_SCALARS] scalar history
   int n_slots = 0;
+  int last_slots = 0;  // slots the last update wrote (and read back into h_slots)
   int* flags = nullptr;  // 0 stop flag, 1 policy steps applied, 2 value steps applied
   double* h_slots = nullptr;  // pinned
   int* h_flags = nullptr;     // pinned
@@ -438,6 +439,7 @@ static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_a
   // ---- one device->host read of the statistics ----
   B200RL_CUDA(cudaMemcpyAsync(h->h_slots, h->slots, (size_t)(K + Kv + 2) * B200RL_N_SCALARS * sizeof(double),
                               cudaMemcpyDeviceToHost, s));
+  h->last_slots = K + Kv + 2;
   B200RL_CUDA(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaMemcpyAsync(h->h_stats3, h->adv_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaStreamSynchronize(s));
@@ -626,6 +628,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
 
   B200RL_CUDA(cudaMemcpyAsync(h->h_slots, h->slots, (size_t)n_slots * B200RL_N_SCALARS * sizeof(double),
                               cudaMemcpyDeviceToHost, s));
+  h->last_slots = n_slots;
   B200RL_CUDA(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaMemcpyAsync(h->h_stats3, h->adv_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaMemcpyAsync(h->h_cg_sc, h->cg_sc, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -693,6 +696,14 @@ extern "C" int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name,
     }
   set_error("device_view: unknown view '%s'", name);
   return 2;
+}
+
+extern "C" int b200rl_onpolicy_scalar_history(b200rl_onpolicy* h, double* out, int32_t max_slots, int32_t* n_slots) {
+  B200RL_REQUIRE(h && out && n_slots && max_slots >= 0, "scalar_history: bad argument");
+  const int n = h->last_slots < max_slots ? h->last_slots : max_slots;
+  if (n > 0) memcpy(out, h->h_slots, (size_t)n * B200RL_N_SCALARS * sizeof(double));
+  *n_slots = h->last_slots;
+  return 0;
 }
 
 // Single stages on the loaded batch, for kernel-level timing (bench.py roofline) and ncu captures.

@@ -172,10 +172,31 @@ class OnPolicyEngine:
 
         return _lib.ALLREDUCE_FN(cb)
 
-    def update(self, hp: PpoHparams, algo: str = "ppo", process_group=None, distributed: bool = False) -> UpdateStats:
+    def _make_allreduce_from(self, fn):
+        import torch
+
+        def cb(user, buf, count, dtype, stream):
+            try:
+                fn(torch.as_tensor(_CudaArray(buf, count, "<f8" if dtype == 1 else "<f4"), device="cuda"))
+                return 0
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        return _lib.ALLREDUCE_FN(cb)
+
+    def update(self, hp: PpoHparams, algo: str = "ppo", process_group=None, distributed: bool = False,
+               allreduce=None) -> UpdateStats:
+        """``distributed``: all-reduce through torch.distributed on ``process_group`` (NCCL).  ``allreduce``: a callable
+        ``fn(tensor)`` that sums the given CUDA tensor over the data-parallel group in place, for transports other than
+        torch.distributed (and for tests)."""
         stats = UpdateStats()
         cb = None
-        if distributed:
+        if allreduce is not None:
+            self._allreduce_cb = self._make_allreduce_from(allreduce)
+            cb = C.cast(self._allreduce_cb, C.c_void_p)
+        elif distributed:
             self._allreduce_cb = self._make_allreduce(process_group)
             cb = C.cast(self._allreduce_cb, C.c_void_p)
         fn = {"ppo": self.lib.b200rl_ppo_update, "vpg": self.lib.b200rl_vpg_update}[algo]
@@ -203,6 +224,15 @@ class OnPolicyEngine:
         check(self.lib.b200rl_onpolicy_fvp(self.h, _ptr(v), _ptr(out), v.size, float(damping), current_stream_handle()),
               "fvp")
         return out
+
+    def scalar_history(self) -> np.ndarray:
+        """[slots, 8] float64 scalar sums of the last update (see b200rl_onpolicy_scalar_history)."""
+        n = C.c_int32()
+        probe = np.zeros((1, _lib.N_SCALARS))
+        check(self.lib.b200rl_onpolicy_scalar_history(self.h, _ptr(probe), 0, C.byref(n)), "scalar_history")
+        out = np.zeros((max(int(n.value), 1), _lib.N_SCALARS))
+        check(self.lib.b200rl_onpolicy_scalar_history(self.h, _ptr(out), int(n.value), C.byref(n)), "scalar_history")
+        return out[:int(n.value)]
 
     def run_stage(self, stage: str, hp: PpoHparams):
         check(self.lib.b200rl_onpolicy_run_stage(self.h, stage.encode(), C.byref(hp), current_stream_handle()),
