@@ -4,6 +4,7 @@ from __future__ import annotations
 import logging
 
 from ..optimizers import ConjugateGradientOptimizer
+from ..optimizers.conjugate_gradient_optimizer import NativeClosure
 from ._onpolicy import adam_hparams
 from .ppo import PPO
 
@@ -37,7 +38,13 @@ class TRPO(PPO):
             raise NotImplementedError("ConjugateGradientOptimizer must hold exactly the policy network's parameters")
         self._push_state(engine, with_old=True)
         engine.load_batch(batch)
-        stats, ts = engine.trpo_update(self._hparams(engine, 0), **opt.hyper_parameters())
+        result = {}
+
+        def native_step(optimizer):  # runs inside optimizer.step (ref trpo.py:180-185 calls it the same way)
+            result["out"] = engine.trpo_update(self._hparams(engine, 0), **optimizer.hyper_parameters())
+
+        opt.step(NativeClosure("surrogate loss", native_step), NativeClosure("KL divergence", native_step))
+        stats, ts = result["out"]
         self._pull_state(engine, with_old=True, policy_adam=False)
         self.last_update_stats, self.last_trpo_stats = stats, ts
         if ts.rejected:
