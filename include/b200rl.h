@@ -193,7 +193,7 @@ typedef struct {
   int32_t policy_steps_applied; /* Adam steps actually taken by the policy loop */
   int32_t value_steps_applied;
   int32_t kernel_launches;      /* kernels launched by this update */
-  int32_t reserved;
+  int32_t fused;                /* 1 = the iterations ran on the fused policy + value step kernel (mlp_tc3.cu) */
   double adv_mean, adv_std;     /* normalize_tensor statistics actually used */
   double value_loss_first, value_loss_last;
 } b200rl_update_stats;
@@ -279,12 +279,14 @@ int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, const b200r
  *   b200rl_discounted_cumsum: out[t] = x[t] + discount * out[t+1]            ref: utils.py:14-28 (scipy lfilter, f64)
  *   b200rl_gae_f64: delta[t] = rewards[t] + gamma*values[t+1] - values[t], t < n (rewards / values hold n+1 entries),
  *                   out = discounted_cumsum(delta, gamma*gae_lambda)          ref: utils.py:31-44
+ *                   values: float64, or float32 (values_f32 = 1: gamma*values is then a float32 product, as numpy
+ *                   evaluates it for the float32 arrays compute_values returns)
  *   b200rl_normalize: out = (x - mean(x)) / std(x), unbiased std, no epsilon  ref: utils.py:90-92
  *   b200rl_polyak: target = f32(rho)*target + f32(1-rho)*param                ref: utils.py:47-57
  * ------------------------------------------------------------------------------------------------------------ */
 int b200rl_discounted_cumsum(const double* x, int64_t n, double discount, double* out, void* stream);
-int b200rl_gae_f64(const double* rewards, const double* values, int64_t n, double gamma, double gae_lambda, double* out,
-                   void* stream);
+int b200rl_gae_f64(const double* rewards, const void* values, int values_f32, int64_t n, double gamma,
+                   double gae_lambda, double* out, void* stream);
 int b200rl_normalize(const float* x, int64_t n, float* out, void* stream);
 int b200rl_polyak(float* target, const float* param, int64_t n, double rho, void* stream);
 

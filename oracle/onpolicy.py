@@ -63,15 +63,21 @@ def mlp_forward(layers: Layers, x: np.ndarray, hidden_act: str = "tanh", out_act
 
 
 def mlp_backward(layers: Layers, acts: Sequence[np.ndarray], dout: np.ndarray, hidden_act: str = "tanh",
-                 out_act: str = "identity", need_dx: bool = False):
+                 out_act: str = "identity", need_dx: bool = False, acc=F32):
     """Reverse-mode gradient of sum(out * dout) w.r.t. every (W, b); restates what
-    torch autograd does for the Sequential of Linear/activation (ref: ppo.py:233-235)."""
+    torch autograd does for the Sequential of Linear/activation (ref: ppo.py:233-235).
+    ``acc=np.float64`` sums the per-row contributions of the weight / bias gradients in float64 (the per-row values
+    stay the float32 ones): at a million rows a float32 sum -- torch's as much as numpy's -- carries ~1e-5 of
+    summation noise of its own, and the full-size parity test needs a reference that does not."""
     n = len(layers)
     grads: Layers = [None] * n  # type: ignore
     d = dout.astype(F32, copy=False)
     for l in reversed(range(n)):
         dz = d * _act_prime_from_output(acts[l + 1], out_act if l == n - 1 else hidden_act)
-        grads[l] = ((dz.T @ acts[l]).astype(F32), dz.sum(axis=0, dtype=F32))
+        if acc is F32:
+            grads[l] = ((dz.T @ acts[l]).astype(F32), dz.sum(axis=0, dtype=F32))
+        else:
+            grads[l] = ((dz.T.astype(acc) @ acts[l].astype(acc)).astype(F32), dz.sum(axis=0, dtype=acc).astype(F32))
         if l > 0 or need_dx:
             d = (dz @ layers[l][0]).astype(F32)
     return (grads, d) if need_dx else grads
@@ -256,7 +262,7 @@ class AdamState:
 # losses & one gradient evaluation
 # --------------------------------------------------------------------------
 def policy_loss_and_grad(layers: Layers, dist_kind: str, log_std, obs, act, adv, old_logp, loss_kind: str,
-                         clip: float = 0.2, hidden_act: str = "tanh", n_global: int | None = None):
+                         clip: float = 0.2, hidden_act: str = "tanh", n_global: int | None = None, acc=F32):
     """Returns dict(loss, grads(flat), logp, kl=mean(old_logp-logp), entropy).
 
     loss_kind:
@@ -286,7 +292,7 @@ def policy_loss_and_grad(layers: Layers, dist_kind: str, log_std, obs, act, adv,
         else:
             raise ValueError(loss_kind)
     dout = (coef[:, None] * d.dlogp_dout(act)).astype(F32)
-    grads = mlp_backward(layers, acts, dout, hidden_act, "identity")
+    grads = mlp_backward(layers, acts, dout, hidden_act, "identity", acc=acc)
     res = {
         "loss": float(loss),
         "grad": flatten_layers(grads),
@@ -298,7 +304,7 @@ def policy_loss_and_grad(layers: Layers, dist_kind: str, log_std, obs, act, adv,
     return res
 
 
-def value_loss_and_grad(layers: Layers, obs, ret, hidden_act: str = "tanh", n_global: int | None = None):
+def value_loss_and_grad(layers: Layers, obs, ret, hidden_act: str = "tanh", n_global: int | None = None, acc=F32):
     """F.mse_loss(squeeze(V(obs)), ret) and its gradient (ref: ppo.py:282-287)."""
     n = obs.shape[0] if n_global is None else n_global
     out, acts = mlp_forward(layers, obs, hidden_act, "identity")
@@ -306,7 +312,7 @@ def value_loss_and_grad(layers: Layers, obs, ret, hidden_act: str = "tanh", n_gl
     diff = (v - ret).astype(F32)
     loss = float(np.sum(diff.astype(np.float64) ** 2) / n)
     dout = (F32(2) * diff / F32(n))[:, None].astype(F32)
-    grads = mlp_backward(layers, acts, dout, hidden_act, "identity")
+    grads = mlp_backward(layers, acts, dout, hidden_act, "identity", acc=acc)
     return {"loss": loss, "grad": flatten_layers(grads), "values": v}
 
 
@@ -316,7 +322,7 @@ def value_loss_and_grad(layers: Layers, obs, ret, hidden_act: str = "tanh", n_gl
 def ppo_train(batch: Dict[str, np.ndarray], policy: Layers, value: Layers, dist_kind: str, log_std,
               policy_adam: AdamState, value_adam: AdamState, gamma=0.99, lam=0.97, clip=0.2, max_kl=0.01,
               n_policy=80, n_value=80, old_policy: Layers | None = None, hidden_act: str = "tanh",
-              trace: bool = False) -> Dict[str, object]:
+              trace: bool = False, acc=F32) -> Dict[str, object]:
     obs, act = batch["obs"], batch["act"]
     sizes_p, sizes_v = layer_sizes(policy), layer_sizes(value)
     old_policy = policy if old_policy is None else old_policy
@@ -338,7 +344,7 @@ def ppo_train(batch: Dict[str, np.ndarray], policy: Layers, value: Layers, dist_
     steps_done = 0
     for i in range(n_policy):  # ppo.py:173-181
         r = policy_loss_and_grad(unflatten_layers(flat_p, sizes_p), dist_kind, log_std, obs, act, adv, old_logp,
-                                 "ppo", clip, hidden_act)
+                                 "ppo", clip, hidden_act, acc=acc)
         if i == 0:  # ppo.py:164-170 (logging before the first update)
             out["loss_before"] = r["loss"]
             out["entropy_before"] = float(np.mean(r["entropy"], dtype=np.float64))
@@ -361,7 +367,7 @@ def ppo_train(batch: Dict[str, np.ndarray], policy: Layers, value: Layers, dist_
     flat_v = flatten_layers(value)
     vlosses = []
     for j in range(n_value):  # ppo.py:186-192
-        r = value_loss_and_grad(unflatten_layers(flat_v, sizes_v), obs, ret, hidden_act)
+        r = value_loss_and_grad(unflatten_layers(flat_v, sizes_v), obs, ret, hidden_act, acc=acc)
         if j == 0:
             out["vgrad0"] = r["grad"]
         vlosses.append(r["loss"])

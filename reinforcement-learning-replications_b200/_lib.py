@@ -61,7 +61,7 @@ class PpoHparams(C.Structure):
 class UpdateStats(C.Structure):
     _fields_ = [("policy_loss_before", C.c_double), ("entropy_before", C.c_double), ("logp_std_before", C.c_double),
                 ("kl_divergence", C.c_double), ("value_loss_mean", C.c_double), ("policy_steps_applied", C.c_int32),
-                ("value_steps_applied", C.c_int32), ("kernel_launches", C.c_int32), ("reserved", C.c_int32),
+                ("value_steps_applied", C.c_int32), ("kernel_launches", C.c_int32), ("fused", C.c_int32),
                 ("adv_mean", C.c_double), ("adv_std", C.c_double), ("value_loss_first", C.c_double),
                 ("value_loss_last", C.c_double)]
 
@@ -145,7 +145,8 @@ SIGNATURES = {
                                       [C.POINTER(C.c_int32), C.c_void_p]),
     "b200rl_tc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200rl_discounted_cumsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
-    "b200rl_gae_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "b200rl_gae_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_void_p,
+                                 C.c_void_p]),
     "b200rl_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b200rl_polyak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     "b200rl_onpolicy_scalar_history": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),

@@ -3,12 +3,16 @@
 // as a host-sync-free stream of kernel launches.  See include/b200rl.h for the C ABI.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "common.cuh"
+#include "tc3.cuh"
 
 namespace b200rl {
+
+bool tc2_path_enabled(const b200rl_mlp_desc& d);
 
 static thread_local std::string g_error;
 static std::atomic<int64_t> g_launches{0};  // engines of different host threads count into it
@@ -81,6 +85,15 @@ struct b200rl_onpolicy {
   int* cg_flags = nullptr;   // 4 ints
   double* h_cg_sc = nullptr; // pinned
   int* h_cg_flags = nullptr; // pinned
+  // fused policy + value step (mlp_tc3.cu)
+  bool fused_ok = false;     // both networks fit the fused kernel's shape gate
+  uint8_t* ximg = nullptr;   // packed observation tiles
+  float* xscale = nullptr;   // [64]
+  float* trip = nullptr;     // [2] floats: 0 observations out of range (pack_obs), 1 range trip inside a step
+  float* grad_all = nullptr; // [Pp + Pv + 16]: both gradients + both scalar tails, the ONE all-reduce buffer per iteration
+  float* snap = nullptr;     // snapshot [3 Pp + 3 Pv + Pp]: restored when a fused update must be redone
+  float* h_trip = nullptr;   // pinned
+  int last_fused = 0;        // the last update ran on the fused path (diagnostics)
   std::vector<void*> allocs;
 };
 
@@ -200,8 +213,18 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
   rc |= dev_alloc(h, &h->pol_v, (size_t)Pp);
   rc |= dev_alloc(h, &h->val_m, (size_t)Pv);
   rc |= dev_alloc(h, &h->val_v, (size_t)Pv);
-  rc |= dev_alloc(h, &h->partials, (size_t)2 * sms * Pmax);  // mlp_tc2 emits two partial rows per CTA
-  rc |= dev_alloc(h, &h->scalar_partials, (size_t)2 * sms * B200RL_N_SCALARS);
+  h->fused_ok = tc3_shape_ok(cfg->policy, cfg->value);
+  // mlp_tc2 emits two partial rows per CTA; the fused step's rows hold both networks' gradients side by side
+  rc |= dev_alloc(h, &h->partials, (size_t)2 * sms * (h->fused_ok ? (size_t)(Pp + Pv) : Pmax));
+  rc |= dev_alloc(h, &h->scalar_partials, (size_t)2 * sms * 2 * B200RL_N_SCALARS);
+  if (h->fused_ok) {
+    rc |= dev_alloc(h, &h->ximg, tc3_ximg_bytes(cfg->max_rows));
+    rc |= dev_alloc(h, &h->xscale, 64);
+    rc |= dev_alloc(h, &h->trip, 4);
+    rc |= dev_alloc(h, &h->grad_all, (size_t)(Pp + Pv) + 2 * B200RL_N_SCALARS);
+    rc |= dev_alloc(h, &h->snap, (size_t)(4 * Pp + 3 * Pv));
+    if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_trip), 4 * sizeof(float)) != cudaSuccess) rc = 1;
+  }
   rc |= dev_alloc(h, &h->absmax, 72);
   rc |= dev_alloc(h, &h->pol_grad, (size_t)Pp + B200RL_N_SCALARS);
   rc |= dev_alloc(h, &h->val_grad, (size_t)Pv + B200RL_N_SCALARS);
@@ -227,6 +250,7 @@ extern "C" void b200rl_onpolicy_destroy(b200rl_onpolicy* h) {
   if (h->h_slots) cudaFreeHost(h->h_slots);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   if (h->h_stats3) cudaFreeHost(h->h_stats3);
+  if (h->h_trip) cudaFreeHost(h->h_trip);
   delete h;
 }
 
@@ -355,9 +379,9 @@ static int run_preamble(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl
 }
 
 static int run_value_loop(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
-                          int64_t n_glob, int slot0, cudaStream_t s) {
+                          int64_t n_glob, int slot0, cudaStream_t s, int j0 = 0) {
   const int grid = b200rl_mlp_grid(&h->cfg.value, h->n_rows, 1);
-  for (int j = 0; j < hp->num_value_gradients; ++j) {  // ppo.py:186-192
+  for (int j = j0; j < hp->num_value_gradients; ++j) {  // ppo.py:186-192
     double* slot = h->slots + (size_t)(slot0 + j) * B200RL_N_SCALARS;
     if (launch_fused(h, h->cfg.value, B200RL_LOSS_MSE, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, n_glob, 0.0,
                      false, false, nullptr, true, nullptr, s)) return 1;
@@ -375,12 +399,122 @@ static int run_value_loop(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200
   return 0;
 }
 
-static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
-                      b200rl_update_stats* stats, void* stream, int policy_loss) {
-  B200RL_REQUIRE(h && hp && stats, "update: NULL argument");
-  B200RL_REQUIRE(h->n_rows > 0, "update: no batch loaded");
-  B200RL_REQUIRE(hp->num_policy_gradients >= 0 && hp->num_value_gradients >= 0, "update: negative step count");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+// ---- fused policy + value iterations (mlp_tc3.cu): step i of both loops in one pass over the batch ----------------
+static void fill_tc3_net(const b200rl_mlp_desc& d, Tc3Net* n, int* P) {
+  n->n_out = d.sizes[3];
+  n->h1 = d.sizes[1];
+  n->h2 = d.sizes[2];
+  int off = 0;
+  for (int l = 0; l < 3; ++l) {
+    n->w_off[l] = off;
+    off += d.sizes[l + 1] * d.sizes[l];
+    n->b_off[l] = off;
+    off += d.sizes[l + 1];
+  }
+  *P = off;
+}
+
+static void fill_seg(Ra3Seg* g, float* params, float* m, float* v, int64_t step, double lr, double b1, double b2,
+                     double eps) {
+  g->params = params;
+  g->m = m;
+  g->v = v;
+  g->one_minus_b1 = (float)(1.0 - b1);
+  g->b2 = (float)b2;
+  g->one_minus_b2 = (float)(1.0 - b2);
+  adam_scalars(step, lr, b1, b2, &g->step_size, &g->bc2_sqrt);
+  g->eps = (float)eps;
+}
+
+// Iterations [0, n_iter) of the policy AND the value loop.  Every `poll` iterations the host looks at the early-stop
+// flag (one 4-byte read-back): once the policy loop has stopped, the remaining value steps are faster on the
+// two-tiles-in-flight value kernel than as the lone chain of the fused one.  Returns the iterations done in *done.
+static int run_fused_iterations(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
+                                int64_t n_glob, int K, int n_iter, cudaStream_t s, int* done) {
+  Tc3Args k;
+  memset(&k, 0, sizeof(k));
+  k.n_in = h->obs_dim;
+  k.dist = h->cfg.dist;
+  fill_tc3_net(h->cfg.policy, &k.net[0], &k.P[0]);
+  fill_tc3_net(h->cfg.value, &k.net[1], &k.P[1]);
+  k.params[0] = h->pol;
+  k.params[1] = h->val;
+  k.n_rows = h->n_rows;
+  k.inv_n = 1.0f / (float)n_glob;
+  k.n_glob_f = (float)n_glob;
+  k.clip_lo = (float)(1.0 - hp->clip_range);
+  k.clip_hi = (float)(1.0 + hp->clip_range);
+  k.ximg = h->ximg;
+  k.xscale = h->xscale;
+  k.actions = h->act;
+  k.log_std = h->log_std;
+  k.adv_raw = h->adv_raw;
+  k.adv_stats = h->adv_stats;
+  k.old_logp = h->old_logp;
+  k.target = h->ret;
+  k.target_absmax = h->absmax + 64;
+  k.partials = h->partials;
+  k.scalar_partials = h->scalar_partials;
+  k.stop_flag = h->flags;
+  k.x_bad = h->trip;
+  k.status = h->trip + 1;
+  k.run_policy = 1;
+  k.run_value = 1;
+  Ra3Args a;
+  memset(&a, 0, sizeof(a));
+  a.partials = h->partials;
+  a.scalar_partials = h->scalar_partials;
+  a.rows = 2 * tc3_grid(h->n_rows);
+  a.P[0] = h->Pp;
+  a.P[1] = h->Pv;
+  a.grad = h->grad_all;
+  a.n_global = (double)n_glob;
+  a.kl_limit = 1.5 * hp->max_kl_divergence;
+  a.kl_limit_on = 1;
+  a.stop_flag = h->flags;
+  a.applied_p = h->flags + 1;
+  a.applied_v = h->flags + 2;
+  a.run_policy = 1;
+  a.run_value = 1;
+  const int64_t n_all = h->Pp + h->Pv + 2 * B200RL_N_SCALARS;
+  constexpr int poll = 8;
+  int i = 0;
+  for (; i < n_iter; ++i) {
+    if (launch_mlp_tc3(k, s)) return 1;
+    fill_seg(&a.seg[0], h->pol, h->pol_m, h->pol_v, h->pol_step + i + 1, hp->policy_lr, hp->policy_beta1,
+             hp->policy_beta2, hp->policy_eps);
+    fill_seg(&a.seg[1], h->val, h->val_m, h->val_v, h->val_step + i + 1, hp->value_lr, hp->value_beta1, hp->value_beta2,
+             hp->value_eps);
+    a.slot_p = h->slots + (size_t)i * B200RL_N_SCALARS;
+    a.slot_v = h->slots + (size_t)(K + 1 + i) * B200RL_N_SCALARS;
+    if (!ar) {
+      a.mode = 0;
+      if (launch_reduce_adam3(a, s)) return 1;
+    } else {
+      a.mode = 1;
+      if (launch_reduce_adam3(a, s)) return 1;
+      if (ar(user, h->grad_all, n_all, 0, s)) {  // ONE all-reduce: both gradients + both scalar tails
+        set_error("allreduce callback failed (fused policy + value gradient)");
+        return 1;
+      }
+      a.mode = 2;
+      if (launch_reduce_adam3(a, s)) return 1;
+    }
+    if ((i % poll) == poll - 1 && i + 1 < n_iter) {
+      B200RL_CUDA(cudaMemcpyAsync(h->h_flags, h->flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200RL_CUDA(cudaStreamSynchronize(s));
+      if (h->h_flags[0] != 0) {
+        ++i;
+        break;
+      }
+    }
+  }
+  *done = i;
+  return 0;
+}
+
+static int run_update_impl(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
+                           b200rl_update_stats* stats, cudaStream_t s, int policy_loss, bool fused, bool* tripped) {
   const int64_t launches0 = launches_total();
   const int64_t n_glob = hp->n_global_rows > 0 ? hp->n_global_rows : h->n_rows;
   const bool ppo = policy_loss == B200RL_LOSS_PPO_CLIP;
@@ -389,6 +523,17 @@ static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_a
   if (ensure_slots(h, K + Kv + 4)) return 1;
   B200RL_CUDA(cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), s));
   B200RL_CUDA(cudaMemsetAsync(h->slots, 0, (size_t)(K + Kv + 4) * B200RL_N_SCALARS * sizeof(double), s));
+  const size_t Pp = (size_t)h->Pp, Pv = (size_t)h->Pv;
+  if (fused) {  // what a redo on the wide-range path starts from
+    B200RL_CUDA(cudaMemsetAsync(h->trip, 0, 4 * sizeof(float), s));
+    float* q = h->snap;
+    const float* src[7] = {h->pol, h->pol_m, h->pol_v, h->old_pol, h->val, h->val_m, h->val_v};
+    for (int t = 0; t < 7; ++t) {
+      const size_t n = t < 4 ? Pp : Pv;
+      B200RL_CUDA(cudaMemcpyAsync(q, src[t], n * 4, cudaMemcpyDeviceToDevice, s));
+      q += n;
+    }
+  }
 
   if (run_preamble(h, hp, ar, user, s)) return 1;
 
@@ -401,7 +546,12 @@ static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_a
     if (launch_fused(h, h->cfg.policy, B200RL_LOSS_EVAL, dist, h->old_pol, h->obs, h->n_rows, n_glob, 0.0, false,
                      false, h->old_logp, false, nullptr, s)) return 1;
   }
-  for (int i = 0; i < K; ++i) {  // ppo.py:173-181 / vpg.py:194-207
+  int i0 = 0;  // iterations of both loops already done by the fused kernel
+  if (fused) {
+    if (launch_pack_obs(h->obs, h->n_rows, h->obs_dim, h->absmax, h->ximg, h->xscale, h->trip, s)) return 1;
+    if (run_fused_iterations(h, hp, ar, user, n_glob, K, K < Kv ? K : Kv, s, &i0)) return 1;
+  }
+  for (int i = i0; i < K; ++i) {  // ppo.py:173-181 / vpg.py:194-207
     double* slot = h->slots + (size_t)i * B200RL_N_SCALARS;
     if (launch_fused(h, h->cfg.policy, policy_loss, dist, h->pol, h->obs, h->n_rows, n_glob, hp->clip_range, true,
                      ppo, nullptr, true, stop, s)) return 1;
@@ -434,15 +584,35 @@ static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_a
     B200RL_CUDA(cudaMemcpyAsync(h->old_pol, h->pol, (size_t)h->Pp * 4, cudaMemcpyDeviceToDevice, s));
   }
 
-  if (run_value_loop(h, hp, ar, user, n_glob, K + 1, s)) return 1;
+  if (run_value_loop(h, hp, ar, user, n_glob, K + 1, s, i0)) return 1;
 
   // ---- one device->host read of the statistics ----
+  if (fused) {
+    // a range trip on ANY rank sends every rank through the redo (the collective keeps them in step)
+    if (ar && ar(user, h->trip, 2, 0, s)) {
+      set_error("allreduce callback failed (range flags)");
+      return 1;
+    }
+    B200RL_CUDA(cudaMemcpyAsync(h->h_trip, h->trip, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
   B200RL_CUDA(cudaMemcpyAsync(h->h_slots, h->slots, (size_t)(K + Kv + 2) * B200RL_N_SCALARS * sizeof(double),
                               cudaMemcpyDeviceToHost, s));
   h->last_slots = K + Kv + 2;
   B200RL_CUDA(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaMemcpyAsync(h->h_stats3, h->adv_stats, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaStreamSynchronize(s));
+  if (fused && (h->h_trip[0] != 0.f || h->h_trip[1] != 0.f)) {
+    // fp16 operands left their range somewhere in this update: put everything back; the caller redoes it
+    const float* q = h->snap;
+    float* dst[7] = {h->pol, h->pol_m, h->pol_v, h->old_pol, h->val, h->val_m, h->val_v};
+    for (int t = 0; t < 7; ++t) {
+      const size_t n = t < 4 ? Pp : Pv;
+      B200RL_CUDA(cudaMemcpyAsync(dst[t], q, n * 4, cudaMemcpyDeviceToDevice, s));
+      q += n;
+    }
+    *tripped = true;
+    return 0;
+  }
 
   memset(stats, 0, sizeof(*stats));
   const double ng = (double)n_glob;
@@ -470,6 +640,28 @@ static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_a
   h->pol_step += applied_p;
   h->val_step += applied_v;
   stats->kernel_launches = (int32_t)(launches_total() - launches0);
+  stats->fused = fused ? 1 : 0;  // 1 = the fused policy + value step kernel did the iterations
+  h->last_fused = fused ? 1 : 0;
+  return 0;
+}
+
+static bool fused_step_enabled() {  // B200RL_FUSED_STEP=0 keeps the two-loop path (A/B parity runs)
+  const char* e = getenv("B200RL_FUSED_STEP");
+  return !(e != nullptr && e[0] == '0');
+}
+
+static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_allreduce_fn ar, void* user,
+                      b200rl_update_stats* stats, void* stream, int policy_loss) {
+  B200RL_REQUIRE(h && hp && stats, "update: NULL argument");
+  B200RL_REQUIRE(h->n_rows > 0, "update: no batch loaded");
+  B200RL_REQUIRE(hp->num_policy_gradients >= 0 && hp->num_value_gradients >= 0, "update: negative step count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool fused = policy_loss == B200RL_LOSS_PPO_CLIP && h->fused_ok && fused_step_enabled() &&
+                     tc2_path_enabled(h->cfg.policy) && tc2_path_enabled(h->cfg.value) &&
+                     hp->num_policy_gradients > 0 && hp->num_value_gradients > 0;
+  bool tripped = false;
+  if (run_update_impl(h, hp, ar, user, stats, s, policy_loss, fused, &tripped)) return 1;
+  if (tripped) return run_update_impl(h, hp, ar, user, stats, s, policy_loss, false, &tripped);
   return 0;
 }
 

@@ -626,6 +626,9 @@ static bool use_tc(const b200rl_mlp_desc& d) {
   return tc_shape_ok(d);
 }
 
+// the fp16 x 2 tensor-core path is in use for this network (shape gate + the A/B environment switches)
+bool tc2_path_enabled(const b200rl_mlp_desc& d) { return use_tc(d) && use_tc2(); }
+
 }  // namespace b200rl
 
 using namespace b200rl;

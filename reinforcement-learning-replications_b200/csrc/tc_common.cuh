@@ -24,7 +24,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
 #pragma unroll 1  // inlined at ~20 sites of the tensor-core kernels: keep the spin loop small (instruction cache)
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0; it < (1u << 22); ++it) {  // ~16 s at the 4 us suspend hint
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"

@@ -18,10 +18,12 @@ struct Affine {  // y_first = s + d * y_after
 };
 __device__ __forceinline__ Affine combine(const Affine l, const Affine r) { return Affine{l.s + l.d * r.s, l.d * r.d}; }
 
-// MODE 0: x = in0[i].  MODE 1 (gae): x = r[i] + gamma * v[i+1] - v[i]  (utils.py:41), in0 = rewards, in1 = values
+// MODE 0: x = in0[i].  MODE 1 / 2 (gae): x = r[i] + gamma * v[i+1] - v[i]  (utils.py:41), in0 = rewards, in1 = values.
+// MODE 2: float32 values -- numpy evaluates `gamma * values[1:]` in the array's dtype (a Python-float gamma does not
+// promote a float32 array), then adds it to the float64 rewards: reproduced operation by operation.
 template <int MODE>
 __global__ void __launch_bounds__(SC_THREADS) discounted_cumsum_kernel(const double* __restrict__ in0,
-                                                                       const double* __restrict__ in1, long long n,
+                                                                       const void* __restrict__ in1v, long long n,
                                                                        double gamma, double discount,
                                                                        double* __restrict__ out) {
   __shared__ Affine s_warp[32];
@@ -40,7 +42,15 @@ __global__ void __launch_bounds__(SC_THREADS) discounted_cumsum_kernel(const dou
     for (int j = 0; j < SC_ITEMS; ++j) {
       const long long i = i0 + j;
       if (i >= 0 && i < n) {
-        x[j] = MODE == 0 ? in0[i] : (in0[i] + gamma * in1[i + 1]) - in1[i];
+        if (MODE == 0) {
+          x[j] = in0[i];
+        } else if (MODE == 1) {
+          const double* in1 = static_cast<const double*>(in1v);
+          x[j] = (in0[i] + gamma * in1[i + 1]) - in1[i];
+        } else {
+          const float* in1 = static_cast<const float*>(in1v);
+          x[j] = (in0[i] + (double)__fmul_rn((float)gamma, in1[i + 1])) - (double)in1[i];
+        }
       } else {
         x[j] = 0.0;  // in front of the vector: contributes nothing to anyone (everything there is discarded)
       }
@@ -132,12 +142,15 @@ extern "C" int b200rl_discounted_cumsum(const double* x, int64_t n, double disco
   return 0;
 }
 
-extern "C" int b200rl_gae_f64(const double* rewards, const double* values, int64_t n, double gamma, double gae_lambda,
-                              double* out, void* stream) {
+extern "C" int b200rl_gae_f64(const double* rewards, const void* values, int values_f32, int64_t n, double gamma,
+                              double gae_lambda, double* out, void* stream) {
   B200RL_REQUIRE(n >= 0 && (n == 0 || (rewards && values && out)), "gae_f64: bad argument");
   if (n == 0) return 0;
-  discounted_cumsum_kernel<1><<<1, SC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(rewards, values, n, gamma,
-                                                                                       gamma * gae_lambda, out);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (values_f32)
+    discounted_cumsum_kernel<2><<<1, SC_THREADS, 0, s>>>(rewards, values, n, gamma, gamma * gae_lambda, out);
+  else
+    discounted_cumsum_kernel<1><<<1, SC_THREADS, 0, s>>>(rewards, values, n, gamma, gamma * gae_lambda, out);
   B200RL_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;

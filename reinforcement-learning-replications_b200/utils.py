@@ -50,13 +50,16 @@ def gae(rewards: np.ndarray, gamma: float, values: np.ndarray, gae_lambda: float
     entries (bootstrapped reward / V(last observation) at the end); returns L float64 advantages."""
     lib = _lib.load()
     r = np.ascontiguousarray(rewards, dtype=np.float64)
-    v = np.ascontiguousarray(values, dtype=np.float64)  # exact widening of the float32 values
+    v = np.asarray(values)
+    f32 = v.dtype == np.float32  # what compute_values returns; numpy keeps gamma * values in float32 then
+    v = np.ascontiguousarray(v, dtype=np.float32 if f32 else np.float64)
     if r.ndim != 1 or r.shape != v.shape or r.size < 1:
         raise ValueError("gae: rewards and values must be 1-D and of equal length (L + 1)")
     n = r.size - 1
     d_r, d_v = torch.from_numpy(r).cuda(), torch.from_numpy(v).cuda()
     d_out = torch.empty(max(n, 1), dtype=torch.float64, device="cuda")
-    _lib.check(lib.b200rl_gae_f64(_p(d_r), _p(d_v), n, float(gamma), float(gae_lambda), _p(d_out), _stream()), "gae_f64")
+    _lib.check(lib.b200rl_gae_f64(_p(d_r), _p(d_v), int(f32), n, float(gamma), float(gae_lambda), _p(d_out), _stream()),
+               "gae_f64")
     return d_out[:n].cpu().numpy()
 
 
