@@ -267,7 +267,8 @@ int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr
 int b200rl_onpolicy_scalar_history(b200rl_onpolicy* h, double* out, int32_t max_slots, int32_t* n_slots);
 
 /* Profiling hook (not on the product path): runs ONE named stage of the update on the loaded batch -- "values",
- * "preamble", "scan", "old_logp", "policy_grad", "policy_grad_kernel", "value_grad", "value_grad_kernel", "fvp" --
+ * "preamble", "scan", "old_logp", "policy_grad", "policy_grad_kernel", "value_grad", "value_grad_kernel", "fvp",
+ * "pack_obs", "fused_step_kernel", "fused_step" --
  * so that bench.py can time single kernels with CUDA events and ncu can capture them.  Asynchronous.
  * Note: the fp16 tensor-core kernels keep one status ring per PROCESS on the device that was current at their first
  * launch: one process drives one GPU (the torchrun / one-rank-per-GPU model of SURVEY 8e). */

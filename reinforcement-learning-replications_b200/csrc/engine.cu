@@ -873,8 +873,9 @@ extern "C" int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name,
       {"values", h->values, h->n_rows, 0},        {"last_values", h->last_values, h->n_ep, 0},
       {"adv_raw", h->adv_raw, h->n_rows, 0},      {"ret", h->ret, h->n_rows, 0},
       {"old_logp", h->old_logp, h->n_rows, 0},    {"adv_stats", h->adv_stats, 3, 1},
-      {"policy_grad", h->pol_grad, h->Pp + B200RL_N_SCALARS, 0},
-      {"value_grad", h->val_grad, h->Pv + B200RL_N_SCALARS, 0},
+      // after a fused update both gradients sit side by side in the all-reduce buffer
+      {"policy_grad", h->last_fused ? h->grad_all : h->pol_grad, h->last_fused ? h->Pp : h->Pp + B200RL_N_SCALARS, 0},
+      {"value_grad", h->last_fused ? h->grad_all + h->Pp : h->val_grad, h->last_fused ? h->Pv : h->Pv + B200RL_N_SCALARS, 0},
       {"policy_params", h->pol, h->Pp, 0},        {"old_policy_params", h->old_pol, h->Pp, 0},
       {"value_params", h->val, h->Pv, 0},         {"obs", h->obs, h->n_rows * h->obs_dim, 0},
       {"cg_x", h->cg_x, h->cg_x ? h->Pp : 0, 0},  {"cg_descent", h->cg_descent, h->cg_descent ? h->Pp : 0, 0},
@@ -933,6 +934,58 @@ extern "C" int b200rl_onpolicy_run_stage(b200rl_onpolicy* h, const char* stage, 
   if (strcmp(stage, "value_grad_kernel") == 0)
     return launch_fused(h, h->cfg.value, B200RL_LOSS_MSE, B200RL_DIST_NONE, h->val, h->obs, h->n_rows, n_glob, 0.0,
                         false, false, nullptr, true, nullptr, s);
+  if (strcmp(stage, "pack_obs") == 0 || strcmp(stage, "fused_step_kernel") == 0 || strcmp(stage, "fused_step") == 0) {
+    B200RL_REQUIRE(h->fused_ok, "run_stage: the networks do not fit the fused step kernel");
+    if (strcmp(stage, "pack_obs") == 0) {
+      B200RL_CUDA(cudaMemsetAsync(h->trip, 0, 4 * sizeof(float), s));
+      if (!h->hints_valid && b200rl_absmax_cols(h->obs, h->n_rows, h->obs_dim, h->absmax, s)) return 1;
+      return launch_pack_obs(h->obs, h->n_rows, h->obs_dim, h->absmax, h->ximg, h->xscale, h->trip, s);
+    }
+    // one iteration of both loops on the packed observations ("pack_obs" and "preamble" first): the step kernel
+    // alone, or with the reduction of its partial rows (mode 1: parameters stay as they are)
+    b200rl_ppo_hparams one = *hp;
+    one.num_policy_gradients = one.num_value_gradients = 0;
+    Tc3Args k;
+    memset(&k, 0, sizeof(k));
+    k.n_in = h->obs_dim;
+    k.dist = h->cfg.dist;
+    fill_tc3_net(h->cfg.policy, &k.net[0], &k.P[0]);
+    fill_tc3_net(h->cfg.value, &k.net[1], &k.P[1]);
+    k.params[0] = h->pol;
+    k.params[1] = h->val;
+    k.n_rows = h->n_rows;
+    k.inv_n = 1.0f / (float)n_glob;
+    k.n_glob_f = (float)n_glob;
+    k.clip_lo = (float)(1.0 - hp->clip_range);
+    k.clip_hi = (float)(1.0 + hp->clip_range);
+    k.ximg = h->ximg;
+    k.xscale = h->xscale;
+    k.actions = h->act;
+    k.log_std = h->log_std;
+    k.adv_raw = h->adv_raw;
+    k.adv_stats = h->adv_stats;
+    k.old_logp = h->old_logp;
+    k.target = h->ret;
+    k.target_absmax = h->absmax + 64;
+    k.partials = h->partials;
+    k.scalar_partials = h->scalar_partials;
+    k.x_bad = h->trip;
+    k.status = h->trip + 1;
+    k.run_policy = k.run_value = 1;
+    if (launch_mlp_tc3(k, s)) return 1;
+    if (strcmp(stage, "fused_step_kernel") == 0) return 0;
+    Ra3Args a;
+    memset(&a, 0, sizeof(a));
+    a.mode = 1;
+    a.partials = h->partials;
+    a.scalar_partials = h->scalar_partials;
+    a.rows = 2 * tc3_grid(h->n_rows);
+    a.P[0] = h->Pp;
+    a.P[1] = h->Pv;
+    a.grad = h->grad_all;
+    a.run_policy = a.run_value = 1;
+    return launch_reduce_adam3(a, s);
+  }
   if (strcmp(stage, "fvp") == 0) {  // one Fisher-vector product (kernel + fixed-order reduction) on the current direction
     if (ensure_trpo(h)) return 1;
     return launch_fvp(h, h->cg_p, h->cg_z, n_glob, s);

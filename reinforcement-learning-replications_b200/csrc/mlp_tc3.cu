@@ -60,8 +60,12 @@ constexpr uint32_t S3_END_SC = 1024;                 // [16 warps][8] doubles
 
 // ---- tensor-memory column map (fp32) ----
 constexpr uint32_t M3_CHAIN = 80, M3_Z = 0, M3_OUT = 64;          // per chain: Z1 -> Z2 -> dH2 -> dH1 share Z
-constexpr uint32_t M3_ACC = 160, M3_ACC_NET = 128;               // per net: DW2 | DW1 (col 31 = db1) | DW3 | DB2
-constexpr uint32_t M3_DW2 = 0, M3_DW1 = 64, M3_DW3 = 96, M3_DB2 = 112;
+// per net: DW2 (64) | DB2 (16, col 15 = db2) | DW1 (64: products with X's h columns, then with its l columns; col 31 =
+// db1) | DW3 (32: products with dOut's h columns, then l).  The B operands of dW1 / dW3 hold their two splits side
+// by side in one swizzle atom, so ONE product per k-step covers both; the halves are added when the accumulators
+// are read, once per launch.  2 x 80 + 2 x 176 = 512 columns: all of tensor memory.
+constexpr uint32_t M3_ACC = 160, M3_ACC_NET = 176;
+constexpr uint32_t M3_DW2 = 0, M3_DB2 = 64, M3_DW1 = 80, M3_DW3 = 144;
 
 enum { C3_G = 0, C3_U1, C3_U2, C3_U3, C3_UH2, C3_UH1, C3_W1, C3_W2, C3_W3, C3_OW3, C3_OW2, C3_OW1, C3_OB, C3_N };
 
@@ -310,14 +314,15 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
     constexpr uint32_t I_128_64_KK = make_idesc_f16(128, 64, 0, 0), I_128_16_KK = make_idesc_f16(128, 16, 0, 0),
                        I_128_64_KM = make_idesc_f16(128, 64, 0, 1), I_128_64_MM = make_idesc_f16(128, 64, 1, 1),
                        I_128_32_MM = make_idesc_f16(128, 32, 1, 1), I_128_16_MM = make_idesc_f16(128, 16, 1, 1);
+    (void)I_128_16_MM;
     const uint32_t ub = base, ubar = bars;
     if (tmem != 0u) __trap();  // a 512-column allocation is the whole tensor memory: base 0 (uniform by construction)
     // views at chain 0 / net 0 / X buffer 0; the others are reached by adding byte offsets to the descriptors
     const Op2 X_K = op2_kmajor(ub + S3_XB, 64);                     // A: X, h at +0, l at +64 bytes
-    const Op2 X_M = op2_mnmajor(ub + S3_XB, T2_ACT, 64);            // B, N = 32: features 0..31 (col 31 = ones)
+    const Op2 X_M = op2_mnmajor(ub + S3_XB, T2_ACT, 64);            // B, N = 64: features h 0..31 (col 31 = ones) | l
     const Op2 X_M16 = op2_mnmajor(ub + S3_XB + 32, T2_ACT, 64);     // B, N = 16: h cols 16..31 (col 31 = ones)
     const Op2 DO_K = op2_kmajor(ub + S3_XB, 32);                    // A, K = 16: dOut h at +0, l at +32 bytes
-    const Op2 DO_M = op2_mnmajor(ub + S3_XB, T2_ACT, 32);           // B, N = 16
+    const Op2 DO_M = op2_mnmajor(ub + S3_XB, T2_ACT, 32);           // B, N = 32: dOut h | l
     const Op2 H1_K = op2_kmajor(ub + S3_H, T2_ACT), H2_K = op2_kmajor(ub + S3_H + 2 * T2_ACT, T2_ACT);
     const Op2 H1_M = op2_mnmajor(ub + S3_H, T2_ACT, T2_ACT), H2_M = op2_mnmajor(ub + S3_H + 2 * T2_ACT, T2_ACT, T2_ACT);
     const Op2 W1T_M = op2_mnmajor(ub + S3_W, 32 * 128, T3_W1T);
@@ -370,8 +375,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
           } else if (stage == 3) {
             // dH2 = dOut W3 ; dW3^T[i][o] += sum_r H2[r][i] dOut[r][o] (must retire before H2 becomes dZ2 in place)
             issue_chain3<1>(tz + M3_Z, I_128_64_KM, op2_at(DO_K, dob + c * 64), op2_at(W3_M, wo));
-            issue_stacked<8, 2>(ta + M3_DW3, I_128_16_MM, (accmask >> (3 * c)) & 1u, op2_at(H2_M, co),
-                                op2_at(DO_M, dob + c * 64));
+            issue_stacked<8, 1>(ta + M3_DW3, I_128_32_MM, (accmask >> (3 * c)) & 1u, op2_at(H2_M, co),
+                                op2_at(DO_M, dob + c * 64));  // N = 32: dOut h | l
             accmask |= 1u << (3 * c);
           } else if (stage == 4) {
             // both chains' stage-3 products have retired (their E4 jobs waited for them before arriving here): the
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
             accmask |= 1u << (3 * c + 1);
           } else {
             // dW1[o][i] += sum_r dZ1[r][o] X[r][i]; column 31 (ones) collects db1.  Then the next tile's Z1.
-            issue_stacked<8, 2>(ta + M3_DW1, I_128_32_MM, (accmask >> (3 * c + 2)) & 1u, op2_at(H1_M, co), op2_at(X_M, xo));
+            issue_stacked<8, 1>(ta + M3_DW1, I_128_64_MM, (accmask >> (3 * c + 2)) & 1u, op2_at(H1_M, co), op2_at(X_M, xo));
             accmask |= 1u << (3 * c + 2);
             if (k + 1 < cta_tiles) issue_z1(c, k + 1);
           }
@@ -635,47 +640,54 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
     tc_fence_after_sync();
     {
       // stacked accumulators: lanes 0..63 = h-split half (partial row 2b), lanes 64..127 = l-split half (row 2b + 1);
-      // 8 chunks of 16 columns per net; warp `part` takes chunks part, part + 4 of both nets
+      // 8 jobs per net (dW2 x 4 column blocks, dW1 x 2, dW3, db2); warp `part` takes jobs part, part + 4 of both nets
       float* dst_row = p.partials + ((size_t)blockIdx.x * 2 + (q >> 1)) * (size_t)(p.P[0] + p.P[1]);
       const int m = 32 * (q & 1) + lane;  // feature index
       const uint32_t ta = tmem + lane_addr + M3_ACC;
-      uint32_t v[16];
+      uint32_t v[16], w[16];
 #pragma unroll 1
       for (int c = c_first; c <= c_last; ++c) {
         const Tc3Net& nn = p.net[c];
         float* dst = dst_row + (c == 0 ? 0 : p.P[0]);
         const float* scl = s_scale + 16 * c;
         const bool have = cta_tiles > 0;
+        const uint32_t tn = ta + c * M3_ACC_NET;
 #pragma unroll 1
-        for (int chunk = part; chunk < 8; chunk += 4) {
+        for (int jb = part; jb < 8; jb += 4) {
+          // columns of this job, and of its second half where the operand's l columns went to their own block
+          const uint32_t col = jb < 4 ? M3_DW2 + 16 * jb : (jb < 6 ? M3_DW1 + 16 * (jb - 4) : (jb == 6 ? M3_DW3 : M3_DB2));
+          const uint32_t col2 = jb < 4 ? col : (jb < 6 ? col + 32 : (jb == 6 ? col + 16 : col));
           if (have) {
-            tmem_ld16(ta + c * M3_ACC_NET + 16 * chunk, v);
+            tmem_ld16(tn + col, v);
+            tmem_ld16(tn + col2, w);
             tmem_wait_ld();
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0u;  // a CTA without tiles: tensor memory was never written
+            for (int j = 0; j < 16; ++j) v[j] = w[j] = 0u;  // a CTA without tiles: tensor memory was never written
           }
-          if (chunk < 4) {  // dW2 [h2 o][h1 i]: columns 16 chunk .. +15
+          if (jb < 4) {  // dW2 [h2 o][h1 i]: columns 16 jb .. +15
             const float u = scl[C3_OW2];
             if (m < nn.h2)
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (16 * chunk + j < nn.h1) dst[nn.w_off[1] + m * nn.h1 + 16 * chunk + j] = __uint_as_float(v[j]) * u;
-          } else if (chunk < 6) {  // dW1 [h1 o][n_in i] in columns 0..30, db1 in column 31
-            const int c0 = 16 * (chunk - 4);
+                if (16 * jb + j < nn.h1) dst[nn.w_off[1] + m * nn.h1 + 16 * jb + j] = __uint_as_float(v[j]) * u;
+          } else if (jb < 6) {  // dW1 [h1 o][n_in i] in columns 0..30, db1 in column 31
+            const int c0 = 16 * (jb - 4);
             const float u = scl[C3_OW1];
             if (m < nn.h1) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < n_in) dst[nn.w_off[0] + m * n_in + c0 + j] = (__uint_as_float(v[j]) * u) * s_xs[32 + c0 + j];
-              if (chunk == 5) dst[nn.b_off[0] + m] = __uint_as_float(v[15]) * scl[C3_OB];
+                if (c0 + j < n_in)
+                  dst[nn.w_off[0] + m * n_in + c0 + j] =
+                      ((__uint_as_float(v[j]) + __uint_as_float(w[j])) * u) * s_xs[32 + c0 + j];
+              if (jb == 5) dst[nn.b_off[0] + m] = (__uint_as_float(v[15]) + __uint_as_float(w[15])) * scl[C3_OB];
             }
-          } else if (chunk == 6) {  // dW3^T [h2 i][16 o]
+          } else if (jb == 6) {  // dW3^T [h2 i][16 o]
             const float u = scl[C3_OW3];
             if (m < nn.h2)
 #pragma unroll
               for (int a = 0; a < 15; ++a)
-                if (a < nn.n_out) dst[nn.w_off[2] + a * nn.h2 + m] = __uint_as_float(v[a]) * u;
+                if (a < nn.n_out) dst[nn.w_off[2] + a * nn.h2 + m] = (__uint_as_float(v[a]) + __uint_as_float(w[a])) * u;
           } else {  // db2 (column 15 = sum_r dZ2[r][o] * ones)
             if (m < nn.h2) dst[nn.b_off[1] + m] = __uint_as_float(v[15]) * scl[C3_OB];
           }
