@@ -259,6 +259,20 @@ int b200rl_onpolicy_fvp(b200rl_onpolicy* h, const float* host_v, float* host_out
  *       "policy_params","old_policy_params","value_params" */
 int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name, void** ptr, int64_t* count, int32_t* dtype);
 
+/* One-shot gradient exchange over peer-mapped device memory (data-parallel runs on ONE node: NVLink / NVSwitch).
+ * Once attached, the fused PPO iterations no longer call `allreduce` for the gradient: every rank stores its reduced
+ * [policy gradient | value gradient | scalar sums] into its exchange buffer and reads all ranks' buffers directly
+ * (sum in rank order => bit-identical parameters on every rank); the callback still carries the three small
+ * collectives per update (advantage statistics, final KL, range flags).
+ *   comm_export: allocates the buffer on first use, returns its CUDA IPC handle (64 bytes) and local device pointer;
+ *   ipc_open / ipc_close: map / unmap another rank's handle in this process (cudaIpcOpenMemHandle);
+ *   comm_attach: peer_ptrs[r] = rank r's buffer as seen from THIS process (own buffer at [rank]); world <= 16.
+ * Every rank must run the same sequence of updates (as with any collective). */
+int b200rl_onpolicy_comm_export(b200rl_onpolicy* h, void* handle64, void** local_ptr);
+int b200rl_ipc_open(const void* handle64, void** ptr);
+int b200rl_ipc_close(void* ptr);
+int b200rl_onpolicy_comm_attach(b200rl_onpolicy* h, int32_t rank, int32_t world, void* const* peer_ptrs);
+
 /* Per-launch scalar sums of the LAST update, as read back by it (host copy, no device work): out[slot][k], k as in
  * b200rl_mlp_loss_grad_args.scalar_partials, already summed over CTAs (and ranks).  PPO: slot i = forward pass of
  * policy step i (so slot i+1, k=1, divided by the row count is the approximate KL after step i, ppo.py:176-178; slot

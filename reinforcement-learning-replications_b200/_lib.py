@@ -149,6 +149,10 @@ SIGNATURES = {
                                  C.c_void_p]),
     "b200rl_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b200rl_polyak": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
+    "b200rl_onpolicy_comm_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200rl_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200rl_ipc_close": (C.c_int, [C.c_void_p]),
+    "b200rl_onpolicy_comm_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "b200rl_onpolicy_scalar_history": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "b200rl_onpolicy_run_stage": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(PpoHparams), C.c_void_p]),
 }

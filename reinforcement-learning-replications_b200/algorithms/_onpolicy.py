@@ -169,12 +169,23 @@ class OnPolicyTrainerMixin:
         write_adam_state(self.value_function.optimizer, self._vlin, *e.get_adam(VALUE))
 
     def _global_rows(self, n_rows: int) -> int:
+        """Rows over all ranks (the denominator of every mean).  The same collective tells the ranks whether any of them
+        holds a fresh engine: then ALL of them (re)attach the NVLink gradient exchange (B200RL_PEER_EXCHANGE=0 keeps
+        the NCCL all-reduce per iteration)."""
         if not self.distributed:
             return 0
+        import os
         import torch.distributed as dist
-        t = torch.tensor([n_rows], dtype=torch.int64, device="cuda")
+        e = self._engine
+        want = os.environ.get("B200RL_PEER_EXCHANGE", "1") != "0"
+        fresh = int(want and e is not None and not e.peer_exchange and not getattr(e, "peer_refused", False))
+        t = torch.tensor([n_rows, fresh], dtype=torch.int64, device="cuda")
         dist.all_reduce(t, group=self.process_group)
-        return int(t.item())
+        if want and int(t[1].item()) > 0 and e is not None:
+            if not e.enable_peer_exchange(self.process_group):
+                e.peer_refused = True
+                logger.warning("peer-memory gradient exchange unavailable: keeping the NCCL all-reduce per iteration")
+        return int(t[0].item())
 
     def pack(self, experience):
         return pack_experience(experience)

@@ -94,6 +94,13 @@ struct b200rl_onpolicy {
   float* snap = nullptr;     // snapshot [3 Pp + 3 Pv + Pp]: restored when a fused update must be redone
   float* h_trip = nullptr;   // pinned
   int last_fused = 0;        // the last update ran on the fused path (diagnostics)
+  // one-shot gradient exchange over peer-mapped memory (data-parallel runs on one node)
+  float* xchg = nullptr;     // this rank's exchange buffer: [2][xchg_stride] floats + 2 sequence words
+  int64_t xchg_stride = 0;
+  float** peers_dev = nullptr;  // device copy of the ranks' buffer pointers
+  unsigned* done_counter = nullptr;
+  int comm_world = 0, comm_rank = 0;
+  unsigned comm_seq = 0;
   std::vector<void*> allocs;
 };
 
@@ -490,6 +497,19 @@ static int run_fused_iterations(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp
     if (!ar) {
       a.mode = 0;
       if (launch_reduce_adam3(a, s)) return 1;
+    } else if (h->comm_world > 1) {  // one-shot exchange over NVLink peer memory: two launches, no collective call
+      a.peers = h->peers_dev;
+      a.world = h->comm_world;
+      a.rank = h->comm_rank;
+      a.xchg_stride = h->xchg_stride;
+      a.seq = ++h->comm_seq;
+      a.done_counter = h->done_counter;
+      a.comm_error = h->flags + 4;
+      a.mode = 3;
+      if (launch_reduce_adam3(a, s)) return 1;
+      if (launch_wait_peers(a, s)) return 1;
+      a.mode = 4;
+      if (launch_reduce_adam3(a, s)) return 1;
     } else {
       a.mode = 1;
       if (launch_reduce_adam3(a, s)) return 1;
@@ -614,6 +634,7 @@ static int run_update_impl(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b20
     return 0;
   }
 
+  B200RL_REQUIRE(h->h_flags[4] == 0, "update: a peer's gradient did not arrive within 10 s (peer exchange over NVLink)");
   memset(stats, 0, sizeof(*stats));
   const double ng = (double)n_glob;
   const int applied_p = h->h_flags[1], applied_v = h->h_flags[2];
@@ -889,6 +910,53 @@ extern "C" int b200rl_onpolicy_device_view(b200rl_onpolicy* h, const char* name,
     }
   set_error("device_view: unknown view '%s'", name);
   return 2;
+}
+
+// ---- peer exchange set-up -----------------------------------------------------------------------------------------
+extern "C" int b200rl_onpolicy_comm_export(b200rl_onpolicy* h, void* handle64, void** local_ptr) {
+  B200RL_REQUIRE(h && handle64 && local_ptr, "comm_export: NULL argument");
+  B200RL_REQUIRE(h->fused_ok, "comm_export: the networks do not fit the fused step kernel (no peer exchange)");
+  if (!h->xchg) {
+    h->xchg_stride = ((h->Pp + h->Pv + 2 * B200RL_N_SCALARS + 31) / 32) * 32;
+    // a dedicated allocation (cudaIpcGetMemHandle exports whole allocations)
+    B200RL_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->xchg), (size_t)(2 * h->xchg_stride) * 4 + 64));
+    B200RL_CUDA(cudaMemset(h->xchg, 0, (size_t)(2 * h->xchg_stride) * 4 + 64));
+    h->allocs.push_back(h->xchg);
+    if (dev_alloc(h, &h->peers_dev, RA3_MAX_WORLD)) return 1;
+    if (dev_alloc(h, &h->done_counter, 4)) return 1;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  B200RL_CUDA(cudaIpcGetMemHandle(&hd, h->xchg));
+  memcpy(handle64, &hd, 64);
+  *local_ptr = h->xchg;
+  return 0;
+}
+
+extern "C" int b200rl_ipc_open(const void* handle64, void** ptr) {
+  B200RL_REQUIRE(handle64 && ptr, "ipc_open: NULL argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  B200RL_CUDA(cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int b200rl_ipc_close(void* ptr) {
+  if (ptr) B200RL_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+
+extern "C" int b200rl_onpolicy_comm_attach(b200rl_onpolicy* h, int32_t rank, int32_t world, void* const* peer_ptrs) {
+  B200RL_REQUIRE(h && peer_ptrs && h->xchg, "comm_attach: call comm_export first");
+  B200RL_REQUIRE(world >= 1 && world <= RA3_MAX_WORLD && rank >= 0 && rank < world, "comm_attach: bad rank / world size");
+  B200RL_REQUIRE(peer_ptrs[rank] == h->xchg, "comm_attach: peer_ptrs[rank] must be this engine's own buffer");
+  B200RL_CUDA(cudaMemcpy(h->peers_dev, peer_ptrs, (size_t)world * sizeof(void*), cudaMemcpyHostToDevice));
+  // every rank (re)starts its sequence at 1; stale sequence words cannot match before they are overwritten
+  B200RL_CUDA(cudaMemset(reinterpret_cast<char*>(h->xchg) + (size_t)(2 * h->xchg_stride) * 4, 0, 64));
+  h->comm_world = world;
+  h->comm_rank = rank;
+  h->comm_seq = 0;
+  return 0;
 }
 
 extern "C" int b200rl_onpolicy_scalar_history(b200rl_onpolicy* h, double* out, int32_t max_slots, int32_t* n_slots) {

@@ -762,6 +762,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
 // (ppo.py:176-181), in ONE launch.  mode 0: reduce + Adam (single GPU); mode 1: reduce only, scalars appended to the
 // flat gradient as float32 (the buffer ONE all-reduce carries); mode 2: Adam only, scalars read back from that tail.
 // A block owns 32 parameters; every block derives the stop decision from the same inputs in the same order.
+//
+// Data-parallel runs on one node replace "mode 1, NCCL all-reduce, mode 2" by a one-shot exchange over peer-mapped
+// memory (NVLink / NVSwitch): mode 3 reduces and stores this rank's [gradient | scalars] into its exchange buffer,
+// the last block to finish publishes the sequence number (release, system scope); mode 4 waits for every rank's
+// sequence number (acquire; wait_peers_kernel, one warp), reads ALL ranks' buffers -- its own included -- and adds them in rank order, so every
+// rank applies bit-identical updates, then runs Adam.  22 KB per rank: latency bound, ~2 us per peer read.
+// Buffers alternate between two parities: a rank can only be one exchange ahead of its slowest peer (it needs that
+// peer's next sequence number to finish its own), so the buffer it overwrites was read by everybody.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RA3_WARPS = 8;
 __global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3Args a) {
@@ -773,7 +781,19 @@ __global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3A
   const long long pidx = (long long)blockIdx.x * 32 + lane;
   const bool stopped_before = a.stop_flag != nullptr && *a.stop_flag != 0;
   const bool run_p = a.run_policy != 0 && !stopped_before, run_v = a.run_value != 0;
-  if (a.mode != 2) {
+  const unsigned parity = a.seq & 1u;
+  if (a.mode == 4) {  // every rank's buffer of this exchange has arrived (wait_peers_kernel ran before this launch)
+    if (threadIdx.x < 2 * B200RL_N_SCALARS) {
+      double t = 0.0;
+      for (int r = 0; r < a.world; ++r) {
+        float x;
+        const float* src = a.peers[r] + parity * a.xchg_stride + Ptot + threadIdx.x;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
+        t += (double)x;
+      }
+      s_scal[threadIdx.x] = t;
+    }
+  } else if (a.mode != 2) {
     // scalar sums: 32 row classes x 16 scalars, then the classes in order (same in every block)
     const int k = lane & 15, cls = warp * 4 + (lane >> 4) * 2;  // two classes per half-warp pass
     for (int half = 0; half < 2; ++half) {
@@ -792,7 +812,17 @@ __global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3A
   }
   __syncthreads();
   float g = 0.f;
-  if (a.mode != 2) {
+  if (a.mode == 4) {
+    if (warp == 0 && pidx < Ptot) {
+      for (int r = 0; r < a.world; ++r) {  // rank order: the same sum on every rank
+        float x;
+        const float* src = a.peers[r] + parity * a.xchg_stride + pidx;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
+        g += x;
+      }
+      if (a.grad != nullptr) a.grad[pidx] = g;
+    }
+  } else if (a.mode != 2) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (pidx < Ptot) {
       const float* qp = a.partials + pidx;
@@ -818,6 +848,23 @@ __global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3A
   }
   if (a.mode == 1) {
     if (blockIdx.x == 0 && threadIdx.x < 2 * B200RL_N_SCALARS) a.grad[Ptot + threadIdx.x] = (float)s_scal[threadIdx.x];
+    return;
+  }
+  if (a.mode == 3) {
+    float* mine = a.peers[a.rank] + parity * a.xchg_stride;
+    if (warp == 0 && pidx < Ptot) mine[pidx] = g;
+    if (blockIdx.x == 0 && threadIdx.x < 2 * B200RL_N_SCALARS) mine[Ptot + threadIdx.x] = (float)s_scal[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(a.done_counter, 1u);
+      if (prev == gridDim.x - 1) {  // every block's part of the buffer is written: publish
+        *a.done_counter = 0u;
+        __threadfence_system();
+        unsigned* flag = reinterpret_cast<unsigned*>(a.peers[a.rank] + 2 * a.xchg_stride) + parity;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.seq) : "memory");
+      }
+    }
     return;
   }
   // early stop (ppo.py:176-181): the KL carried by this step's forward pass is the KL after the PREVIOUS update
@@ -851,7 +898,31 @@ __global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3A
   }
 }
 
+// One warp waits until every rank has published the sequence number of this exchange.  A separate, tiny launch: while
+// it spins it holds next to nothing of its SM, and the gather + Adam launch behind it needs no polling at all.
+__global__ void __launch_bounds__(32) wait_peers_kernel(float* const* peers, int world, long long xchg_stride,
+                                                        unsigned seq, int* comm_error) {
+  if ((int)threadIdx.x >= world) return;
+  const unsigned* flag = reinterpret_cast<const unsigned*>(peers[threadIdx.x] + 2 * xchg_stride) + (seq & 1u);
+  const long long t0 = clock64();
+  unsigned seen;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+    if (seen != seq && clock64() - t0 > 20000000000LL) {  // ~10 s: a rank died or never launched
+      *comm_error = 1;
+      break;
+    }
+  } while (seen != seq);
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------
+int launch_wait_peers(const Ra3Args& a, cudaStream_t s) {
+  wait_peers_kernel<<<1, 32, 0, s>>>(a.peers, a.world, a.xchg_stride, a.seq, a.comm_error);
+  B200RL_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
 int tc3_configure() {
   static const int rc = []() -> int {
     return (int)cudaFuncSetAttribute(mlp_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM_BYTES);

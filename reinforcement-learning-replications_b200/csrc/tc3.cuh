@@ -40,8 +40,12 @@ struct Ra3Seg {
   float one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps;
 };
 
+constexpr int RA3_MAX_WORLD = 16;
+
 struct Ra3Args {
-  int mode;  // 0 reduce + Adam, 1 reduce only (scalars appended to grad), 2 Adam only (scalars from grad's tail)
+  // 0 reduce + Adam, 1 reduce only (scalars appended to grad), 2 Adam only (scalars from grad's tail),
+  // 3 reduce + publish into this rank's exchange buffer, 4 gather every rank's buffer over NVLink + Adam
+  int mode;
   const float* partials;
   const double* scalar_partials;
   int rows;          // partial rows (2 * grid of the step kernel)
@@ -54,6 +58,13 @@ struct Ra3Args {
   int* stop_flag;
   int *applied_p, *applied_v;
   int run_policy, run_value;
+  // peer exchange (modes 3 / 4): every rank's buffer is [2 parities][xchg_stride floats] followed by 2 sequence words
+  float* const* peers;       // device array [world] of the ranks' exchange buffers (peer-mapped device pointers)
+  int world, rank;
+  long long xchg_stride;
+  unsigned seq;              // sequence number of this exchange (parity = seq & 1)
+  unsigned* done_counter;    // device word, zero between launches
+  int* comm_error;           // raised when a peer's flag did not arrive within the time-out
 };
 
 bool tc3_shape_ok(const b200rl_mlp_desc& pol, const b200rl_mlp_desc& val);
@@ -63,5 +74,6 @@ int launch_pack_obs(const float* obs, int64_t n_rows, int n_in, const float* abs
                     float* bad_flag, cudaStream_t s);
 int launch_mlp_tc3(const Tc3Args& k, cudaStream_t s);
 int launch_reduce_adam3(const Ra3Args& a, cudaStream_t s);
+int launch_wait_peers(const Ra3Args& a, cudaStream_t s);
 
 }  // namespace b200rl

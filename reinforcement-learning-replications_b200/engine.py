@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import DIST, MlpDesc, OnPolicyConfig, PpoHparams, TrpoHparams, TrpoStats, UpdateStats, check
 
 POLICY, OLD_POLICY, VALUE = 0, 1, 2
+_OPENED_IPC: Dict[bytes, int] = {}  # CUDA IPC handle -> device pointer of the mapping in this process
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -66,6 +67,7 @@ class OnPolicyEngine:
         self.n_episodes = 0
         self._allreduce_cb = None
         self._keep = []
+        self.peer_exchange = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -185,6 +187,57 @@ class OnPolicyEngine:
                 return 1
 
         return _lib.ALLREDUCE_FN(cb)
+
+    # ---- one-shot gradient exchange over peer-mapped memory (one node, NVLink) ---------------------------------
+    def comm_export(self):
+        """(64-byte CUDA IPC handle, local device pointer) of this engine's exchange buffer."""
+        handle = (C.c_uint8 * 64)()
+        ptr = C.c_void_p()
+        check(self.lib.b200rl_onpolicy_comm_export(self.h, handle, C.byref(ptr)), "comm_export")
+        return bytes(handle), int(ptr.value)
+
+    def comm_attach(self, rank: int, peer_ptrs: Sequence[int]):
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        check(self.lib.b200rl_onpolicy_comm_attach(self.h, int(rank), len(peer_ptrs), arr), "comm_attach")
+        self.peer_exchange = True
+
+    def enable_peer_exchange(self, process_group=None) -> bool:
+        """Exchange IPC handles over torch.distributed and map every rank's buffer (all ranks on ONE node).  Returns
+        False (and leaves the NCCL all-reduce in place) when the ranks cannot map each other's memory."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        if world < 2 or world > 16:
+            return False
+        ok = 1
+        try:
+            handle, mine = self.comm_export()
+        except _lib.B200RLError:
+            handle, mine, ok = b"", 0, 0
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (handle, ok), group=process_group)
+        ptrs = []
+        if all(g[1] for g in gathered):
+            for r, (hd, _) in enumerate(gathered):
+                if r == rank:
+                    ptrs.append(mine)
+                    continue
+                if hd not in _OPENED_IPC:  # a handle can be mapped once per process: keep the mapping
+                    p = C.c_void_p()
+                    buf = (C.c_uint8 * 64).from_buffer_copy(hd)
+                    if self.lib.b200rl_ipc_open(buf, C.byref(p)) != 0:
+                        ok = 0
+                        break
+                    _OPENED_IPC[hd] = int(p.value)
+                ptrs.append(_OPENED_IPC[hd])
+        else:
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=process_group)  # all or nobody
+        if int(t.item()) != 1:
+            return False
+        self.comm_attach(rank, ptrs)
+        return True
 
     def update(self, hp: PpoHparams, algo: str = "ppo", process_group=None, distributed: bool = False,
                allreduce=None) -> UpdateStats:

@@ -1,9 +1,11 @@
 """Data-parallel parity check, run under torchrun on N GPUs (NCCL):
    torchrun --nproc-per-node N tests/dist_check.py
 Every rank builds the same global batch, trains on its contiguous block of episodes with distributed=True, and the
-result must match a single-GPU run on the whole batch (value net 1e-5 of max|ref|; policy net 5e-5 after 6 PPO steps --
-the 1-GPU and 2-GPU runs sum gradients in a different order and Adam amplifies near-zero entries): the sharded engine computes the same global
-mean / std / KL and applies the same reduced gradient on every rank."""
+result must match the numpy ORACLE on the whole batch at 1e-5 of max|ref| (north_star), and a single-GPU run of the
+same engine at 2e-5 (two results that are each within 1e-5 of the oracle): the sharded engine computes the same global
+mean / std / KL and applies the same reduced gradient on every rank.  Both gradient-exchange
+paths are exercised: the one-shot exchange over peer-mapped memory (default) and the NCCL all-reduce per iteration
+(B200RL_PEER_EXCHANGE=0)."""
 import os
 import sys
 
@@ -33,10 +35,14 @@ def main():
                                   mean_fn=lambda o: O.mlp_forward(pl, o)[0])
     hp = dict(num_policy_gradients=6, num_value_gradients=6)
     ok = True
-    for max_kl in (float("inf"), 0.002):  # second setting triggers the device-side early stop on every rank
+    oracle = {}
+    # (max_kl, peer exchange): the 0.002 setting triggers the device-side early stop on every rank
+    for max_kl, peer in ((float("inf"), "1"), (0.002, "1"), (float("inf"), "0"), (0.002, "0")):
+        os.environ["B200RL_PEER_EXCHANGE"] = peer
         dp = build(ps, vs, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std, distributed=True,
                    max_kl_divergence=max_kl, **hp)
         dp.train_packed(synthetic.shard_batch(full, rank, world))
+        path = "peer-memory exchange" if dp._engine.peer_exchange else "NCCL all-reduce"
         p_dp, v_dp = flat(dp.policy.network).copy(), flat(dp.value_function.network).copy()
         st = dp.last_update_stats
         # all ranks must hold bit-identical parameters
@@ -52,11 +58,20 @@ def main():
             rs = ref.last_update_stats
             ep = np.abs(p_dp - flat(ref.policy.network)).max() / np.abs(flat(ref.policy.network)).max()
             ev = np.abs(v_dp - flat(ref.value_function.network)).max() / np.abs(flat(ref.value_function.network)).max()
-            good = (same and ep < 5e-5 and ev < 1e-5 and st.policy_steps_applied == rs.policy_steps_applied
+            if max_kl not in oracle:
+                oracle[max_kl] = O.ppo_train(full, pl, vl, "gaussian", log_std, O.AdamState(5702, 3e-4),
+                                             O.AdamState(5377, 1e-3), max_kl=max_kl, n_policy=6, n_value=6)
+            o = oracle[max_kl]
+            eop = np.abs(p_dp - o["policy_flat"]).max() / np.abs(o["policy_flat"]).max()
+            eov = np.abs(v_dp - o["value_flat"]).max() / np.abs(o["value_flat"]).max()
+            good = (same and ep < 2e-5 and ev < 2e-5 and eop < 1e-5 and eov < 1e-5
+                    and st.policy_steps_applied == rs.policy_steps_applied == o["policy_steps"]
+                    and dp._engine.peer_exchange == (peer == "1")
                     and abs(st.kl_divergence - rs.kl_divergence) < 1e-4 * abs(rs.kl_divergence) + 1e-8
                     and abs(st.value_loss_mean - rs.value_loss_mean) < 1e-5 * rs.value_loss_mean
                     and abs(st.adv_std - rs.adv_std) < 1e-9 * rs.adv_std)
-            print(f"max_kl={max_kl}: world={world} ranks_identical={same} policy_err={ep:.2e} value_err={ev:.2e} "
+            print(f"max_kl={max_kl} [{path}]: world={world} ranks_identical={same} vs oracle: policy {eop:.2e} value {eov:.2e}; "
+                  f"vs 1-GPU run: policy_err={ep:.2e} value_err={ev:.2e} "
                   f"steps {st.policy_steps_applied}/{rs.policy_steps_applied} kl {st.kl_divergence:.6g}/{rs.kl_divergence:.6g} "
                   f"vloss {st.value_loss_mean:.6g}/{rs.value_loss_mean:.6g} -> {'OK' if good else 'FAIL'}")
             ok = ok and good

@@ -122,6 +122,79 @@ def test_data_parallel_update_matches_oracle_and_single_engine(max_kl):
         e.close()
 
 
+def test_data_parallel_peer_exchange_two_engines_one_gpu():
+    """The one-shot gradient exchange over peer-mapped memory (reduce_adam3 modes 3 / 4 + wait_peers_kernel), driven
+    by two engines on one GPU: each on its own stream and host thread, exchange buffers attached by raw pointer (on a
+    multi-GPU node the pointers come from CUDA IPC handles, tests/dist_check.py).  Same bars as the hook-based run."""
+    from rl_replicas_b200 import synthetic
+    from rl_replicas_b200.engine import OLD_POLICY, POLICY, VALUE, OnPolicyEngine
+    rng = np.random.default_rng(1)
+    ps, vs = [17, 64, 64, 6], [17, 64, 64, 1]
+    pl, vl = _layers(rng, ps), _layers(rng, vs)
+    log_std = np.full(6, -0.5, np.float32)
+    full = synthetic.ragged_batch(20000, 17, 6, False, seed=4, min_len=50, max_len=400,
+                                  mean_fn=lambda o: O.mlp_forward(pl, o)[0])
+    n, K = full["obs"].shape[0], 5
+    engines = []
+    for r in range(2):
+        b = synthetic.shard_batch(full, r, 2)
+        e = OnPolicyEngine(ps, vs, "gaussian", b["obs"].shape[0], b["ep_done"].shape[0])
+        e.set_params(POLICY, O.flatten_layers(pl))
+        e.set_params(OLD_POLICY, O.flatten_layers(pl))
+        e.set_params(VALUE, O.flatten_layers(vl))
+        e.set_log_std(log_std)
+        e.set_adam(POLICY, None, None, 0)
+        e.set_adam(VALUE, None, None, 0)
+        e.load_batch(b)
+        engines.append(e)
+    ptrs = [e.comm_export()[1] for e in engines]
+    for r, e in enumerate(engines):
+        e.comm_attach(r, ptrs)
+    torch.cuda.synchronize()
+    barrier, bufs, stats, errors = threading.Barrier(2), [None, None], [None, None], []
+
+    def hook(rank):  # the three small collectives of an update; the engines run on different streams here
+        def fn(t):
+            torch.cuda.current_stream().synchronize()
+            bufs[rank] = t
+            barrier.wait()
+            if rank == 0:
+                total = bufs[0] + bufs[1]
+                bufs[0].copy_(total)
+                bufs[1].copy_(total)
+                torch.cuda.current_stream().synchronize()
+            barrier.wait()
+        return fn
+
+    def work(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                hp = OnPolicyEngine.hparams(n_global_rows=n, max_kl_divergence=float("inf"), num_policy_gradients=K,
+                                            num_value_gradients=K)
+                stats[r] = engines[r].update(hp, allreduce=hook(r))
+                torch.cuda.current_stream().synchronize()
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+            barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert stats[0].fused == 1 and stats[1].fused == 1
+    pd, vd = [e.get_params(POLICY) for e in engines], [e.get_params(VALUE) for e in engines]
+    np.testing.assert_array_equal(pd[0], pd[1])
+    np.testing.assert_array_equal(vd[0], vd[1])
+    out = O.ppo_train(full, pl, vl, "gaussian", log_std, O.AdamState(5702, 3e-4), O.AdamState(5377, 1e-3),
+                      max_kl=float("inf"), n_policy=K, n_value=K)
+    assert rel_err(pd[0], out["policy_flat"]) < 1e-5 and rel_err(vd[0], out["value_flat"]) < 1e-5
+    assert abs(stats[0].kl_divergence - out["kl"]) < 1e-4 * abs(out["kl"]) + 1e-8
+    for e in engines:
+        e.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # (c) config 2 at full size against the oracle
 # ---------------------------------------------------------------------------------------------------------------
@@ -155,10 +228,18 @@ def test_full_size_config2_against_the_oracle():
           f"value grad err {err_v:.2e} ({noise_v:.2e})")
     assert err_p < max(1e-5, noise_p), (err_p, noise_p)
     assert err_v < max(1e-5, noise_v), (err_v, noise_v)
-    # one Adam step turns a gradient entry g into lr * g / (|g| + eps): entries near eps amplify any difference, so
-    # parameters are compared entry-wise against BOTH oracles' envelope
-    for got, key in ((flat(ppo.policy.network), "policy_flat"), (flat(ppo.value_function.network), "value_flat")):
-        assert rel_err(got, out[key]) < max(1e-5, 2 * rel_err(o32[key], out[key])), key
+    # The first Adam step moves an entry by lr * g / (|g| + eps): entries with |g| near eps = 1e-8 turn a 1e-9 gradient
+    # difference into a macroscopic fraction of lr, so at this size the parameters are checked for what they must be --
+    # torch's Adam applied to the (already checked) gradient the GPU computed -- and against the oracle entry-wise
+    # wherever the gradient is large enough for the step to be well conditioned.
+    for got, g_gpu, flat0, n_par, lr, key, gkey in (
+            (flat(ppo.policy.network), pg, O.flatten_layers(pl), 5702, 3e-4, "policy_flat", "grad0"),
+            (flat(ppo.value_function.network), vg, O.flatten_layers(vl), 5377, 1e-3, "value_flat", "vgrad0")):
+        want = O.AdamState(n_par, lr).apply(flat0.copy(), g_gpu)
+        assert rel_err(got, want) < 1e-6, key
+        solid = np.abs(out[gkey]) > 1e-4 * np.abs(out[gkey]).max()
+        assert solid.mean() > 0.9
+        assert rel_err(got[solid], out[key][solid]) < 1e-5, key
     st = ppo.last_update_stats
     assert abs(st.value_loss_first - out["value_loss_mean"]) < 1e-5 * out["value_loss_mean"]
     assert abs(st.kl_divergence - out["kl"]) < 1e-4 * abs(out["kl"]) + 1e-8
