@@ -10,12 +10,15 @@ normalisation -> 80 policy-gradient steps (+ final KL pass) -> old-policy sync -
 Workload at N GPUs: 1024 envs x 1000 steps PER GPU (BASELINE configs[1]; configs[4] at N = 8) -- weak scaling.
 
   value : transitions/s with the batch already resident in HBM (engine.update only).
-  e2e   : same through the public API, PPO.train_packed(host batch): pinned-host -> device copies of the batch,
-          parameter/optimizer-state upload, the update, and the device -> host read-back of parameters,
-          optimizer state and the logged scalars, all inside the timed region.
+  e2e   : same through the public API, PPO.train(experience) with a PackedExperience in pinned host memory (the
+          rollout store a sampler fills): host -> device copies of the batch, parameter / optimizer-state upload, the
+          update, and the device -> host read-back of parameters, optimizer state and the logged scalars, all inside the
+          timed region.
 
-Only the two CPU legs (`cpu_baseline` of the default run, `--impl reference`) import `oracle/`; the measured arm builds its
-learners and synthetic data from `rl_replicas_b200.synthetic` alone.
+The CPU legs (`cpu_baseline` of the default run, `--impl reference`) run the UNMODIFIED reference, pip-installed from
+/root/reference into git-ignored baseline/_ref by __graft_entry__.build() (kind "reference"); only if that package is
+absent they fall back to oracle/torch_port.py (kind "port").  The measured arm imports neither: it builds its learners
+and synthetic data from `rl_replicas_b200.synthetic` alone.
 """
 from __future__ import annotations
 
@@ -39,6 +42,7 @@ N_POLICY, N_VALUE = 80, 80
 # algorithmic fp32-equivalent FLOPs per row (2*MAC), SURVEY.md section 8: policy fwd 11136 / bwd 20096, value 10496 / 18816
 FLOP_POLICY_STEP = 11136 + 20096
 FLOP_VALUE_STEP = 10496 + 18816
+FLOP_FUSED_STEP = FLOP_POLICY_STEP + FLOP_VALUE_STEP  # one mlp_tc3 launch = policy step + value step
 FLOP_PER_TRANSITION = (N_POLICY + 1) * 11136 + N_POLICY * 20096 + (N_VALUE + 1) * 10496 + N_VALUE * 18816
 
 
@@ -103,41 +107,122 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def _numa0_cpus():
+    """CPUs of NUMA node 0 (the reference arm is pinned there: no cross-socket traffic, repeatable timings)."""
+    try:
+        txt = open("/sys/devices/system/node/node0/cpulist").read().strip()
+        cpus = []
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        return cpus or sorted(allowed)
+    except Exception:
+        return sorted(os.sched_getaffinity(0))
+
+
+def _import_reference():
+    """The unmodified reference from baseline/_ref (None if it was not installed).  gymnasium is not in the image and the
+    update path uses it for type annotations only: a stub module stands in."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "rl_replicas")):
+        return None
+    import types
+    if "gymnasium" not in sys.modules:
+        gym, spaces = types.ModuleType("gymnasium"), types.ModuleType("gymnasium.spaces")
+        for name in ("Env", "Space"):
+            setattr(gym, name, type(name, (), {}))
+        for name in ("Box", "Discrete"):
+            setattr(spaces, name, type(name, (gym.Space,), {}))
+        gym.spaces, gym.make = spaces, (lambda *a, **k: None)
+        sys.modules["gymnasium"], sys.modules["gymnasium.spaces"] = gym, spaces
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import rl_replicas  # noqa: F401
+        from rl_replicas.algorithms import PPO  # noqa: F401
+        return rl_replicas
+    except Exception:
+        return None
+
+
 def cpu_reference_run(steps, warmup, n_envs=64, horizon=1000):
-    """The reference's CPU path for this workload.  The reference itself is Python-on-torch and does not travel to
-    the GPU box, so the arm is oracle/torch_port.py: the same torch CPU calls (F.linear/tanh, distributions, autograd,
-    torch.optim.Adam, scipy lfilter) on all host threads torch will use.  Bounded sample of the same workload:
-    n_envs x horizon transitions, the same 80 + 80 full-batch steps (throughput is size-independent to first order)."""
+    """The reference's CPU path for this workload: rl_replicas.algorithms.PPO.train(experience) itself when the package
+    is installed under baseline/_ref, on a bounded sample of the same workload (n_envs x horizon transitions, the same
+    80 + 80 full-batch steps; throughput is size-independent to first order), pinned to NUMA node 0 with a fixed thread
+    count.  Returns (cpu_baseline dict, best seconds per step)."""
     import torch
-    from oracle import onpolicy as O, torch_port as T
-    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is meant to use the host's cores
-    want = max(torch.get_num_threads(), (os.cpu_count() or 2) // 2)
-    if want != torch.get_num_threads():
-        torch.set_num_threads(want)
+    cpus = _numa0_cpus()
+    try:
+        os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    threads = max(1, min(32, len(cpus) // 2 if len(cpus) >= 4 else len(cpus)))  # physical cores of the node, at most 32
+    torch.set_num_threads(threads)  # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm uses the host's cores
     pl, vl, log_std = make_nets()
     b = make_batch(n_envs, horizon, pl, seed=0)
     n = n_envs * horizon
+    ref = _import_reference()
+    if ref is not None:
+        from rl_replicas.algorithms import PPO
+        from rl_replicas.experience import Experience
+        from rl_replicas.networks import MLP
+        from rl_replicas.policies import GaussianPolicy
+        from rl_replicas.value_function import ValueFunction
+        from rl_replicas_b200 import synthetic
+
+        def load(net, layers):
+            linears = [m for m in net.modules() if isinstance(m, torch.nn.Linear)]
+            with torch.no_grad():
+                for lin, (w, bias) in zip(linears, layers):
+                    lin.weight.copy_(torch.from_numpy(w))
+                    lin.bias.copy_(torch.from_numpy(bias))
+
+        pnet, vnet = MLP(POLICY_SIZES), MLP(VALUE_SIZES)
+        load(pnet, pl)
+        load(vnet, vl)
+        policy = GaussianPolicy(pnet, torch.optim.Adam(pnet.parameters(), lr=3e-4),
+                                torch.nn.Parameter(torch.from_numpy(log_std.copy())))
+        vf = ValueFunction(vnet, torch.optim.Adam(vnet.parameters(), lr=1e-3))
+        algo = PPO(policy, vf, None, None, num_policy_gradients=N_POLICY, num_value_gradients=N_VALUE,
+                   max_kl_divergence=float("inf"))
+
+        class _Sink:
+            def record_scalar(self, *a, **k):
+                pass
+
+        algo.metrics_manager, algo.current_total_steps = _Sink(), 0
+        exp = Experience(**synthetic.to_experience_lists(b, False))
+        step_fn, kind = (lambda: algo.train(exp)), "reference"
+        what = "rl_replicas 0.0.7 PPO.train(experience), unmodified, from baseline/_ref"
+    else:
+        from oracle import torch_port as T
+        step_fn = lambda: T.ppo_train(b, pl, vl, "gaussian", log_std, max_kl=float("inf"), n_policy=N_POLICY,
+                                      n_value=N_VALUE)
+        kind, what = "port", "torch-CPU port of the reference (oracle/torch_port.py; baseline/_ref is not installed)"
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        T.ppo_train(b, pl, vl, "gaussian", log_std, max_kl=float("inf"), n_policy=N_POLICY, n_value=N_VALUE)
+        step_fn()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    best = float(np.mean(times))
-    return dict(value=n / best, unit="transitions/s", cores=int(torch.get_num_threads()), kind="port",
-                host_cpus=os.cpu_count(),
+    best = float(np.min(times))
+    return dict(value=n / best, unit="transitions/s", cores=int(threads), kind=kind, host_cpus=os.cpu_count(),
+                numa0_cpus=len(cpus), mean_value=n / float(np.mean(times)),
                 sample=f"{n_envs} envs x {horizon} steps = {n} transitions, {N_POLICY}+{N_VALUE} full-batch steps, "
-                       f"torch-CPU port of the reference (oracle/torch_port.py), mean of {len(times)} run(s)"), best
+                       f"{what}; {threads} threads pinned to NUMA node 0; best of {len(times)} run(s) after {warmup} "
+                       f"warm-up (BASELINE.md section 3)"), best
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, sec = cpu_reference_run(args.steps, min(args.warmup, 1))
+    cb, sec = cpu_reference_run(args.steps, args.warmup)
     line = {"impl": "reference", "metric": "ppo_update_transitions_per_sec", "value": cb["value"],
-            "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,6 +284,15 @@ def main():
 
     ppo = synthetic.onpolicy_learner("ppo", pl, vl, log_std, num_policy_gradients=N_POLICY, num_value_gradients=N_VALUE,
                                      max_kl_divergence=float("inf"), distributed=distributed)
+    # the rollout store a sampler fills, in pinned host memory: what the public train() is handed
+    from rl_replicas_b200.experience import PackedExperience
+    store = PackedExperience(n_local, OBS, ACT, pinned=True)
+    off = batch["ep_offsets"]
+    for ep in range(E):
+        a, z = int(off[ep]), int(off[ep + 1])
+        done_col = np.zeros(z - a, dtype=bool)
+        done_col[-1] = bool(batch["ep_done"][ep])
+        store.append_episode(batch["obs"][a:z], batch["act"][a:z], batch["rew"][a:z], done_col, batch["last_obs"][ep])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -231,7 +325,8 @@ def main():
     if sampler:
         sampler.start()
     l0 = lib.b200rl_launch_count()
-    ms_e2e = timed(lambda: ppo.train_packed(pinned), args.steps, args.warmup)
+    ms_e2e = timed(lambda: ppo.train(store), args.steps, args.warmup)  # the reference's boundary call (ppo.py:139)
+    fused_path = int(ppo.last_update_stats.fused)
     launches_per_step = (lib.b200rl_launch_count() - l0) // (args.steps + args.warmup)
 
     # ---------------- value: batch resident in HBM ----------------
@@ -256,8 +351,19 @@ def main():
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / reps
 
+    engine.run_stage("preamble", hp)
+    engine.run_stage("old_logp", hp)
+    ms_pack = stage_ms("pack_obs", 10)
+    ms_fused = stage_ms("fused_step_kernel", 10)
     ms_pol = stage_ms("policy_grad_kernel", 10)
     ms_val = stage_ms("value_grad_kernel", 10)
+    tf_fused = FLOP_FUSED_STEP * n_local / (ms_fused * 1e-3) / 1e12
+    ncu = {}
+    try:  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture (tools/ncu_summary.py)
+        with open(os.path.join(ROOT, "profiles", "r02_tc3_ncu.json")) as f:
+            ncu = json.load(f)
+    except Exception:
+        pass
     scan_reps = 20
     engine.run_stage("values", hp)
     ms_scan_pair = stage_ms("scan", scan_reps)
@@ -407,22 +513,34 @@ def main():
             "e2e": {"value": e2e, "unit": "transitions/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "dtype_note": "fp32 semantics (1e-5 parity vs the float32 reference); tensor-core products are 3 fp16 MMAs "
-                          "on two-way fp16 splits with fp32 accumulation, range-checked with a bf16x3 re-run",
+                          "on two-way fp16 splits with fp32 accumulation, range-checked (a trip redoes the update on "
+                          "the wide-range kernels)",
             "tc_wide_range_reruns": int(_lib.load().b200rl_tc_fallback_count()),
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": {"kernel": "mlp_tc2_kernel<true> (tcgen05 fp16x2 policy fwd+loss+bwd, one launch per policy step; "
-                                   "timed with the predicated wide-range re-run queued behind it)",
-                         "bound": "tensor", "achieved": tf_pol, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": tf_pol / pk["tf_sust"],
-                         "traffic": 105.9e6 if (E, T) == (1024, 1000) else None,
-                         "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of one ncu "
-                                         "--set full capture at this shape (profiles/r01_tc2_summary.md section 5; "
-                                         "algorithmic 100 B x 1.024 M rows = 102.4 MB)",
-                         "note": f"fp32-equivalent algorithmic FLOPs ({FLOP_POLICY_STEP}/row) over the CUDA-event "
-                                 f"launch time; peak = 16-bit dense sustained GEMM ({pk['src']}); the kernel executes 3 fp16 MMAs per "
-                                 f"logical fp32 product",
-                         "ms_per_launch": ms_pol},
+            "fused_step_path": fused_path,
+            "roofline": {"kernel": "mlp_tc3_kernel (tcgen05 fp16x2: policy fwd + PPO-clip loss + bwd AND value fwd + MSE + "
+                                   "bwd over the same 128-row tile, one launch per PPO iteration; observations packed "
+                                   "once per update and staged by cp.async.bulk)",
+                         "bound": "tensor", "achieved": tf_fused, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                         "frac": tf_fused / pk["tf_sust"],
+                         "traffic": ncu.get("dram_bytes_per_launch") if (E, T) == (1024, 1000) else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of one ncu --set full "
+                                         "capture at this shape (profiles/r02_tc3_ncu.json); algorithmic: 104 B per row "
+                                         "of reference data (fp32 obs 68 + act 24 + adv 4 + old log-prob 4 + return 4) "
+                                         "= 106.5 MB; the kernel reads the packed fp16-pair observations (128 B per row) "
+                                         "instead of the fp32 ones: 164 B per row = 167.9 MB",
+                         "ncu": {k: ncu.get(k) for k in ("issue_active_pct", "tensor_pipe_active_pct", "duration_us",
+                                                         "warp_instructions", "registers", "source")},
+                         "note": f"fp32-equivalent algorithmic FLOPs ({FLOP_FUSED_STEP}/row: policy {FLOP_POLICY_STEP} + "
+                                 f"value {FLOP_VALUE_STEP}) over the CUDA-event launch time; peak = 16-bit dense sustained "
+                                 f"GEMM ({pk['src']}); the kernel executes 3 fp16 MMAs per logical fp32 product (2 for "
+                                 f"weight gradients), so 100 % of this roofline is not reachable at fp32-grade accuracy",
+                         "ms_per_launch": ms_fused},
+            "pack_obs": {"ms_per_launch": ms_pack, "note": "once per update: fp32 observations -> packed fp16-pair tiles"},
+            "roofline_policy_kernel": {"kernel": "mlp_tc2_kernel<true> (the two-loop path / VPG / TRPO surrogate)",
+                                       "bound": "tensor", "achieved": tf_pol, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                                       "frac": tf_pol / pk["tf_sust"], "ms_per_launch": ms_pol},
             "roofline_value_kernel": {"bound": "tensor", "achieved": tf_val, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                                       "frac": tf_val / pk["tf_sust"], "ms_per_launch": ms_val},
             "roofline_scan": {"kernel": "gae_scan_episode_kernel<double> (single launch: scan + statistics)", "bound": "hbm", "achieved": gbs_scan,
@@ -441,7 +559,7 @@ def main():
             "other_configs": extras,
         }
         if not args.no_cpu_baseline and world == 1:
-            cb, _ = cpu_reference_run(1, 0)
+            cb, _ = cpu_reference_run(2, 1)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if distributed:

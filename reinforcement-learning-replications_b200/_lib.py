@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200rl.so")
+LIB_PATH = os.environ.get("B200RL_LIB") or os.path.join(HERE, "libb200rl.so")  # B200RL_LIB: an A/B build of the library
 
 MAX_LAYERS = 4
 N_SCALARS = 8

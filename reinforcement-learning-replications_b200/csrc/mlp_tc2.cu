@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
         float z[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[j] = fmaf(__uint_as_float(v[j]), unscale, bias[cs + j]);
-        tanh16(z);  // |tanh| <= 1, and Z is finite: observations, weights and biases were all checked
+        tanh16_scaled(z, 1.f);  // |tanh| <= 1, and Z is finite: observations, weights and biases were all checked
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(z[j]);
         if (BACKWARD && stage == 1) t2_tmem_st16(tz + tm_col + cs, v);

@@ -455,12 +455,12 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
         float z[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[j] = fmaf(__uint_as_float(v[j]), unscale, bs[cs + j]);
-        tanh16(z);
+        tanh16_scaled(z, sH);  // tanh(z) * 2^14
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           float x[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = z[8 * ch + j] * sH;
+          for (int j = 0; j < 8; ++j) x[j] = z[8 * ch + j];
           store_chunk2(sm, dst, r, (cs >> 3) + ch, x);
         }
         arrive();

@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
         float z[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) z[j] = fmaf(__uint_as_float(v[j]), unscale, bias[cs + j]);
-        tanh16(z);  // Z is finite: observations, weights and biases were all checked
+        tanh16_scaled(z, 1.f);  // Z is finite: observations, weights and biases were all checked
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(z[j]);
         if (keep_fp32) t2_tmem_st16(tz + tm_z + cs, v);
