@@ -67,6 +67,12 @@ constexpr uint32_t M3_CHAIN = 80, M3_Z = 0, M3_OUT = 64;          // per chain: 
 constexpr uint32_t M3_ACC = 160, M3_ACC_NET = 176;
 constexpr uint32_t M3_DW2 = 0, M3_DB2 = 64, M3_DW1 = 80, M3_DW3 = 144;
 
+#ifdef B200RL_TC3_TIMING
+// CTA 0: [0..9] job wait cycles (2 * (stage - 1) + chain), [10..19] job work cycles, [20..29] issuer: wait for the
+// stage inputs, [30..39] issuer: issuing, [40] issuer: waiting for the bulk copy, [41] tiles of the CTA
+__device__ unsigned long long g_tc3_t[48];
+#endif
+
 enum { C3_G = 0, C3_U1, C3_U2, C3_U3, C3_UH2, C3_UH1, C3_W1, C3_W2, C3_W3, C3_OW3, C3_OW2, C3_OW1, C3_OB, C3_N };
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -164,6 +170,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
   const uint32_t bars = base + S3_BARS;  // ready[c] at +8c, chain[c] at +16+8c, xfull[b] at +32+8b
   const int n_in = p.n_in;
   bool bad = false;
+#ifdef B200RL_TC3_TIMING
+  unsigned long long tacc[48];
+  for (int i = 0; i < 48; ++i) tacc[i] = 0;
+  const long long t_kernel0 = clock64();
+#endif
 
   // ---- one-time setup: zero operand buffers; scales; weights of both networks as fp16 pairs; biases ----
   for (uint32_t i = tid; i < S3_OPERANDS_END / 16; i += T3_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
@@ -344,8 +355,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
     };
     auto issue_z1 = [&](const int c, long long k) {  // Z1 = X W1^T of tile k for chain c
       const uint32_t b = (uint32_t)(k & 1);
+#ifdef B200RL_TC3_TIMING
+      const long long xt0 = clock64();
+#endif
       mbar_wait(ubar + 32 + 8 * b, (uint32_t)((k >> 1) & 1));
       tc_fence_after_sync();
+#ifdef B200RL_TC3_TIMING
+      tacc[40] += (unsigned long long)(clock64() - xt0);
+#endif
       issue_chain3<2>(c * M3_CHAIN + M3_Z, I_128_64_KM, op2_at(X_K, b * T2_ACT), op2_at(W1T_M, c * S3_WNET));
     };
     if (cta_tiles > 0) {
@@ -365,9 +382,16 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
         for (int c = c_first; c <= c_last; ++c) {
           const uint32_t co = c * S3_CHAIN, wo = c * S3_WNET;
           const uint32_t tz = c * M3_CHAIN, ta = M3_ACC + c * M3_ACC_NET;
+#ifdef B200RL_TC3_TIMING
+          const long long it0 = clock64();
+#endif
           mbar_wait(ubar + 8 * c, (par_ready >> c) & 1u);  // every epilogue thread has delivered the stage inputs
           par_ready ^= 1u << c;
           tc_fence_after_sync();
+#ifdef B200RL_TC3_TIMING
+          const long long it1 = clock64();
+          tacc[20 + 2 * (stage - 1) + c] += (unsigned long long)(it1 - it0);
+#endif
           if (stage == 1) {  // Z2 = H1 W2^T
             issue_chain3<4>(tz + M3_Z, I_128_64_KK, op2_at(H1_K, co), op2_at(W2_K, wo));
           } else if (stage == 2) {  // OUT = H2 W3^T
@@ -395,9 +419,18 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
           }
           umma_commit_elect(ubar + 16 + 8 * c);
           __syncwarp();
+#ifdef B200RL_TC3_TIMING
+          tacc[30 + 2 * (stage - 1) + c] += (unsigned long long)(clock64() - it1);
+#endif
         }
       }
     }
+#ifdef B200RL_TC3_TIMING
+    if (lane == 0 && blockIdx.x == 0) {
+      for (int i = 20; i <= 40; ++i) g_tc3_t[i] = tacc[i];
+      g_tc3_t[41] = (unsigned long long)cta_tiles;
+    }
+#endif
   } else {
     // =============================== epilogue warps: one pool of 16 ===================================
     // Jobs run in the fixed order (policy, E1) (value, E1) (policy, E2) ... (value, E5) | next tile, all 16 warps on
@@ -423,6 +456,9 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
       adv_inv_std = 1.f / (float)sqrt((s2 - cnt * mean * mean) / (cnt - 1.0));
     }
 
+#ifdef B200RL_TC3_TIMING
+    long long t_work0 = 0;
+#endif
     auto job = [&](const int c, const int stage, const long long k) {
       const uint32_t tz = tmem + lane_addr + (uint32_t)c * M3_CHAIN;
       const uint32_t so = S3_H + (uint32_t)c * S3_CHAIN;
@@ -439,9 +475,19 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
         mbar_arrive(bar_ready);
       };
       auto wait_chain = [&]() {
+#ifdef B200RL_TC3_TIMING
+        const long long w0 = clock64();
+#endif
         mbar_wait(bar_chain, (ph_chain >> c) & 1u);
         ph_chain ^= 1u << c;
         tc_fence_after_sync();
+#ifdef B200RL_TC3_TIMING
+        {
+          const long long w1 = clock64();
+          tacc[2 * (stage - 1) + c] += (unsigned long long)(w1 - w0);
+          t_work0 = w1;
+        }
+#endif
       };
       if (stage == 1 || stage == 2) {
         // ---- E1 / E2: Z (TMEM) * unscale + bias -> tanh -> fp16 pairs ----
@@ -618,15 +664,26 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
       }
     };
 
+#ifdef B200RL_TC3_TIMING
+    const long long t_loop0 = clock64();
+#endif
 #pragma unroll 1
     for (long long k = 0; k < cta_tiles; ++k) {
 #pragma unroll 1
       for (int stage = 1; stage <= 5; ++stage) {
 #pragma unroll 1
-        for (int c = c_first; c <= c_last; ++c) job(c, stage, k);  // one copy of the job code (instruction cache)
+        for (int c = c_first; c <= c_last; ++c) {
+          job(c, stage, k);  // one copy of the job code (instruction cache)
+#ifdef B200RL_TC3_TIMING
+          tacc[10 + 2 * (stage - 1) + c] += (unsigned long long)(clock64() - t_work0);
+#endif
+        }
       }
     }
 
+#ifdef B200RL_TC3_TIMING
+    const long long t_loop_end = clock64();
+#endif
     // ---- per-CTA results ----
     if (cta_tiles > 0) {
 #pragma unroll 1
@@ -747,6 +804,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
       p.scalar_partials[((size_t)blockIdx.x * 2 + 1) * (2 * B200RL_N_SCALARS) + s] = 0.0;
     }
     if (bad) *s_bad = 1;
+#ifdef B200RL_TC3_TIMING
+    if (tid == 0 && blockIdx.x == 0) {
+      for (int i = 0; i < 20; ++i) g_tc3_t[i] = tacc[i];
+      g_tc3_t[42] = (unsigned long long)(t_loop0 - t_kernel0);   // setup
+      g_tc3_t[43] = (unsigned long long)(t_loop_end - t_loop0);  // tile loop
+      g_tc3_t[44] = (unsigned long long)(clock64() - t_loop_end);  // read-out
+    }
+#endif
   }
 
   // ---- teardown ----
@@ -979,3 +1044,13 @@ int launch_reduce_adam3(const Ra3Args& a, cudaStream_t s) {
 }
 
 }  // namespace b200rl
+
+#ifdef B200RL_TC3_TIMING
+extern "C" int b200rl_debug_tc3_timing(unsigned long long* out48, int reset) {
+  if (reset) {
+    unsigned long long z[48] = {0};
+    return (int)cudaMemcpyToSymbol(b200rl::g_tc3_t, z, sizeof(z));
+  }
+  return (int)cudaMemcpyFromSymbol(out48, b200rl::g_tc3_t, sizeof(unsigned long long) * 48);
+}
+#endif

@@ -38,3 +38,19 @@ if __name__ == "__main__":
 
     out = {s: ms(s, reps) for s in ("pack_obs", "fused_step_kernel", "fused_step", "policy_grad_kernel", "value_grad_kernel")}
     print({k: round(v, 4) for k, v in out.items()}, "fused update:", ppo.last_update_stats.fused)
+    if os.environ.get("B200RL_TC3_TIMING"):
+        import ctypes as C
+        from rl_replicas_b200 import _lib
+        lib = _lib.load()
+        out = (C.c_ulonglong * 48)()
+        lib.b200rl_debug_tc3_timing(out, 1)
+        e.run_stage("fused_step_kernel", hp)
+        torch.cuda.synchronize()
+        lib.b200rl_debug_tc3_timing(out, 0)
+        tiles = max(int(out[41]), 1)
+        names = [f"E{s}{'pv'[c]}" for s in range(1, 6) for c in range(2)]
+        print("tiles of CTA 0:", tiles, "setup", int(out[42]), "tile loop", int(out[43]), "read-out", int(out[44]), "cycles")
+        print("job wait  / tile:", {n: int(out[i]) // tiles for i, n in enumerate(names)}, "sum", sum(int(out[i]) for i in range(10)) // tiles)
+        print("job work  / tile:", {n: int(out[10 + i]) // tiles for i, n in enumerate(names)}, "sum", sum(int(out[10 + i]) for i in range(10)) // tiles)
+        print("issuer wait/tile:", {n.replace('E', 'S'): int(out[20 + i]) // tiles for i, n in enumerate(names)}, "sum", sum(int(out[20 + i]) for i in range(10)) // tiles)
+        print("issuer issue/tile:", {n.replace('E', 'S'): int(out[30 + i]) // tiles for i, n in enumerate(names)}, "sum", sum(int(out[30 + i]) for i in range(10)) // tiles, "xfull wait", int(out[40]) // tiles)
