@@ -445,22 +445,24 @@ def main():
 
     def td3_config4():
         """TD3 synthetic Hopper-shaped replay (obs 11, act 3), minibatch 256, 256-256 nets, 50 train steps per call."""
-        from rl_replicas_b200.experience import Experience
         rng = np.random.default_rng(2)
         H = 256
         mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
                          for i, o in zip(sz[:-1], sz[1:])]
         PSz, QSz = [11, H, H, 3], [14, H, H, 1]
         algo, rb = synthetic.offpolicy_learner(True, mk(PSz), [mk(QSz), mk(QSz)])
-        n_rb = 100000  # sampling cost does not depend on the buffer size; 1 M Python-list entries only cost host RAM/time
-        ex = Experience()
+        n_rb = 1_000_000  # BASELINE config 4: a full 1 M-transition replay, device-resident (108 MB of HBM)
+        from rl_replicas_b200.experience import PackedExperience
         obs_rb = rng.standard_normal((n_rb + 1, 11)).astype(np.float32)
-        ex.observations = [[obs_rb[i] for i in range(n_rb)]]
-        ex.actions = [[a for a in rng.uniform(-1, 1, (n_rb, 3)).astype(np.float32)]]
-        ex.rewards = [[float(x) for x in rng.standard_normal(n_rb)]]
-        ex.dones = [[bool(x) for x in (rng.random(n_rb) < 0.001)]]
-        ex.last_observations = [obs_rb[n_rb]]
-        rb.add_experience(ex)
+        store = PackedExperience(n_rb, 11, 3)
+        L = 1000
+        for ep in range(n_rb // L):
+            a = ep * L
+            d = np.zeros(L, dtype=bool)
+            d[-1] = True
+            store.append_episode(obs_rb[a:a + L], rng.uniform(-1, 1, (L, 3)).astype(np.float32), rng.standard_normal(L), d,
+                                 obs_rb[a + L])
+        rb.add_experience(store)
         S4, B4 = 50, 256
         algo.train(rb, S4, B4)
         t0 = time.perf_counter()
@@ -483,7 +485,7 @@ def main():
             eng.train(*args4)
         ms_dev = (time.perf_counter() - t0) * 1e3 / reps
         return {"workload": "TD3 synthetic Hopper-shaped (obs 11, act 3), minibatch 256, MLP(256,256), 50 train steps/call, "
-                            "replay 100k transitions",
+                            "replay 1 M transitions (device-resident columns)",
                 "ms_per_train_call_e2e": ms_call, "train_steps_per_s_e2e": S4 / (ms_call * 1e-3),
                 "transitions_per_s_e2e": S4 * B4 / (ms_call * 1e-3),
                 "ms_per_train_call_engine": ms_dev, "train_steps_per_s_engine": S4 / (ms_dev * 1e-3),

@@ -341,6 +341,14 @@ int b200rl_offpolicy_set_adam(b200rl_offpolicy* h, int which, const float* exp_a
                               int64_t step, void* stream);
 int b200rl_offpolicy_get_adam(b200rl_offpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
                               int64_t* step, void* stream);
+/* The whole learner state in one call and one synchronisation (what TD3.train / DDPG.train move per call): blob = the
+ * parameters of every present network 0..5 in order, then exp_avg and exp_avg_sq of optimizers 0..2; steps[3] = the
+ * Adam step counts.  b200rl_offpolicy_state_floats = length of the blob. */
+int64_t b200rl_offpolicy_state_floats(b200rl_offpolicy* h);
+int b200rl_offpolicy_get_state(b200rl_offpolicy* h, float* blob, int64_t n_floats, int64_t* steps, void* stream);
+int b200rl_offpolicy_set_state(b200rl_offpolicy* h, const float* blob, int64_t n_floats, const int64_t* steps,
+                               void* stream);
+
 /* HOST buffers: obs/next_obs [S,B,O], act [S,B,A], rew/done [S,B] float32 (done as 0/1), noise [S,B,A] raw N(0,1)
  * draws (NULL for DDPG).  Outputs (host): q1_values/q2_values [S,B] (the logged pre-update Q-values), q1_losses /
  * q2_losses [S], policy_losses [*n_policy_updates].  One upload, S steps without host synchronisation, one read-back. */

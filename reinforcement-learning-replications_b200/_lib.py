@@ -138,6 +138,9 @@ SIGNATURES = {
     "b200rl_offpolicy_set_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "b200rl_offpolicy_get_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                             C.POINTER(C.c_int64), C.c_void_p]),
+    "b200rl_offpolicy_state_floats": (C.c_int64, [C.c_void_p]),
+    "b200rl_offpolicy_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "b200rl_offpolicy_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "b200rl_offpolicy_train": (C.c_int, [C.c_void_p, C.POINTER(OffPolicyHparams), C.c_int32, C.c_int32] +
                                [C.c_void_p] * 11 + [C.POINTER(C.c_int32), C.c_void_p]),
     "b200rl_offpolicy_train_gather": (C.c_int, [C.c_void_p, C.POINTER(OffPolicyHparams), C.c_int32, C.c_int32] +

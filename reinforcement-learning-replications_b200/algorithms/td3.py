@@ -63,6 +63,65 @@ class _OffPolicyBase:
             self._engine = e
         return e
 
+    # The host modules stay the reference point between train() calls (the sampler acts with self.policy on the CPU, a
+    # user may edit or load weights), so every call moves the whole learner state down and up again -- as ONE blob per
+    # direction with one synchronisation each (24 separate synchronous copies per call before: the transfers cost more
+    # than the 50 train steps between them).
+    def _tensor_slots(self, e, trainable, targets, lins):
+        """[(host tensor or (optimizer, param, key), offset, count)] in the engine's blob order."""
+        layout, total = e.state_layout()
+        mods = {i: (m, l) for i, (m, l) in enumerate(zip(trainable, lins))}
+        mods.update({3 + i: (m, l) for i, (m, l) in enumerate(zip(targets, lins[len(trainable):]))})
+        slots = []
+        for kind, i, off, count in layout:
+            m, l = mods[i]
+            o = off
+            for lin in l:
+                for p_ in (lin.weight, lin.bias):
+                    slots.append((kind, p_, m, o, p_.numel()))
+                    o += p_.numel()
+            assert o == off + count
+        return slots, total
+
+    def _upload_state(self, e, trainable, targets, lins) -> None:
+        slots, total = self._tensor_slots(e, trainable, targets, lins)
+        blob = torch.zeros(total, dtype=torch.float32)
+        steps = [0, 0, 0]
+        with torch.no_grad():
+            for kind, p_, m, off, n in slots:
+                if kind == "params":
+                    blob[off:off + n] = p_.detach().reshape(-1)
+                else:
+                    st = m.optimizer.state.get(p_)
+                    if st and "exp_avg" in st:
+                        blob[off:off + n] = st["exp_avg" if kind == "m" else "exp_avg_sq"].reshape(-1)
+        for i, (m, l) in enumerate(zip(trainable, lins)):
+            adam_hparams(m.optimizer, l, "optimizer")  # refuses anything but a plain Adam over exactly this network
+            _, _, steps[i] = read_adam_state(m.optimizer, l)
+        e.set_state(blob.numpy(), steps)
+
+    def _download_state(self, e, trainable, targets, lins) -> None:
+        slots, _ = self._tensor_slots(e, trainable, targets, lins)
+        blob, steps = e.get_state()
+        src = torch.from_numpy(blob)
+        index = {id(m): i for i, m in enumerate(trainable)}
+        with torch.no_grad():
+            for kind, p_, m, off, n in slots:
+                view = src[off:off + n].view_as(p_)
+                if kind == "params":
+                    p_.copy_(view)
+                    continue
+                step = steps[index[id(m)]]
+                if step == 0:
+                    continue
+                st = m.optimizer.state[p_]
+                key = "exp_avg" if kind == "m" else "exp_avg_sq"
+                if key in st and st[key].shape == p_.shape:
+                    st[key].copy_(view)
+                else:
+                    st[key] = view.clone()
+                st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
+
     def _hparams(self, noisy: bool, delay: int) -> OffPolicyHparams:
         trainable, _ = self._nets()
         lin = lambda m: describe_mlp(m.network)[3]
@@ -112,11 +171,7 @@ class _OffPolicyBase:
             done = stack("dones", np.float32)                       # bool -> .int() (td3.py:228), used as (1 - d)
         e = self._ensure_engine(max(S, 1), B)
         lins = [describe_mlp(m.network)[3] for m in trainable + targets]
-        for i, (m, l) in enumerate(zip(trainable, lins)):
-            e.set_params(i, flat_params(l))
-            e.set_adam(i, *read_adam_state(m.optimizer, l))
-        for i, l in enumerate(lins[len(trainable):]):
-            e.set_params(3 + i, flat_params(l))
+        self._upload_state(e, trainable, targets, lins)
         if S == 0:
             out = None
         elif device_replay:
@@ -124,11 +179,7 @@ class _OffPolicyBase:
             out = e.train_gather(self._hparams(noisy, delay), columns, rows, idx, noise)
         else:
             out = e.train(self._hparams(noisy, delay), obs, act, rew, nobs, done, noise)
-        for i, (m, l) in enumerate(zip(trainable, lins)):
-            write_flat(l, e.get_params(i))
-            write_adam_state(m.optimizer, l, *e.get_adam(i))
-        for i, l in enumerate(lins[len(trainable):]):
-            write_flat(l, e.get_params(3 + i))
+        self._download_state(e, trainable, targets, lins)
         self.last_train_output = out
         return out
 

@@ -937,12 +937,21 @@ extern "C" int b200rl_ipc_open(const void* handle64, void** ptr) {
   B200RL_REQUIRE(handle64 && ptr, "ipc_open: NULL argument");
   cudaIpcMemHandle_t hd;
   memcpy(&hd, handle64, 64);
-  B200RL_CUDA(cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  const cudaError_t e = cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();  // the caller falls back to the collective path: do not leave the error for a later launch check
+    set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
   return 0;
 }
 
 extern "C" int b200rl_ipc_close(void* ptr) {
-  if (ptr) B200RL_CUDA(cudaIpcCloseMemHandle(ptr));
+  if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cudaIpcCloseMemHandle failed");
+    return 1;
+  }
   return 0;
 }
 

@@ -463,6 +463,65 @@ extern "C" int b200rl_offpolicy_get_adam(b200rl_offpolicy* h, int which, float* 
   return 0;
 }
 
+// Whole learner state in ONE call and ONE synchronisation: blob = for every present network 0..5 its parameters, then
+// for every optimizer 0..2 (policy, Q1, Q2) exp_avg and exp_avg_sq; steps[3] = Adam step counts.
+static int64_t state_floats(const b200rl_offpolicy* h) {
+  int64_t n = 0;
+  for (int i = 0; i < 6; ++i)
+    if (h->net[i].params) n += h->net[i].P;
+  for (int i = 0; i < 3; ++i)
+    if (h->net[i].m) n += 2 * h->net[i].P;
+  return n;
+}
+
+extern "C" int64_t b200rl_offpolicy_state_floats(b200rl_offpolicy* h) { return h ? state_floats(h) : -1; }
+
+extern "C" int b200rl_offpolicy_get_state(b200rl_offpolicy* h, float* blob, int64_t n_floats, int64_t* steps,
+                                          void* stream) {
+  B200RL_REQUIRE(h && blob && steps && n_floats == state_floats(h), "offpolicy_get_state: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* q = blob;
+  for (int i = 0; i < 6; ++i)
+    if (h->net[i].params) {
+      B200RL_CUDA(cudaMemcpyAsync(q, h->net[i].params, (size_t)h->net[i].P * 4, cudaMemcpyDeviceToHost, s));
+      q += h->net[i].P;
+    }
+  for (int i = 0; i < 3; ++i) {
+    steps[i] = h->net[i].m ? h->net[i].step : 0;
+    if (h->net[i].m) {
+      B200RL_CUDA(cudaMemcpyAsync(q, h->net[i].m, (size_t)h->net[i].P * 4, cudaMemcpyDeviceToHost, s));
+      q += h->net[i].P;
+      B200RL_CUDA(cudaMemcpyAsync(q, h->net[i].v, (size_t)h->net[i].P * 4, cudaMemcpyDeviceToHost, s));
+      q += h->net[i].P;
+    }
+  }
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int b200rl_offpolicy_set_state(b200rl_offpolicy* h, const float* blob, int64_t n_floats, const int64_t* steps,
+                                          void* stream) {
+  B200RL_REQUIRE(h && blob && steps && n_floats == state_floats(h), "offpolicy_set_state: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float* q = blob;
+  for (int i = 0; i < 6; ++i)
+    if (h->net[i].params) {
+      B200RL_CUDA(cudaMemcpyAsync(h->net[i].params, q, (size_t)h->net[i].P * 4, cudaMemcpyHostToDevice, s));
+      q += h->net[i].P;
+    }
+  for (int i = 0; i < 3; ++i)
+    if (h->net[i].m) {
+      B200RL_REQUIRE(steps[i] >= 0, "offpolicy_set_state: negative step count");
+      B200RL_CUDA(cudaMemcpyAsync(h->net[i].m, q, (size_t)h->net[i].P * 4, cudaMemcpyHostToDevice, s));
+      q += h->net[i].P;
+      B200RL_CUDA(cudaMemcpyAsync(h->net[i].v, q, (size_t)h->net[i].P * 4, cudaMemcpyHostToDevice, s));
+      q += h->net[i].P;
+      h->net[i].step = steps[i];
+    }
+  B200RL_CUDA(cudaStreamSynchronize(s));  // `blob` may be a temporary of the caller
+  return 0;
+}
+
 // Enqueue the S train steps on `s` (plain launches or under stream capture).  Everything that varies between calls
 // with the same (S, B, hyper-parameters) is read from device buffers: staged minibatches, Adam scalar tables.
 static int enqueue_steps(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int S, int B, cudaStream_t s,

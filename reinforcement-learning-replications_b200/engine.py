@@ -218,6 +218,11 @@ class OnPolicyEngine:
         dist.all_gather_object(gathered, (handle, ok), group=process_group)
         ptrs = []
         if all(g[1] for g in gathered):
+            # mappings of buffers that no longer exist on their rank (its engine was replaced) go first: a new
+            # allocation may land where the old one was, and that cannot be mapped twice
+            live = {hd for r, (hd, _) in enumerate(gathered) if r != rank}
+            for hd in [h_ for h_ in _OPENED_IPC if h_ not in live]:
+                self.lib.b200rl_ipc_close(C.c_void_p(_OPENED_IPC.pop(hd)))
             for r, (hd, _) in enumerate(gathered):
                 if r == rank:
                     ptrs.append(mine)
@@ -361,6 +366,33 @@ class OffPolicyEngine:
         check(self.lib.b200rl_offpolicy_get_adam(self.h, which, _ptr(m), _ptr(v), m.size, C.byref(step),
                                                  current_stream_handle()), "get_adam")
         return m, v, int(step.value)
+
+    # ---- whole state in one transfer ----
+    def state_layout(self):
+        """[(kind, net index, offset, count)] of the state blob: ("params", 0..5) then ("m" / "v", 0..2)."""
+        present = [0, 1] + ([2] if self.n_q == 2 else []) + [3, 4] + ([5] if self.n_q == 2 else [])
+        out, off = [], 0
+        for i in present:
+            out.append(("params", i, off, self._n(i)))
+            off += self._n(i)
+        for i in [0, 1] + ([2] if self.n_q == 2 else []):
+            for kind in ("m", "v"):
+                out.append((kind, i, off, self._n(i)))
+                off += self._n(i)
+        assert off == int(self.lib.b200rl_offpolicy_state_floats(self.h))
+        return out, off
+
+    def get_state(self):
+        _, n = self.state_layout()
+        blob = np.empty(n, dtype=np.float32)
+        steps = (C.c_int64 * 3)()
+        check(self.lib.b200rl_offpolicy_get_state(self.h, _ptr(blob), n, steps, current_stream_handle()), "get_state")
+        return blob, [int(x) for x in steps]
+
+    def set_state(self, blob: np.ndarray, steps):
+        blob = _c(blob, np.float32)
+        st = (C.c_int64 * 3)(*[int(x) for x in steps])
+        check(self.lib.b200rl_offpolicy_set_state(self.h, _ptr(blob), blob.size, st, current_stream_handle()), "set_state")
 
     def train(self, hp, obs, act, rew, next_obs, done, noise=None):
         """obs/next_obs [S,B,O], act [S,B,A], rew/done [S,B], noise [S,B,A] or None -> dict of logged quantities."""

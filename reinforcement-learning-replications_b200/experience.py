@@ -133,6 +133,18 @@ class PackedExperience(Experience):
         return dict(obs=self._obs[:n], act=act, rew=self._rew[:n], last_obs=np.stack(self._last).astype(np.float32),
                     ep_offsets=np.asarray(self._offsets, dtype=np.int64), ep_done=done)
 
+    def transition_columns(self):
+        """(observations [n,O], actions [n,A] or [n], rewards [n], next_observations [n,O], dones [n]) as arrays: what a
+        replay buffer appends (``flattened_*`` of the reference, experience.py:60-84) without building Python lists."""
+        n = self._offsets[-1]
+        obs = self._obs[:n]
+        nxt = np.empty_like(obs)
+        nxt[:-1] = obs[1:]
+        for k, end in enumerate(self._offsets[1:]):
+            nxt[end - 1] = self._last[k]  # the step that closes an episode is followed by its last observation
+        act = self._act[:n] if self._a >= 1 else self._act[:n, 0]
+        return obs, act, self._rew[:n], nxt, self._done[:n]
+
     # ---- the reference's nested-list API, as views ----
     def _episodes(self, column):
         return [list(column[b:e]) for b, e in zip(self._offsets[:-1], self._offsets[1:])]

@@ -57,8 +57,11 @@ class ReplayBuffer:
         return (self._head + logical) % self._capacity if self._capacity else logical
 
     def add_experience(self, experience: Experience) -> None:
-        new = (experience.flattened_observations, experience.flattened_actions, experience.flattened_rewards,
-               experience.flattened_next_observations, experience.flattened_dones)
+        if hasattr(experience, "transition_columns"):  # PackedExperience: contiguous columns, no per-row Python objects
+            new = experience.transition_columns()
+        else:
+            new = (experience.flattened_observations, experience.flattened_actions, experience.flattened_rewards,
+                   experience.flattened_next_observations, experience.flattened_dones)
         n = len(new[0])
         if n == 0:
             return

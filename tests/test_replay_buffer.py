@@ -80,3 +80,23 @@ def test_batched_index_draws_consume_the_numpy_stream_like_repeated_sample_minib
     for s in range(5):
         for k in ReplayBuffer.COLUMNS:
             np.testing.assert_array_equal(cols[k][s], a[s][k])
+
+
+def test_packed_experience_appends_by_columns_like_the_list_path():
+    """ReplayBuffer.add_experience takes PackedExperience.transition_columns() (slice copies) instead of walking the
+    flattened_* lists; both must leave the same transitions behind (ref: replay_buffer.py:30-49, experience.py:60-84)."""
+    from rl_replicas_b200.experience import Experience, PackedExperience
+    rng = np.random.default_rng(3)
+    pe = PackedExperience(50, 4, 2)
+    o = rng.standard_normal((51, 4)).astype(np.float32)
+    for a, b in ((0, 20), (20, 50)):
+        d = np.zeros(b - a, dtype=bool)
+        d[-1] = a == 0
+        pe.append_episode(o[a:b], rng.uniform(-1, 1, (b - a, 2)).astype(np.float32), rng.standard_normal(b - a), d, o[b])
+    r1, r2 = ReplayBuffer(), ReplayBuffer()
+    r1.add_experience(pe)
+    r2.add_experience(Experience(observations=pe.observations, actions=pe.actions, rewards=pe.rewards,
+                                 last_observations=pe.last_observations, dones=pe.dones))
+    for k in ReplayBuffer.COLUMNS:
+        np.testing.assert_array_equal(np.asarray(getattr(r1, k)), np.asarray(getattr(r2, k)))
+    np.testing.assert_array_equal(np.asarray(r1.next_observations)[19], o[20])  # episode end -> its last observation
