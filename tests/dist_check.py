@@ -1,8 +1,8 @@
 """Data-parallel parity check, run under torchrun on N GPUs (NCCL):
    torchrun --nproc-per-node N tests/dist_check.py
 Every rank builds the same global batch, trains on its contiguous block of episodes with distributed=True, and the
-result must match the numpy ORACLE on the whole batch at 1e-5 of max|ref| (north_star), and a single-GPU run of the
-same engine at 2e-5 (two results that are each within 1e-5 of the oracle): the sharded engine computes the same global
+result must match the numpy ORACLE on the whole batch at 1e-5 of max|ref| (north_star; see the note on PPO's clip
+mask below), and a single-GPU run of the same engine at 1e-5: the sharded engine computes the same global
 mean / std / KL and applies the same reduced gradient on every rank.  Both gradient-exchange
 paths are exercised: the one-shot exchange over peer-mapped memory (default) and the NCCL all-reduce per iteration
 (B200RL_PEER_EXCHANGE=0)."""
@@ -36,11 +36,18 @@ def main():
     hp = dict(num_policy_gradients=6, num_value_gradients=6)
     ok = True
     oracle = {}
-    # (max_kl, peer exchange): the 0.002 setting triggers the device-side early stop on every rank
-    for max_kl, peer in ((float("inf"), "1"), (0.002, "1"), (float("inf"), "0"), (0.002, "0")):
+    # (max_kl, clip range, peer exchange).  max_kl = 0.002 triggers the device-side early stop on every rank.
+    # clip = 1e9 never clips: the surrogate is smooth in the parameters and six steps must agree with the oracle at 1e-5.
+    # With the default clip = 0.2 a sample whose ratio sits at 1 +- 0.2 flips its mask on a one-ulp difference in the
+    # parameters (it does so between any two float32 implementations, the reference's CPU arithmetic included), so
+    # that configuration is held to 1e-5 against the SAME engine on one GPU (identical arithmetic, different
+    # reduction tree) and to 1e-4 against the oracle.
+    cases = [(float("inf"), 1e9, "1"), (float("inf"), 0.2, "1"), (0.002, 0.2, "1"),
+             (float("inf"), 1e9, "0"), (float("inf"), 0.2, "0"), (0.002, 0.2, "0")]
+    for max_kl, clip, peer in cases:
         os.environ["B200RL_PEER_EXCHANGE"] = peer
         dp = build(ps, vs, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std, distributed=True,
-                   max_kl_divergence=max_kl, **hp)
+                   max_kl_divergence=max_kl, clip_range=clip, **hp)
         dp.train_packed(synthetic.shard_batch(full, rank, world))
         path = "peer-memory exchange" if dp._engine.peer_exchange else "NCCL all-reduce"
         p_dp, v_dp = flat(dp.policy.network).copy(), flat(dp.value_function.network).copy()
@@ -53,32 +60,34 @@ def main():
         same = bool(torch.equal(lo, hi))
         if rank == 0:
             ref = build(ps, vs, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std,
-                        max_kl_divergence=max_kl, **hp)
+                        max_kl_divergence=max_kl, clip_range=clip, **hp)
             ref.train_packed(full)
             rs = ref.last_update_stats
             ep = np.abs(p_dp - flat(ref.policy.network)).max() / np.abs(flat(ref.policy.network)).max()
             ev = np.abs(v_dp - flat(ref.value_function.network)).max() / np.abs(flat(ref.value_function.network)).max()
-            if max_kl not in oracle:
+            key = (max_kl, clip)
+            if key not in oracle:
                 # gradient sums in float64: a float32 BLAS sum has noise of its own that Adam's g / (|g| + eps)
                 # amplifies for near-zero entries (it depends on the host's BLAS kernels, not on the GPU result)
-                oracle[max_kl] = O.ppo_train(full, pl, vl, "gaussian", log_std, O.AdamState(5702, 3e-4),
-                                             O.AdamState(5377, 1e-3), max_kl=max_kl, n_policy=6, n_value=6,
-                                             acc=np.float64)
-            o = oracle[max_kl]
-            if (max_kl, 32) not in oracle:  # for the record: the same oracle with float32 gradient sums
-                oracle[(max_kl, 32)] = O.ppo_train(full, pl, vl, "gaussian", log_std, O.AdamState(5702, 3e-4),
-                                                   O.AdamState(5377, 1e-3), max_kl=max_kl, n_policy=6, n_value=6)
-            o32 = oracle[(max_kl, 32)]
+                oracle[key] = O.ppo_train(full, pl, vl, "gaussian", log_std, O.AdamState(5702, 3e-4),
+                                          O.AdamState(5377, 1e-3), max_kl=max_kl, clip=clip, n_policy=6, n_value=6,
+                                          acc=np.float64)
+            o = oracle[key]
+            if key + (32,) not in oracle:  # for the record: the same oracle with float32 gradient sums
+                oracle[key + (32,)] = O.ppo_train(full, pl, vl, "gaussian", log_std, O.AdamState(5702, 3e-4),
+                                                  O.AdamState(5377, 1e-3), max_kl=max_kl, clip=clip, n_policy=6, n_value=6)
+            o32 = oracle[key + (32,)]
             e32 = np.abs(p_dp - o32["policy_flat"]).max() / np.abs(o32["policy_flat"]).max()
             eop = np.abs(p_dp - o["policy_flat"]).max() / np.abs(o["policy_flat"]).max()
             eov = np.abs(v_dp - o["value_flat"]).max() / np.abs(o["value_flat"]).max()
-            good = (same and ep < 2e-5 and ev < 2e-5 and eop < 1e-5 and eov < 1e-5
+            bar_policy = 1e-5 if (clip > 1e6 or o["policy_steps"] <= 3) else 1e-4
+            good = (same and ep < 1e-5 and ev < 1e-5 and eop < bar_policy and eov < 1e-5
                     and st.policy_steps_applied == rs.policy_steps_applied == o["policy_steps"]
                     and dp._engine.peer_exchange == (peer == "1")
                     and abs(st.kl_divergence - rs.kl_divergence) < 1e-4 * abs(rs.kl_divergence) + 1e-8
                     and abs(st.value_loss_mean - rs.value_loss_mean) < 1e-5 * rs.value_loss_mean
                     and abs(st.adv_std - rs.adv_std) < 1e-9 * rs.adv_std)
-            print(f"max_kl={max_kl} [{path}]: world={world} ranks_identical={same} vs oracle: policy {eop:.2e} (float32-sum oracle {e32:.2e}) value {eov:.2e}; "
+            print(f"max_kl={max_kl} clip={clip:g} [{path}]: world={world} ranks_identical={same} vs oracle: policy {eop:.2e} (float32-sum oracle {e32:.2e}) value {eov:.2e}; "
                   f"vs 1-GPU run: policy_err={ep:.2e} value_err={ev:.2e} "
                   f"steps {st.policy_steps_applied}/{rs.policy_steps_applied} kl {st.kl_divergence:.6g}/{rs.kl_divergence:.6g} "
                   f"vloss {st.value_loss_mean:.6g}/{rs.value_loss_mean:.6g} -> {'OK' if good else 'FAIL'}")
