@@ -61,7 +61,8 @@ int64_t b200rl_launch_count(void);
 int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp);
 /* CTAs the fused MLP kernels use for n_rows rows on the current device (= rows of `partials`); -1 on error.
  * with_backward: 0 forward only, 1 forward + backward, 2 Fisher-vector product, 3 forward only on the fp32 kernel
- * (launches that set out_full / old_out / B200RL_FLAG_NO_TC). */
+ * (launches that set out_full / old_out / B200RL_FLAG_NO_TC), 4 forward + backward on the fp32 kernel
+ * (B200RL_FLAG_NO_TC or train_log_std). */
 int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -121,6 +122,9 @@ typedef struct {
   const float* obs_absmax; /* optional device array [sizes[0]]: per-feature max |obs| over the batch (scales of the fp16
                               tensor-core kernel; NULL = a pre-pass computes it on every launch, b200rl_absmax_cols) */
   const float* target_absmax; /* optional device scalar: max |target| (MSE backward); NULL = pre-pass */
+  int32_t train_log_std;   /* Gaussian policy losses with a backward pass: also emit dLoss/dlog_std -- partial rows then
+                              have P + sizes[L] columns (the gradient of log_std in the last sizes[L]).  Runs on the fp32
+                              kernel.  policies/gaussian_policy.py:25-37 with log_std inside the optimizer */
 } b200rl_mlp_loss_grad_args;
 
 int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* args, void* stream);
@@ -210,6 +214,11 @@ int b200rl_onpolicy_set_adam(b200rl_onpolicy* h, int which, const float* exp_avg
 int b200rl_onpolicy_get_adam(b200rl_onpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
                              int64_t* step, void* stream);
 int b200rl_onpolicy_set_log_std(b200rl_onpolicy* h, const float* host_log_std, int64_t n, void* stream);
+/* Trainable log_std (policies/gaussian_policy.py:25-37 when the user put log_std into the policy optimizer, after the
+ * network's parameters): from then on the policy vectors of set / get_params (which 0 and 1) and set / get_adam (which 0)
+ * are [network parameters | log_std], the PPO / VPG policy steps differentiate through it (on the fp32 kernel) and
+ * Adam updates it; b200rl_onpolicy_set_log_std is then unused.  TRPO refuses it. */
+int b200rl_onpolicy_set_train_log_std(b200rl_onpolicy* h, int32_t on);
 
 /* Packed trajectory batch.  src_on_device = 0: HOST buffers (pinned or pageable), copied
  * with cudaMemcpyAsync; 1: device buffers (device-to-device copy). */

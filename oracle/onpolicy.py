@@ -301,6 +301,12 @@ def policy_loss_and_grad(layers: Layers, dist_kind: str, log_std, obs, act, adv,
     }
     if old_logp is not None:
         res["kl"] = float(np.sum((old_logp - logp).astype(np.float64)) / n)
+    if dist_kind == "gaussian":
+        # d logp / d log_std_a = (act_a - mu_a)^2 / var_a - 1  (torch Normal.log_prob with scale = exp(log_std),
+        # ref policies/gaussian_policy.py:34): the gradient autograd hands to a log_std that sits in the optimizer
+        var = np.exp(F32(2) * np.asarray(log_std, dtype=F32))
+        z2 = ((act - out) ** 2 / var).astype(F32)
+        res["grad_log_std"] = (coef[:, None] * (z2 - F32(1))).sum(axis=0, dtype=acc).astype(F32)
     return res
 
 
@@ -322,7 +328,9 @@ def value_loss_and_grad(layers: Layers, obs, ret, hidden_act: str = "tanh", n_gl
 def ppo_train(batch: Dict[str, np.ndarray], policy: Layers, value: Layers, dist_kind: str, log_std,
               policy_adam: AdamState, value_adam: AdamState, gamma=0.99, lam=0.97, clip=0.2, max_kl=0.01,
               n_policy=80, n_value=80, old_policy: Layers | None = None, hidden_act: str = "tanh",
-              trace: bool = False, acc=F32) -> Dict[str, object]:
+              trace: bool = False, acc=F32, train_log_std: bool = False) -> Dict[str, object]:
+    """``train_log_std``: log_std sits behind the network's parameters in the policy optimizer (``policy_adam`` then has
+    P + A entries) and is trained by the policy steps; the old policy keeps its own (initial) log_std."""
     obs, act = batch["obs"], batch["act"]
     sizes_p, sizes_v = layer_sizes(policy), layer_sizes(value)
     old_policy = policy if old_policy is None else old_policy
@@ -339,28 +347,39 @@ def ppo_train(batch: Dict[str, np.ndarray], policy: Layers, value: Layers, dist_
     out: Dict[str, object] = {"values": values, "last_values": last_values, "adv_raw": adv_raw, "ret": ret,
                               "adv": adv, "old_logp": old_logp}
     flat_p = flatten_layers(policy)
+    n_net = flat_p.size
+    log_std_cur = None if log_std is None else np.asarray(log_std, dtype=F32).copy()
+    if train_log_std:
+        flat_p = np.concatenate([flat_p, log_std_cur])
     kl_trace, policy_params_trace = [], []
     kl = 0.0
     steps_done = 0
     for i in range(n_policy):  # ppo.py:173-181
-        r = policy_loss_and_grad(unflatten_layers(flat_p, sizes_p), dist_kind, log_std, obs, act, adv, old_logp,
+        r = policy_loss_and_grad(unflatten_layers(flat_p[:n_net], sizes_p), dist_kind, log_std_cur, obs, act, adv, old_logp,
                                  "ppo", clip, hidden_act, acc=acc)
+        if train_log_std:
+            r["grad"] = np.concatenate([r["grad"], r["grad_log_std"]])
         if i == 0:  # ppo.py:164-170 (logging before the first update)
             out["loss_before"] = r["loss"]
             out["entropy_before"] = float(np.mean(r["entropy"], dtype=np.float64))
             out["logp_std_before"] = float(np.std(r["logp"].astype(np.float64), ddof=1))
             out["grad0"] = r["grad"]
         flat_p = policy_adam.apply(flat_p, r["grad"])
+        if train_log_std:
+            log_std_cur = flat_p[n_net:].copy()
         steps_done += 1
         if trace:
             policy_params_trace.append(flat_p.copy())
         # ppo.py:176-181 -- approx KL with the updated policy
-        logp_new = Dist(dist_kind, mlp_forward(unflatten_layers(flat_p, sizes_p), obs, hidden_act)[0], log_std).log_prob(act)
+        logp_new = Dist(dist_kind, mlp_forward(unflatten_layers(flat_p[:n_net], sizes_p), obs, hidden_act)[0],
+                        log_std_cur).log_prob(act)
         kl = float(np.sum((old_logp - logp_new).astype(np.float64)) / obs.shape[0])
         kl_trace.append(kl)
         if kl > 1.5 * max_kl:
             break
-    out.update(policy_flat=flat_p, kl=kl, kl_trace=np.asarray(kl_trace), policy_steps=steps_done)
+    out.update(policy_flat=flat_p[:n_net], kl=kl, kl_trace=np.asarray(kl_trace), policy_steps=steps_done)
+    if train_log_std:
+        out["log_std"] = log_std_cur
     if trace:
         out["policy_params_trace"] = np.stack(policy_params_trace)
 

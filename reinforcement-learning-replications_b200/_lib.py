@@ -41,7 +41,7 @@ class LossGradArgs(C.Structure):
                 ("old_logp", C.c_void_p), ("target", C.c_void_p), ("row_out", C.c_void_p), ("partials", C.c_void_p),
                 ("scalar_partials", C.c_void_p), ("skip_flag", C.c_void_p), ("out_full", C.c_void_p),
                 ("old_out", C.c_void_p), ("direction", C.c_void_p), ("flags", C.c_int32),
-                ("obs_absmax", C.c_void_p), ("target_absmax", C.c_void_p)]
+                ("obs_absmax", C.c_void_p), ("target_absmax", C.c_void_p), ("train_log_std", C.c_int32)]
 
 
 class OnPolicyConfig(C.Structure):
@@ -119,6 +119,7 @@ SIGNATURES = {
     "b200rl_onpolicy_set_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "b200rl_onpolicy_get_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                            C.POINTER(C.c_int64), C.c_void_p]),
+    "b200rl_onpolicy_set_train_log_std": (C.c_int, [C.c_void_p, C.c_int32]),
     "b200rl_onpolicy_set_log_std": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200rl_onpolicy_load_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),

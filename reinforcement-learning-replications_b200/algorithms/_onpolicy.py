@@ -68,25 +68,26 @@ def write_flat(linears: List[nn.Linear], flat: np.ndarray) -> None:
     assert o == src.numel()
 
 
-def adam_hparams(optimizer, linears: List[nn.Linear], what: str):
-    """(lr, beta1, beta2, eps) of a plain torch.optim.Adam over exactly this network's parameters, in order."""
+def adam_hparams(optimizer, linears: List[nn.Linear], what: str, extra=()):
+    """(lr, beta1, beta2, eps) of a plain torch.optim.Adam over exactly this network's parameters, in order (followed by
+    the tensors of ``extra``, e.g. a trainable log_std)."""
     if type(optimizer) is not torch.optim.Adam:
         raise NotImplementedError(f"{what}: the engine implements torch.optim.Adam, got {type(optimizer).__name__}")
     if len(optimizer.param_groups) != 1:
         raise NotImplementedError(f"{what}: exactly one param group is supported")
     g = optimizer.param_groups[0]
-    want = [t for l in linears for t in (l.weight, l.bias)]
+    want = [t for l in linears for t in (l.weight, l.bias)] + list(extra)
     if len(g["params"]) != len(want) or any(a is not b for a, b in zip(g["params"], want)):
         raise NotImplementedError(
             f"{what}: optimizer must hold exactly the network's parameters in order "
-            "(a trainable log_std inside the optimizer is not supported yet)")
+            "(for a Gaussian policy optionally followed by its log_std)")
     if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False):
         raise NotImplementedError(f"{what}: weight_decay / amsgrad / maximize are not supported")
     return float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"])
 
 
-def read_adam_state(optimizer, linears: List[nn.Linear]):
-    ps = [t for l in linears for t in (l.weight, l.bias)]
+def read_adam_state(optimizer, linears: List[nn.Linear], extra=()):
+    ps = [t for l in linears for t in (l.weight, l.bias)] + list(extra)
     if not all(p in optimizer.state and "exp_avg" in optimizer.state[p] for p in ps):
         return None, None, 0
     m = torch.cat([optimizer.state[p]["exp_avg"].reshape(-1).float() for p in ps]).numpy()
@@ -97,19 +98,18 @@ def read_adam_state(optimizer, linears: List[nn.Linear]):
     return m, v, steps.pop()
 
 
-def write_adam_state(optimizer, linears: List[nn.Linear], m: np.ndarray, v: np.ndarray, step: int) -> None:
+def write_adam_state(optimizer, linears: List[nn.Linear], m: np.ndarray, v: np.ndarray, step: int, extra=()) -> None:
     if step == 0:
         return
     mt, vt = torch.from_numpy(m), torch.from_numpy(v)
     o = 0
-    for l in linears:
-        for p in (l.weight, l.bias):
-            n = p.numel()
-            st = optimizer.state[p]
-            st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
-            st["exp_avg"] = mt[o:o + n].view_as(p).clone()
-            st["exp_avg_sq"] = vt[o:o + n].view_as(p).clone()
-            o += n
+    for p in [t for l in linears for t in (l.weight, l.bias)] + list(extra):
+        n = p.numel()
+        st = optimizer.state[p]
+        st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
+        st["exp_avg"] = mt[o:o + n].view_as(p).clone()
+        st["exp_avg_sq"] = vt[o:o + n].view_as(p).clone()
+        o += n
 
 
 class OnPolicyTrainerMixin:
@@ -134,38 +134,57 @@ class OnPolicyTrainerMixin:
             raise NotImplementedError(f"unsupported policy type {type(self.policy).__name__}")
         return psizes, vsizes, dist, pact
 
+    def _trainable_log_std(self):
+        """``[policy.log_std]`` when the user put it into the policy optimizer behind the network's parameters (then it
+        is trained like in the reference, ref policies/gaussian_policy.py:25-37 + torch autograd), else ``[]``."""
+        if not isinstance(self.policy, GaussianPolicy) or type(self.policy.optimizer) is not torch.optim.Adam:
+            return []
+        params = [p for g in self.policy.optimizer.param_groups for p in g["params"]]
+        return [self.policy.log_std] if any(p is self.policy.log_std for p in params) else []
+
     def _ensure_engine(self, n_rows: int, n_episodes: int) -> OnPolicyEngine:
         psizes, vsizes, dist, act = self._describe()
+        train_ls = bool(self._trainable_log_std())
         e = self._engine
         if (e is None or e.policy_sizes != psizes or e.value_sizes != vsizes or e.dist != dist
-                or e.max_rows < n_rows or e.max_episodes < n_episodes):
+                or e.train_log_std != train_ls or e.max_rows < n_rows or e.max_episodes < n_episodes):
             if e is not None:
                 e.close()
             cap_rows = max(n_rows, int(1.25 * n_rows) if e is not None else n_rows)
             cap_eps = max(n_episodes, 2 * n_episodes if e is not None else n_episodes)
-            e = OnPolicyEngine(psizes, vsizes, dist, cap_rows, cap_eps, hidden_act=act, rewards_f64=True)
+            e = OnPolicyEngine(psizes, vsizes, dist, cap_rows, cap_eps, hidden_act=act, rewards_f64=True,
+                               train_log_std=train_ls)
             self._engine = e
         return e
 
     def _push_state(self, e: OnPolicyEngine, with_old: bool) -> None:
-        e.set_params(POLICY, flat_params(self._plin))
+        ls = self._trainable_log_std()
+        tail = lambda policy: ([policy.log_std.detach().float().reshape(-1).numpy()] if ls else [])
+        e.set_params(POLICY, np.concatenate([flat_params(self._plin)] + tail(self.policy)))
         if with_old:
-            e.set_params(OLD_POLICY, flat_params(describe_mlp(self.old_policy.network)[3]))
+            old_lin = describe_mlp(self.old_policy.network)[3]
+            e.set_params(OLD_POLICY, np.concatenate([flat_params(old_lin)] + tail(self.old_policy)))
         e.set_params(VALUE, flat_params(self._vlin))
-        if e.dist == "gaussian":
+        if e.dist == "gaussian" and not ls:
             e.set_log_std(self.policy.log_std.detach().float().numpy())
         if type(self.policy.optimizer) is torch.optim.Adam:
-            e.set_adam(POLICY, *read_adam_state(self.policy.optimizer, self._plin))
+            e.set_adam(POLICY, *read_adam_state(self.policy.optimizer, self._plin, ls))
         e.set_adam(VALUE, *read_adam_state(self.value_function.optimizer, self._vlin))
 
     def _pull_state(self, e: OnPolicyEngine, with_old: bool, policy_adam: bool = True) -> None:
-        write_flat(self._plin, e.get_params(POLICY))
+        ls = self._trainable_log_std()
+        flat = e.get_params(POLICY)
+        n_net = flat.size - (ls[0].numel() if ls else 0)
+        write_flat(self._plin, flat[:n_net])
+        if ls:
+            with torch.no_grad():
+                ls[0].copy_(torch.from_numpy(flat[n_net:].copy()).view_as(ls[0]))
         write_flat(self._vlin, e.get_params(VALUE))
         if with_old:
-            # ref ppo.py:183: old_policy.load_state_dict(policy.state_dict())
+            # ref ppo.py:183: old_policy.load_state_dict(policy.state_dict())  (log_std is part of the state dict)
             self.old_policy.load_state_dict(self.policy.state_dict())
         if policy_adam:
-            write_adam_state(self.policy.optimizer, self._plin, *e.get_adam(POLICY))
+            write_adam_state(self.policy.optimizer, self._plin, *e.get_adam(POLICY), extra=ls)
         write_adam_state(self.value_function.optimizer, self._vlin, *e.get_adam(VALUE))
 
     def _global_rows(self, n_rows: int) -> int:

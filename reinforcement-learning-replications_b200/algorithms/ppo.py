@@ -80,7 +80,7 @@ class PPO(OnPolicyTrainerMixin):
             gamma=self.gamma, gae_lambda=self.gae_lambda, clip_range=self.clip_range,
             max_kl_divergence=self.max_kl_divergence, num_policy_gradients=self.num_policy_gradients,
             num_value_gradients=self.num_value_gradients,
-            policy_adam=adam_hparams(self.policy.optimizer, self._plin, "policy optimizer"),
+            policy_adam=adam_hparams(self.policy.optimizer, self._plin, "policy optimizer", self._trainable_log_std()),
             value_adam=adam_hparams(self.value_function.optimizer, self._vlin, "value-function optimizer"),
             n_global_rows=n_global)
 

@@ -35,7 +35,9 @@ class TRPO(PPO):
         want = [t for l in self._plin for t in (l.weight, l.bias)]
         have = [p for g in opt.param_groups for p in g["params"]]
         if len(have) != len(want) or any(a is not b for a, b in zip(have, want)):
-            raise NotImplementedError("ConjugateGradientOptimizer must hold exactly the policy network's parameters")
+            raise NotImplementedError(
+                "ConjugateGradientOptimizer must hold exactly the policy network's parameters (the native constrained "
+                "step covers the network; a log_std inside the conjugate-gradient optimizer is not supported)")
         self._push_state(engine, with_old=True)
         engine.load_batch(batch)
         result = {}

@@ -94,6 +94,10 @@ struct b200rl_onpolicy {
   float* snap = nullptr;     // snapshot [3 Pp + 3 Pv + Pp]: restored when a fused update must be redone
   float* h_trip = nullptr;   // pinned
   int last_fused = 0;        // the last update ran on the fused path (diagnostics)
+  // trainable log_std (policies/gaussian_policy.py:25-37 with log_std inside the optimizer): the policy vector is then
+  // [network parameters | log_std] for set / get_params, Adam and the gradient; policy steps run on the fp32 kernel
+  int train_log_std = 0;
+  int n_ls = 0;              // entries appended to the policy vector (= action width when train_log_std)
   // one-shot gradient exchange over peer-mapped memory (data-parallel runs on one node)
   float* xchg = nullptr;     // this rank's exchange buffer: [2][xchg_stride] floats + 2 sequence words
   int64_t xchg_stride = 0;
@@ -150,7 +154,9 @@ int launch_fused(b200rl_onpolicy* h, const b200rl_mlp_desc& mlp, int loss, int d
   a.obs = obs;
   if (dist != B200RL_DIST_NONE) {
     a.actions = h->act;
-    a.log_std = h->log_std;
+    // trainable log_std lives behind the network parameters of the (old) policy vector
+    a.log_std = !h->train_log_std ? h->log_std : (params == h->old_pol ? h->old_pol + h->Pp : h->pol + h->Pp);
+    a.train_log_std = h->train_log_std && loss != B200RL_LOSS_EVAL && loss != B200RL_LOSS_MSE;
   }
   if (use_adv) {
     a.adv_raw = h->adv_raw;
@@ -212,17 +218,17 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
   rc |= dev_alloc(h, &h->adv_stats, 4);
   h->scan_ws_bytes = b200rl_gae_scan_workspace_bytes(cfg->max_rows);
   rc |= dev_alloc(h, reinterpret_cast<char**>(&h->scan_ws), h->scan_ws_bytes);
-  rc |= dev_alloc(h, &h->pol, (size_t)Pp);
-  rc |= dev_alloc(h, &h->old_pol, (size_t)Pp);
+  rc |= dev_alloc(h, &h->pol, (size_t)Pp + 16);
+  rc |= dev_alloc(h, &h->old_pol, (size_t)Pp + 16);
   rc |= dev_alloc(h, &h->val, (size_t)Pv);
   rc |= dev_alloc(h, &h->log_std, 16);
-  rc |= dev_alloc(h, &h->pol_m, (size_t)Pp);
-  rc |= dev_alloc(h, &h->pol_v, (size_t)Pp);
+  rc |= dev_alloc(h, &h->pol_m, (size_t)Pp + 16);
+  rc |= dev_alloc(h, &h->pol_v, (size_t)Pp + 16);
   rc |= dev_alloc(h, &h->val_m, (size_t)Pv);
   rc |= dev_alloc(h, &h->val_v, (size_t)Pv);
   h->fused_ok = tc3_shape_ok(cfg->policy, cfg->value);
   // mlp_tc2 emits two partial rows per CTA; the fused step's rows hold both networks' gradients side by side
-  rc |= dev_alloc(h, &h->partials, (size_t)2 * sms * (h->fused_ok ? (size_t)(Pp + Pv) : Pmax));
+  rc |= dev_alloc(h, &h->partials, (size_t)2 * sms * (h->fused_ok ? (size_t)(Pp + Pv) : Pmax + 16));
   rc |= dev_alloc(h, &h->scalar_partials, (size_t)2 * sms * 2 * B200RL_N_SCALARS);
   if (h->fused_ok) {
     rc |= dev_alloc(h, &h->ximg, tc3_ximg_bytes(cfg->max_rows));
@@ -233,7 +239,7 @@ extern "C" int b200rl_onpolicy_create(const b200rl_onpolicy_config* cfg, b200rl_
     if (!rc && cudaMallocHost(reinterpret_cast<void**>(&h->h_trip), 4 * sizeof(float)) != cudaSuccess) rc = 1;
   }
   rc |= dev_alloc(h, &h->absmax, 72);
-  rc |= dev_alloc(h, &h->pol_grad, (size_t)Pp + B200RL_N_SCALARS);
+  rc |= dev_alloc(h, &h->pol_grad, (size_t)Pp + 16 + B200RL_N_SCALARS);
   rc |= dev_alloc(h, &h->val_grad, (size_t)Pv + B200RL_N_SCALARS);
   rc |= dev_alloc(h, &h->flags, 8);
   if (!rc) rc |= ensure_slots(h, 256);
@@ -263,8 +269,8 @@ extern "C" void b200rl_onpolicy_destroy(b200rl_onpolicy* h) {
 
 static float* param_ptr(b200rl_onpolicy* h, int which, int64_t* n) {
   switch (which) {
-    case 0: *n = h->Pp; return h->pol;
-    case 1: *n = h->Pp; return h->old_pol;
+    case 0: *n = h->Pp + h->n_ls; return h->pol;
+    case 1: *n = h->Pp + h->n_ls; return h->old_pol;
     case 2: *n = h->Pv; return h->val;
     default: *n = 0; return nullptr;
   }
@@ -294,7 +300,7 @@ extern "C" int b200rl_onpolicy_get_params(b200rl_onpolicy* h, int which, float* 
 extern "C" int b200rl_onpolicy_set_adam(b200rl_onpolicy* h, int which, const float* exp_avg, const float* exp_avg_sq,
                                         int64_t n, int64_t step, void* stream) {
   B200RL_REQUIRE(h && (which == 0 || which == 2), "set_adam: which must be 0 (policy) or 2 (value)");
-  const int64_t cnt = which == 0 ? h->Pp : h->Pv;
+  const int64_t cnt = which == 0 ? h->Pp + h->n_ls : h->Pv;
   B200RL_REQUIRE(n == cnt && step >= 0, "set_adam: expects %lld floats, got %lld", (long long)cnt, (long long)n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* m = which == 0 ? h->pol_m : h->val_m;
@@ -310,13 +316,21 @@ extern "C" int b200rl_onpolicy_set_adam(b200rl_onpolicy* h, int which, const flo
 extern "C" int b200rl_onpolicy_get_adam(b200rl_onpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
                                         int64_t* step, void* stream) {
   B200RL_REQUIRE(h && (which == 0 || which == 2) && exp_avg && exp_avg_sq && step, "get_adam: bad arguments");
-  const int64_t cnt = which == 0 ? h->Pp : h->Pv;
+  const int64_t cnt = which == 0 ? h->Pp + h->n_ls : h->Pv;
   B200RL_REQUIRE(n == cnt, "get_adam: expects %lld floats, got %lld", (long long)cnt, (long long)n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   B200RL_CUDA(cudaMemcpyAsync(exp_avg, which == 0 ? h->pol_m : h->val_m, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaMemcpyAsync(exp_avg_sq, which == 0 ? h->pol_v : h->val_v, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   B200RL_CUDA(cudaStreamSynchronize(s));
   *step = which == 0 ? h->pol_step : h->val_step;
+  return 0;
+}
+
+extern "C" int b200rl_onpolicy_set_train_log_std(b200rl_onpolicy* h, int32_t on) {
+  B200RL_REQUIRE(h, "set_train_log_std: NULL handle");
+  B200RL_REQUIRE(!on || h->cfg.dist == B200RL_DIST_GAUSSIAN, "set_train_log_std: only Gaussian policies have a log_std");
+  h->train_log_std = on ? 1 : 0;
+  h->n_ls = on ? h->act_cols : 0;
   return 0;
 }
 
@@ -571,22 +585,24 @@ static int run_update_impl(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b20
     if (launch_pack_obs(h->obs, h->n_rows, h->obs_dim, h->absmax, h->ximg, h->xscale, h->trip, s)) return 1;
     if (run_fused_iterations(h, hp, ar, user, n_glob, K, K < Kv ? K : Kv, s, &i0)) return 1;
   }
+  const int64_t Pe = h->Pp + h->n_ls;  // policy vector incl. a trainable log_std
+  const int grid_pp = h->train_log_std ? b200rl_mlp_grid(&h->cfg.policy, h->n_rows, 4) : grid_p;
   for (int i = i0; i < K; ++i) {  // ppo.py:173-181 / vpg.py:194-207
     double* slot = h->slots + (size_t)i * B200RL_N_SCALARS;
     if (launch_fused(h, h->cfg.policy, policy_loss, dist, h->pol, h->obs, h->n_rows, n_glob, hp->clip_range, true,
                      ppo, nullptr, true, stop, s)) return 1;
-    if (b200rl_reduce_partials(h->partials, h->scalar_partials, grid_p, h->Pp, h->pol_grad, slot, ar ? 1 : 0, stop, s))
+    if (b200rl_reduce_partials(h->partials, h->scalar_partials, grid_pp, Pe, h->pol_grad, slot, ar ? 1 : 0, stop, s))
       return 1;
-    if (ar && ar(user, h->pol_grad, h->Pp + B200RL_N_SCALARS, 0, s)) {
+    if (ar && ar(user, h->pol_grad, Pe + B200RL_N_SCALARS, 0, s)) {
       set_error("allreduce callback failed (policy gradient)");
       return 1;
     }
     // KL carried by this forward pass = approx KL after the previous update (ppo.py:176-181), checked on device
-    const void* kl = !ppo ? nullptr : (ar ? static_cast<const void*>(h->pol_grad + h->Pp + 1)
+    const void* kl = !ppo ? nullptr : (ar ? static_cast<const void*>(h->pol_grad + Pe + 1)
                                           : static_cast<const void*>(slot + 1));
-    if (b200rl_adam_step(h->pol, h->pol_grad, h->pol_m, h->pol_v, h->Pp, h->pol_step + i + 1, hp->policy_lr,
+    if (b200rl_adam_step(h->pol, h->pol_grad, h->pol_m, h->pol_v, Pe, h->pol_step + i + 1, hp->policy_lr,
                          hp->policy_beta1, hp->policy_beta2, hp->policy_eps, kl, ar ? 1 : 0, (double)n_glob,
-                         1.5 * hp->max_kl_divergence, stop, h->flags + 1, ar ? h->pol_grad + h->Pp : nullptr,
+                         1.5 * hp->max_kl_divergence, stop, h->flags + 1, ar ? h->pol_grad + Pe : nullptr,
                          ar ? slot : nullptr, s))
       return 1;
   }
@@ -601,7 +617,7 @@ static int run_update_impl(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b20
       return 1;
     }
     // ppo.py:183: old_policy.load_state_dict(policy.state_dict())
-    B200RL_CUDA(cudaMemcpyAsync(h->old_pol, h->pol, (size_t)h->Pp * 4, cudaMemcpyDeviceToDevice, s));
+    B200RL_CUDA(cudaMemcpyAsync(h->old_pol, h->pol, (size_t)Pe * 4, cudaMemcpyDeviceToDevice, s));
   }
 
   if (run_value_loop(h, hp, ar, user, n_glob, K + 1, s, i0)) return 1;
@@ -677,7 +693,7 @@ static int run_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, b200rl_a
   B200RL_REQUIRE(h->n_rows > 0, "update: no batch loaded");
   B200RL_REQUIRE(hp->num_policy_gradients >= 0 && hp->num_value_gradients >= 0, "update: negative step count");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool fused = policy_loss == B200RL_LOSS_PPO_CLIP && h->fused_ok && fused_step_enabled() &&
+  const bool fused = policy_loss == B200RL_LOSS_PPO_CLIP && h->fused_ok && !h->train_log_std && fused_step_enabled() &&
                      tc2_path_enabled(h->cfg.policy) && tc2_path_enabled(h->cfg.value) &&
                      hp->num_policy_gradients > 0 && hp->num_value_gradients > 0;
   bool tripped = false;
@@ -757,6 +773,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
   B200RL_REQUIRE(h && hp && cg && stats && ts, "trpo_update: NULL argument");
   B200RL_REQUIRE(h->n_rows > 0, "trpo_update: no batch loaded");
   B200RL_REQUIRE(cg->n_conjugate_gradients >= 1 && cg->max_backtracks >= 1, "trpo_update: bad CG parameters");
+  B200RL_REQUIRE(!h->train_log_std, "trpo_update: a trainable log_std is not part of the conjugate-gradient step");
   if (ensure_trpo(h)) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t launches0 = launches_total();

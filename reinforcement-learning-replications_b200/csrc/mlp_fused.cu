@@ -143,6 +143,7 @@ struct FusedArgs {
   unsigned seq;
   int total_rows;          // partial rows the consumer reduces (> gridDim.x when standing in for a tensor-core launch)
   unsigned long long* rerun_counter;  // b200rl_tc_fallback_count's device counter
+  int train_log_std;       // Gaussian: partial rows carry dLoss/dlog_std in columns P .. P + A - 1 (row stride P + A)
 };
 
 unsigned long long* tc_fallback_counter_ptr();  // mlp_tc.cu
@@ -296,6 +297,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
   __syncthreads();
 
   double sc[7] = {0, 0, 0, 0, 0, 0, 0};  // loss terms, old_logp - logp, entropy, logp, logp^2, rows, KL(old||new)
+  float dls[16];  // this thread's share of dLoss/dlog_std (train_log_std)
+#pragma unroll
+  for (int a = 0; a < 16; ++a) dls[a] = 0.f;
   const long long num_tiles = (p.n_rows + TM - 1) / TM;
   const int n0 = Y.n[0], ld0 = Y.ld[0];
 
@@ -507,6 +511,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
               dzrm[a] = g;
               dzt[a * TM + r] = g;
             }
+            if (p.train_log_std) {
+              // d logp / d log_std_a = (act_a - mu_a)^2 / var_a - 1   (Normal.log_prob with scale = exp(log_std),
+              // gaussian_policy.py:34); the entropy does not enter the losses (ppo.py:245-255, vpg.py:203)
+              const float* act = p.actions + row * A_out;
+#pragma unroll
+              for (int a = 0; a < 16; ++a)
+                if (a < A_out) dls[a] += coef * ((__ldg(act + a) - out[a]) * dlp[a] - 1.f);
+            }
           }
           sc[0] += (double)term;
           if (p.old_logp != nullptr) sc[1] += (double)(oldlp - lp);
@@ -576,8 +588,26 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
 
   // ---- per-CTA results ----
   if (BACKWARD) {
-    float* dst = p.partials + (size_t)blockIdx.x * Y.P;
+    const int n_ls = p.train_log_std ? Y.n[Y.L] : 0;
+    float* dst = p.partials + (size_t)blockIdx.x * (Y.P + n_ls);
     for (int i = tid; i < Y.P; i += MLP_THREADS) dst[i] = smem[Y.s_dw + i];
+    if (n_ls > 0) {  // per-thread sums -> warp tree -> the warps in order: fixed order, reproducible
+      __shared__ float s_ls[MLP_THREADS / 32][16];
+      const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        float t = dls[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_ls[warp][a] = t;
+      }
+      __syncthreads();
+      if (tid < n_ls) {
+        float t = 0.f;
+        for (int w = 0; w < MLP_THREADS / 32; ++w) t += s_ls[w][tid];
+        dst[Y.P + tid] = t;
+      }
+    }
   }
   if (p.scalar_partials != nullptr) {
     __shared__ double s_sc[7][MLP_THREADS / 32];
@@ -647,14 +677,14 @@ extern "C" int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp) {
 // (launches that use out_full / old_out / B200RL_FLAG_NO_TC)
 extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward) {
   if (!mlp) return -1;
-  if (with_backward < 2 && use_tc(*mlp)) {
+  if (with_backward >= 0 && with_backward < 2 && use_tc(*mlp)) {
     if (!use_tc2()) return tc_grid(n_rows);
     const int g = tc2_grid(n_rows);
     return g > 0 ? 2 * g : -1;
   }
   if (with_backward == 2 && use_tc(*mlp) && use_tc2()) return tc_fvp_total_rows(*mlp, n_rows);
   MlpLayout lay;
-  if (build_layout(*mlp, with_backward == 1 || with_backward == 2, &lay, with_backward == 2)) return -1;
+  if (build_layout(*mlp, with_backward == 1 || with_backward == 2 || with_backward == 4, &lay, with_backward == 2)) return -1;
   return fused_grid(lay, n_rows);
 }
 
@@ -700,6 +730,7 @@ static int launch_fused(const b200rl_mlp_loss_grad_args* a, const unsigned* run_
   k.out_full = a->out_full;
   k.old_out = a->old_out;
   k.direction = a->direction;
+  k.train_log_std = (a->train_log_std != 0 && backward && a->dist == B200RL_DIST_GAUSSIAN) ? 1 : 0;
   const int grid = fused_grid(k.lay, a->n_rows);
   B200RL_REQUIRE(grid > 0, "mlp_loss_grad: no CUDA device");
   const int mode = fvp ? 2 : (backward ? 1 : 0);
@@ -755,7 +786,9 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
     const int rows = b200rl_mlp_grid(&a->mlp, 0, fvp ? 2 : (backward ? 1 : ((a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC)) ? 3 : 0)));
     B200RL_REQUIRE(rows > 0, "mlp_loss_grad: no CUDA device");
     if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
-    if (backward) B200RL_CUDA(cudaMemsetAsync(a->partials, 0, (size_t)rows * k.lay.P * sizeof(float), s));
+    if (backward)
+      B200RL_CUDA(cudaMemsetAsync(a->partials, 0,
+                                  (size_t)rows * (k.lay.P + (a->train_log_std ? k.lay.n[L] : 0)) * sizeof(float), s));
     if (a->scalar_partials)
       B200RL_CUDA(cudaMemsetAsync(a->scalar_partials, 0, (size_t)rows * B200RL_N_SCALARS * sizeof(double), s));
     return 0;
@@ -786,7 +819,7 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
     B200RL_REQUIRE(total > 0, "mlp_loss_grad: no CUDA device");
     return launch_mlp_tc_fvp(a, n_glob_all, total, s);
   }
-  const bool needs_fp32 = fvp || a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC);
+  const bool needs_fp32 = fvp || a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC) || a->train_log_std;
   if (!needs_fp32 && use_tc(a->mlp)) {
     const int64_t n_glob_tc = a->n_global > 0 ? a->n_global : a->n_rows;
     return use_tc2() ? launch_mlp_tc2(a, n_glob_tc, s) : launch_mlp_tc(a, n_glob_tc, s);

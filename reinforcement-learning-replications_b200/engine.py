@@ -44,7 +44,7 @@ class OnPolicyEngine:
     """Device-resident state of one PPO / VPG / TRPO learner."""
 
     def __init__(self, policy_sizes: Sequence[int], value_sizes: Sequence[int], dist: str, max_rows: int,
-                 max_episodes: int, hidden_act: str = "tanh", rewards_f64: bool = True):
+                 max_episodes: int, hidden_act: str = "tanh", rewards_f64: bool = True, train_log_std: bool = False):
         self.lib = _lib.load()
         current_stream_handle()  # fail early and loudly without a GPU
         cfg = OnPolicyConfig()
@@ -63,6 +63,10 @@ class OnPolicyEngine:
         h = C.c_void_p()
         check(self.lib.b200rl_onpolicy_create(C.byref(cfg), C.byref(h)), "onpolicy_create")
         self.h = h
+        self.train_log_std = bool(train_log_std)
+        if self.train_log_std:  # the policy vector becomes [network parameters | log_std]
+            check(self.lib.b200rl_onpolicy_set_train_log_std(h, 1), "set_train_log_std")
+            self.n_policy += int(policy_sizes[-1])
         self.n_rows = 0
         self.n_episodes = 0
         self._allreduce_cb = None

@@ -125,6 +125,37 @@ def sampled_actions_case(name, discrete):
     print(name, single.shape, single.dtype, batched.shape, "first", single[:5].tolist() if discrete else single[0])
 
 
+def trainable_log_std_case(name):
+    """PPO on a Gaussian policy whose log_std sits in the optimizer behind the network's parameters: the reference then
+    trains it (autograd through Normal(loc, exp(log_std)), policies/gaussian_policy.py:25-37)."""
+    set_seed_for_libraries(0)
+    obs_dim, act_dim = 17, 6
+    pnet, vnet = MLP([obs_dim, 64, 64, act_dim]), MLP([obs_dim, 64, 64, 1])
+    log_std = torch.nn.Parameter(-0.5 * torch.ones(act_dim))
+    policy = GaussianPolicy(pnet, torch.optim.Adam(list(pnet.parameters()) + [log_std], lr=3e-4), log_std)
+    vf = ValueFunction(vnet, torch.optim.Adam(vnet.parameters(), lr=1e-3))
+    with torch.no_grad():
+        batch = synthetic.fixed_batch(6, 200, obs_dim, act_dim, seed=12, frac_not_done=0.34,
+                                      mean_fn=lambda o: policy.network(torch.from_numpy(o)).numpy())
+    out = dict(batch)
+    out["policy_flat0"], out["value_flat0"] = G.flat(pnet), G.flat(vnet)
+    out["log_std0"] = log_std.detach().numpy().copy()
+    ppo = PPO(policy, vf, None, None, num_policy_gradients=6, num_value_gradients=3, max_kl_divergence=float("inf"))
+    ppo.metrics_manager = G.Recorder()
+    ppo.current_total_steps = 0
+    ppo.train(Experience(**synthetic.to_experience_lists(batch, False)))
+    out["policy_flat_final"], out["value_flat_final"] = G.flat(pnet), G.flat(vnet)
+    out["log_std_final"] = log_std.detach().numpy().copy()
+    out["old_log_std_final"] = ppo.old_policy.log_std.detach().numpy().copy()
+    st = policy.optimizer.state[log_std]
+    out["log_std_adam_m"], out["log_std_adam_v"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+    out["log_std_adam_step"] = float(st["step"])
+    for k, val in ppo.metrics_manager.scalars.items():
+        out["metric:" + k] = val
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "log_std", out["log_std0"][:3], "->", out["log_std_final"][:3], "kl", out["metric:policy/kl_divergence"])
+
+
 def utils_kats():
     out = {}
     rng = np.random.default_rng(3)
@@ -166,3 +197,4 @@ if __name__ == "__main__":
     sampled_actions_case("sampled_actions_categorical", True)
     sampled_actions_case("sampled_actions_gaussian", False)
     utils_kats()
+    trainable_log_std_case("ppo_trainable_log_std")

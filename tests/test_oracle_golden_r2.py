@@ -137,3 +137,18 @@ def test_native_closures_refuse_to_be_called_outside_the_optimizer():
     from rl_replicas_b200.optimizers.conjugate_gradient_optimizer import NativeClosure
     with pytest.raises(NotImplementedError):
         NativeClosure("surrogate loss", lambda opt: None)()
+
+
+def test_oracle_trains_log_std_like_the_reference():
+    """log_std inside the policy optimizer (policies/gaussian_policy.py:25-37): six PPO steps move it; the oracle's
+    closed-form d logp / d log_std = z^2 - 1 must follow the reference's autograd."""
+    g = load_golden("ppo_trainable_log_std")
+    policy = O.unflatten_layers(g["policy_flat0"], [17, 64, 64, 6])
+    value = O.unflatten_layers(g["value_flat0"], [17, 64, 64, 1])
+    out = O.ppo_train(batch_of(g), policy, value, "gaussian", g["log_std0"], O.AdamState(5702 + 6, 3e-4),
+                      O.AdamState(5377, 1e-3), max_kl=float("inf"), n_policy=6, n_value=3, train_log_std=True)
+    assert np.abs(g["log_std_final"] - g["log_std0"]).max() > 1e-3  # it really moved
+    assert rel_err(out["log_std"], g["log_std_final"]) < 1e-5
+    assert rel_err(out["policy_flat"], g["policy_flat_final"]) < 1e-5
+    assert rel_err(out["value_flat"], g["value_flat_final"]) < 1e-5
+    assert abs(out["kl"] - g["metric:policy/kl_divergence"]) < 1e-4 * abs(g["metric:policy/kl_divergence"]) + 1e-8
