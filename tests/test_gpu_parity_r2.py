@@ -307,7 +307,10 @@ def test_sampled_actions_after_a_gpu_update_equal_the_references(case):
     ppo = build(ps, vs, "categorical" if discrete else "gaussian", g["policy_flat0"], g["value_flat0"], g.get("log_std"),
                 num_policy_gradients=1, num_value_gradients=1, max_kl_divergence=float("inf"))
     ppo.train_packed(batch_of(g))
-    assert rel_err(flat(ppo.policy.network), g["policy_flat_final"]) < 1e-5
+    # one Adam step moves every entry by lr * g / (|g| + 1e-8): where |g| is comparable to the epsilon, a 1e-9 difference
+    # in g is a visible fraction of lr -- the parameters must agree to 2 % of ONE step (6e-6 absolute), which keeps
+    # the action distributions within 1e-5 of each other
+    assert np.abs(flat(ppo.policy.network) - g["policy_flat_final"]).max() < 0.02 * 3e-4
     probe = g["probe_obs"]
     torch.manual_seed(1234)
     single = np.stack([np.asarray(ppo.policy.get_action_numpy(probe[i])) for i in range(probe.shape[0])])
