@@ -544,9 +544,15 @@ __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const S
   constexpr int STAGE_BYTES = 256 * (int)sizeof(RewT) + 256 * 4;
   unsigned char* wbase = ep_smem + (size_t)warp * EP_STAGES * STAGE_BYTES;
   long long ie = (long long)blockIdx.x * EP_WARPS + warp, ics = 0, ibot = 0;  // issue-side iterator
+  long long nx_beg = 0, nx_end = 0;  // offsets of the issue side's NEXT episode, fetched one episode ahead (the loads
+                                     // then complete under the current episode's chunks instead of stalling the switch)
   if (ie < p.n_ep) {
     ibot = __ldg(p.off + ie) & ~7LL;
     ics = ((__ldg(p.off + ie + 1) + 7) & ~7LL) - 256;
+    if (ie + n_warps < p.n_ep) {
+      nx_beg = __ldg(p.off + ie + n_warps);
+      nx_end = __ldg(p.off + ie + n_warps + 1);
+    }
   }
   auto issue_next = [&](int st) {
     if (ie < p.n_ep) {
@@ -564,8 +570,12 @@ __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const S
       if (ics + 256 <= ibot) {  // episode covered: move to this warp's next one
         ie += n_warps;
         if (ie < p.n_ep) {
-          ibot = __ldg(p.off + ie) & ~7LL;
-          ics = ((__ldg(p.off + ie + 1) + 7) & ~7LL) - 256;
+          ibot = nx_beg & ~7LL;
+          ics = ((nx_end + 7) & ~7LL) - 256;
+          if (ie + n_warps < p.n_ep) {
+            nx_beg = __ldg(p.off + ie + n_warps);
+            nx_end = __ldg(p.off + ie + n_warps + 1);
+          }
         }
       }
     }
