@@ -85,19 +85,21 @@ class _OffPolicyBase:
 
     def _upload_state(self, e, trainable, targets, lins) -> None:
         slots, total = self._tensor_slots(e, trainable, targets, lins)
-        blob = torch.zeros(total, dtype=torch.float32)
         steps = [0, 0, 0]
-        with torch.no_grad():
-            for kind, p_, m, off, n in slots:
-                if kind == "params":
-                    blob[off:off + n] = p_.detach().reshape(-1)
-                else:
-                    st = m.optimizer.state.get(p_)
-                    if st and "exp_avg" in st:
-                        blob[off:off + n] = st["exp_avg" if kind == "m" else "exp_avg_sq"].reshape(-1)
         for i, (m, l) in enumerate(zip(trainable, lins)):
             adam_hparams(m.optimizer, l, "optimizer")  # refuses anything but a plain Adam over exactly this network
             _, _, steps[i] = read_adam_state(m.optimizer, l)
+        pieces = []
+        with torch.no_grad():
+            for kind, p_, m, off, n in slots:  # slots come in blob order: ONE concatenation builds the blob
+                if kind == "params":
+                    pieces.append(p_.detach().reshape(-1))
+                else:
+                    st = m.optimizer.state.get(p_)
+                    pieces.append(st["exp_avg" if kind == "m" else "exp_avg_sq"].reshape(-1)
+                                  if st and "exp_avg" in st else torch.zeros(n))
+            blob = torch.cat(pieces).float()
+        assert blob.numel() == total
         e.set_state(blob.numpy(), steps)
 
     def _download_state(self, e, trainable, targets, lins) -> None:
@@ -105,22 +107,27 @@ class _OffPolicyBase:
         blob, steps = e.get_state()
         src = torch.from_numpy(blob)
         index = {id(m): i for i, m in enumerate(trainable)}
-        with torch.no_grad():
-            for kind, p_, m, off, n in slots:
-                view = src[off:off + n].view_as(p_)
-                if kind == "params":
-                    p_.copy_(view)
-                    continue
-                step = steps[index[id(m)]]
-                if step == 0:
-                    continue
-                st = m.optimizer.state[p_]
-                key = "exp_avg" if kind == "m" else "exp_avg_sq"
-                if key in st and st[key].shape == p_.shape:
-                    st[key].copy_(view)
-                else:
-                    st[key] = view.clone()
+        dsts, srcs = [], []
+        for kind, p_, m, off, n in slots:
+            view = src[off:off + n].view_as(p_)
+            if kind == "params":
+                dsts.append(p_.data)
+                srcs.append(view)
+                continue
+            step = steps[index[id(m)]]
+            if step == 0:
+                continue
+            st = m.optimizer.state[p_]
+            key = "exp_avg" if kind == "m" else "exp_avg_sq"
+            if key in st and st[key].shape == p_.shape:
+                dsts.append(st[key])
+                srcs.append(view)
+            else:
+                st[key] = view.clone()
+            if kind == "m":
                 st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
+        with torch.no_grad():
+            torch._foreach_copy_(dsts, srcs)  # one call for all tensors
 
     def _hparams(self, noisy: bool, delay: int) -> OffPolicyHparams:
         trainable, _ = self._nets()
