@@ -198,3 +198,39 @@ def test_ddpg_learn_loop_with_evaluation(tmp_path):
     assert os.path.exists(os.path.join(tmp_path, "model.pt"))
     d = (torch.nn.utils.parameters_to_vector(algo.target_policy.network.parameters()) - after).abs().max()
     assert 0 < float(d) < 1.0  # polyak-averaged target trails the online policy
+
+
+@pytest.mark.parametrize("sampler_kind", ["batch", "vector"])
+def test_ppo_learns_cartpole_config1(tmp_path, sampler_kind):
+    """BASELINE config 1 (PPO, CartPole-v1, MLP(64, 64), 4000 steps per epoch, seed 0, the recipe of the reference's
+    benchmarks/run_ppo.py) on the CartPole dynamics of tests/cartpole.py: the default hyper-parameters (80 + 80 steps,
+    KL early stop) must make the policy better within a few epochs.  Categorical actions through the nested-list
+    sampler and through the vectorised sampler's packed store."""
+    from cartpole import CartPole
+    from rl_replicas_b200.algorithms import PPO
+    from rl_replicas_b200.networks import MLP
+    from rl_replicas_b200.policies import CategoricalPolicy
+    from rl_replicas_b200.samplers import BatchSampler, VectorSampler
+    from rl_replicas_b200.utils import set_seed_for_libraries
+    from rl_replicas_b200.value_function import ValueFunction
+    set_seed_for_libraries(0)
+    torch.use_deterministic_algorithms(False)
+    env = CartPole()
+    pnet, vnet = MLP([4, 64, 64, 2]), MLP([4, 64, 64, 1])
+    sampler = (BatchSampler(env, seed=0) if sampler_kind == "batch"
+               else VectorSampler([CartPole() for _ in range(8)], seed=0))
+    returns = []
+
+    class Recording:  # the sampler the learner sees: records the average sampled return of every epoch
+        def sample(self, num_samples, policy):
+            exp = sampler.sample(num_samples, policy)
+            returns.append(float(np.mean(exp.episode_returns)))
+            return exp
+
+    algo = PPO(CategoricalPolicy(pnet, torch.optim.Adam(pnet.parameters(), lr=3e-4)),
+               ValueFunction(vnet, torch.optim.Adam(vnet.parameters(), lr=1e-3)), env, Recording())
+    algo.learn(num_epochs=6, batch_size=4000, output_dir=str(tmp_path))
+    assert algo.last_update_stats.fused == 1  # the default recipe runs on the fused step kernel
+    assert len(returns) == 6
+    assert returns[0] < 40  # a random policy balances for ~22 steps
+    assert max(returns[3:]) > 2.0 * returns[0], returns
