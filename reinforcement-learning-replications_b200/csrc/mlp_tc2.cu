@@ -159,20 +159,26 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
   }
   for (int i = tid; i < 2 * 128; i += T2_THREADS) s_rowmax[i] = 0.f;
   __syncthreads();
+  // the parameter vector is brought into the (still unused, later fully overwritten) H1 buffer of slot 0 with
+  // independent coalesced loads: the passes below would otherwise pay one L2 round trip per element, serially
+  float* s_par = reinterpret_cast<float*>(sm + S2_H1);
+#pragma unroll 8
+  for (int i = tid; i < p.P; i += T2_THREADS) s_par[i] = __ldg(p.params + i);
+  __syncthreads();
   {
     float m1 = 0.f, m2 = 0.f, m3 = 0.f;
     for (int idx = tid; idx < h1 * n_in; idx += T2_THREADS) {
-      const float w = __ldg(p.params + p.w_off[0] + idx) * s_xs[32 + idx % n_in];
+      const float w = (s_par[p.w_off[0] + idx]) * s_xs[32 + idx % n_in];
       m1 = fmaxf(m1, fabsf(w));
       if (w != w) bad = true;
     }
     for (int idx = tid; idx < h2 * h1; idx += T2_THREADS) {
-      const float w = __ldg(p.params + p.w_off[1] + idx);
+      const float w = (s_par[p.w_off[1] + idx]);
       m2 = fmaxf(m2, fabsf(w));
       if (w != w) bad = true;
     }
     for (int idx = tid; idx < A_out * h2; idx += T2_THREADS) {
-      const float w = __ldg(p.params + p.w_off[2] + idx);
+      const float w = (s_par[p.w_off[2] + idx]);
       m3 = fmaxf(m3, fabsf(w));
       if (w != w) bad = true;
     }
@@ -243,18 +249,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     };
     const float sw1 = s_scale[SC_W1], sw2 = s_scale[SC_W2], sw3 = s_scale[SC_W3];
     for (int idx = tid; idx < h1 * n_in; idx += T2_THREADS)  // W1 stored transposed: row = input, column = output
-      put(S2_W1T, T2_W1T, idx % n_in, idx / n_in, (__ldg(p.params + p.w_off[0] + idx) * s_xs[32 + idx % n_in]) * sw1);
+      put(S2_W1T, T2_W1T, idx % n_in, idx / n_in, ((s_par[p.w_off[0] + idx]) * s_xs[32 + idx % n_in]) * sw1);
     for (int idx = tid; idx < h2 * h1; idx += T2_THREADS)
-      put(S2_W2, T2_W, idx / h1, idx % h1, __ldg(p.params + p.w_off[1] + idx) * sw2);
+      put(S2_W2, T2_W, idx / h1, idx % h1, (s_par[p.w_off[1] + idx]) * sw2);
     for (int idx = tid; idx < A_out * h2; idx += T2_THREADS)
-      put(S2_W3, T2_W3, idx / h2, idx % h2, __ldg(p.params + p.w_off[2] + idx) * sw3);
+      put(S2_W3, T2_W3, idx / h2, idx % h2, (s_par[p.w_off[2] + idx]) * sw3);
     for (int i = tid; i < 64; i += T2_THREADS) {
-      s_bias[i] = i < h1 ? __ldg(p.params + p.b_off[0] + i) : 0.f;
-      s_bias[64 + i] = i < h2 ? __ldg(p.params + p.b_off[1] + i) : 0.f;
+      s_bias[i] = i < h1 ? (s_par[p.b_off[0] + i]) : 0.f;
+      s_bias[64 + i] = i < h2 ? (s_par[p.b_off[1] + i]) : 0.f;
       if (!(fabsf(s_bias[i]) < INFINITY) || !(fabsf(s_bias[64 + i]) < INFINITY)) bad = true;
     }
     for (int i = tid; i < 16; i += T2_THREADS) {
-      s_bias[128 + i] = i < A_out ? __ldg(p.params + p.b_off[2] + i) : 0.f;
+      s_bias[128 + i] = i < A_out ? (s_par[p.b_off[2] + i]) : 0.f;
       if (!(fabsf(s_bias[128 + i]) < INFINITY)) bad = true;
     }
     if (p.dist == B200RL_DIST_GAUSSIAN)

@@ -177,28 +177,41 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
   const long long t_kernel0 = clock64();
 #endif
 
-  // ---- one-time setup: zero operand buffers; scales; weights of both networks as fp16 pairs; biases ----
-  for (uint32_t i = tid; i < S3_OPERANDS_END / 16; i += T3_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  // ---- one-time setup: scales; weights of both networks as fp16 pairs; biases ----
+  // Only the weight operands need zero padding (X tiles arrive whole by bulk copy, H and dOut are fully written by
+  // their jobs before any MMA reads them).  Both parameter vectors (44 KB) are first brought into the still unused
+  // activation buffers with independent, coalesced loads: the two passes below (maxima, then conversion) would
+  // otherwise pay an L2 round trip per element, one after the other -- 17 of the 18 us this set-up used to take.
+  for (uint32_t i = S3_W / 16 + tid; i < S3_OPERANDS_END / 16; i += T3_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) *s_bad = 0;
   if (tid < 64) s_xs[tid] = __ldg(p.xscale + tid);
+  float* s_par = reinterpret_cast<float*>(sm + S3_H);
+  static_assert(2 * S3_CHAIN >= 4 * (2 * 6000 + 64), "parameter staging area");
+#pragma unroll 1
+  for (int net = 0; net < 2; ++net) {
+    const float* par = p.params[net];
+    float* dst = s_par + (net == 0 ? 0 : p.P[0]);
+#pragma unroll 8
+    for (int i = tid; i < p.P[net]; i += T3_THREADS) dst[i] = (*(par + i));
+  }
   __syncthreads();
 #pragma unroll 1
   for (int net = 0; net < 2; ++net) {
     const Tc3Net& nn = p.net[net];
-    const float* par = p.params[net];
+    const float* par = s_par + (net == 0 ? 0 : p.P[0]);
     float m1 = 0.f, m2 = 0.f, m3 = 0.f;
     for (int idx = tid; idx < nn.h1 * n_in; idx += T3_THREADS) {
-      const float w = __ldg(par + nn.w_off[0] + idx) * s_xs[32 + idx % n_in];
+      const float w = (*(par + nn.w_off[0] + idx)) * s_xs[32 + idx % n_in];
       m1 = fmaxf(m1, fabsf(w));
       if (w != w) bad = true;
     }
     for (int idx = tid; idx < nn.h2 * nn.h1; idx += T3_THREADS) {
-      const float w = __ldg(par + nn.w_off[1] + idx);
+      const float w = (*(par + nn.w_off[1] + idx));
       m2 = fmaxf(m2, fabsf(w));
       if (w != w) bad = true;
     }
     for (int idx = tid; idx < nn.n_out * nn.h2; idx += T3_THREADS) {
-      const float w = __ldg(par + nn.w_off[2] + idx);
+      const float w = (*(par + nn.w_off[2] + idx));
       m3 = fmaxf(m3, fabsf(w));
       if (w != w) bad = true;
     }
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
 #pragma unroll 1
   for (int net = 0; net < 2; ++net) {
     const Tc3Net& nn = p.net[net];
-    const float* par = p.params[net];
+    const float* par = s_par + (net == 0 ? 0 : p.P[0]);
     const uint32_t wb = S3_W + net * S3_WNET;
     auto put = [&](uint32_t buf, uint32_t stride, int r, int c, float x) {
       const __half hb = __float2half_rn(x);
@@ -273,19 +286,19 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
     const float* sc = s_scale + 16 * net;
     const float sw1 = sc[C3_W1], sw2 = sc[C3_W2], sw3 = sc[C3_W3];
     for (int idx = tid; idx < nn.h1 * n_in; idx += T3_THREADS)  // W1 transposed: row = input, column = output
-      put(wb, T3_W1T, idx % n_in, idx / n_in, (__ldg(par + nn.w_off[0] + idx) * s_xs[32 + idx % n_in]) * sw1);
+      put(wb, T3_W1T, idx % n_in, idx / n_in, ((*(par + nn.w_off[0] + idx)) * s_xs[32 + idx % n_in]) * sw1);
     for (int idx = tid; idx < nn.h2 * nn.h1; idx += T3_THREADS)
-      put(wb + 2 * T3_W1T, T3_W2, idx / nn.h1, idx % nn.h1, __ldg(par + nn.w_off[1] + idx) * sw2);
+      put(wb + 2 * T3_W1T, T3_W2, idx / nn.h1, idx % nn.h1, (*(par + nn.w_off[1] + idx)) * sw2);
     for (int idx = tid; idx < nn.n_out * nn.h2; idx += T3_THREADS)
-      put(wb + 2 * T3_W1T + 2 * T3_W2, T3_W3, idx / nn.h2, idx % nn.h2, __ldg(par + nn.w_off[2] + idx) * sw3);
+      put(wb + 2 * T3_W1T + 2 * T3_W2, T3_W3, idx / nn.h2, idx % nn.h2, (*(par + nn.w_off[2] + idx)) * sw3);
     float* bb = s_bias + 160 * net;
     for (int i = tid; i < 64; i += T3_THREADS) {
-      bb[i] = i < nn.h1 ? __ldg(par + nn.b_off[0] + i) : 0.f;
-      bb[64 + i] = i < nn.h2 ? __ldg(par + nn.b_off[1] + i) : 0.f;
+      bb[i] = i < nn.h1 ? (*(par + nn.b_off[0] + i)) : 0.f;
+      bb[64 + i] = i < nn.h2 ? (*(par + nn.b_off[1] + i)) : 0.f;
       if (!(fabsf(bb[i]) < INFINITY) || !(fabsf(bb[64 + i]) < INFINITY)) bad = true;
     }
     for (int i = tid; i < 16; i += T3_THREADS) {
-      bb[128 + i] = i < nn.n_out ? __ldg(par + nn.b_off[2] + i) : 0.f;
+      bb[128 + i] = i < nn.n_out ? (*(par + nn.b_off[2] + i)) : 0.f;
       if (!(fabsf(bb[128 + i]) < INFINITY)) bad = true;
     }
   }
