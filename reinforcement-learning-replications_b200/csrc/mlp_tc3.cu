@@ -663,7 +663,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
         // (loading this thread's H chunks BEFORE the wait -- it wrote them itself two jobs ago -- to hide the
         // shared-memory latency under the barrier: 0.551 vs 0.525 ms, the 16 extra live registers spill at the 96 cap;
         // a second commit right behind the dH product, so that this job computes while the weight-gradient products
-        // still read H and only its stores wait for them, measured 2 % SLOWER: 0.5515 vs 0.540 ms)
+        // still read H and only its stores wait for them, measured 2 % SLOWER: 0.5515 vs 0.540 ms.  With `setmaxnreg`
+        // -- a full fifth warpgroup of 128 threads whose idle warps hand their registers over: 104 per epilogue thread
+        // and 64 for the MMA warp, or 112 / 32; registers are conserved inside the CTA, 640 x 96 = 128 AUX + 512 EPI --
+        // the spills go away and the prefetch is STILL slower (0.540 vs 0.522 ms): early shared-memory reads compete
+        // with the tensor pipe's operand fetches, which are what the waiting job is waiting for.  All reverted.)
         wait_chain();  // dH (and the weight-gradient products that still read H)
         // (1 - H^2) * 2^28 = fma(-Hs, Hs, 2^28) with Hs = H * 2^14 as stored; 2^-28 is folded into the unscale factor
         const float unscale = scl[stage == 4 ? C3_UH2 : C3_UH1] * hh;
