@@ -135,14 +135,17 @@ def test_train_vs_oracle_benchmark_shape(twin):
     adams = {k: O.AdamState(O.flatten_layers(nets[k]).size, 1e-3) for k in names}
     logs = OP.offpolicy_train(nets, adams, mbs, noise, policy_delay=2 if twin else 1, twin=twin)
     out = algo.last_train_output
-    assert rel_err(out["q1_values"], np.stack(logs["q1_values"])) < 1e-4
-    assert rel_err(out["q1_losses"], np.asarray(logs["q1_losses"])) < 1e-4
-    assert rel_err(out["policy_losses"], np.asarray(logs["policy_losses"])) < 1e-4
     q_nets = [algo.q_function_1, algo.q_function_2] if twin else [algo.q_function]
-    assert rel_err(flat(algo.policy.network), O.flatten_layers(nets["policy"])) < 1e-4
+    errs = {"q1_values": rel_err(out["q1_values"], np.stack(logs["q1_values"])),
+            "q1_losses": rel_err(out["q1_losses"], np.asarray(logs["q1_losses"])),
+            "policy_losses": rel_err(out["policy_losses"], np.asarray(logs["policy_losses"])),
+            "policy": rel_err(flat(algo.policy.network), O.flatten_layers(nets["policy"])),
+            "target_policy": rel_err(flat(algo.target_policy.network), O.flatten_layers(nets["target_policy"]))}
     for i, q in enumerate(q_nets):
-        assert rel_err(flat(q.network), O.flatten_layers(nets[f"q{i + 1}"])) < 1e-4
-    assert rel_err(flat(algo.target_policy.network), O.flatten_layers(nets["target_policy"])) < 1e-4
+        errs[f"q{i + 1}"] = rel_err(flat(q.network), O.flatten_layers(nets[f"q{i + 1}"]))
+    print("benchmark-shape errors:", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < 2e-5, (k, v, errs)  # north_star: 1e-5 per tensor; 2e-5 after ten Adam steps of three networks
 
 
 def test_device_replay_gather_and_graph_replay_match_the_staged_path():
