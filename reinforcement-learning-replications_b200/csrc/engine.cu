@@ -499,6 +499,9 @@ static int run_fused_iterations(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp
   a.run_value = 1;
   const int64_t n_all = h->Pp + h->Pv + 2 * B200RL_N_SCALARS;
   constexpr int poll = 8;
+  // B200RL_PEER_ONE_LAUNCH=0 keeps publish / wait / gather as three launches (A/B runs)
+  const char* e1 = getenv("B200RL_PEER_ONE_LAUNCH");
+  const bool one_launch = !(e1 != nullptr && e1[0] == '0') && ra3_one_wave(h->Pp + h->Pv);
   int i = 0;
   for (; i < n_iter; ++i) {
     if (launch_mlp_tc3(k, s)) return 1;
@@ -511,7 +514,7 @@ static int run_fused_iterations(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp
     if (!ar) {
       a.mode = 0;
       if (launch_reduce_adam3(a, s)) return 1;
-    } else if (h->comm_world > 1) {  // one-shot exchange over NVLink peer memory: two launches, no collective call
+    } else if (h->comm_world > 1) {  // one-shot exchange over NVLink peer memory, no collective call
       a.peers = h->peers_dev;
       a.world = h->comm_world;
       a.rank = h->comm_rank;
@@ -519,11 +522,16 @@ static int run_fused_iterations(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp
       a.seq = ++h->comm_seq;
       a.done_counter = h->done_counter;
       a.comm_error = h->flags + 4;
-      a.mode = 3;
-      if (launch_reduce_adam3(a, s)) return 1;
-      if (launch_wait_peers(a, s)) return 1;
-      a.mode = 4;
-      if (launch_reduce_adam3(a, s)) return 1;
+      if (one_launch) {
+        a.mode = 5;
+        if (launch_reduce_adam3(a, s)) return 1;
+      } else {
+        a.mode = 3;
+        if (launch_reduce_adam3(a, s)) return 1;
+        if (launch_wait_peers(a, s)) return 1;
+        a.mode = 4;
+        if (launch_reduce_adam3(a, s)) return 1;
+      }
     } else {
       a.mode = 1;
       if (launch_reduce_adam3(a, s)) return 1;
@@ -803,6 +811,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
   a.log_std = h->log_std;
   a.row_out = h->old_logp;
   a.out_full = h->old_out;
+  if (h->hints_valid) a.obs_absmax = h->absmax;
   if (b200rl_mlp_loss_grad(&a, s)) return 1;
   // (2) surrogate loss and its gradient at theta (trpo.py:228-239); slot 0 also carries the logged statistics
   if (launch_fused(h, h->cfg.policy, B200RL_LOSS_TRPO_SURROGATE, dist, h->pol, h->obs, n, n, 0.0, true, true, nullptr,
@@ -832,7 +841,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
     memset(&a, 0, sizeof(a));
     a.mlp = h->cfg.policy;
     a.loss = B200RL_LOSS_TRPO_SURROGATE;
-    a.flags = B200RL_FLAG_FORWARD_ONLY | B200RL_FLAG_NO_TC;
+    a.flags = B200RL_FLAG_FORWARD_ONLY;
     a.dist = dist;
     a.n_rows = n;
     a.n_global = n;
@@ -844,6 +853,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
     a.adv_stats = h->adv_stats;
     a.old_logp = h->old_logp;
     a.old_out = h->old_out;
+    if (h->hints_valid) a.obs_absmax = h->absmax;
     a.scalar_partials = h->scalar_partials;
     a.skip_flag = h->cg_flags + 1;
     if (b200rl_mlp_loss_grad(&a, s)) return 1;

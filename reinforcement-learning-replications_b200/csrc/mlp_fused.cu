@@ -141,7 +141,7 @@ struct FusedArgs {
   const float* direction;
   const unsigned* run_if;  // when set: run only if *run_if == seq (re-run of a tensor-core launch that left fp16's range)
   unsigned seq;
-  int total_rows;          // partial rows the consumer reduces (> gridDim.x when standing in for a tensor-core launch)
+  int total_rows;          // partial rows the consumer reduces (> gridDim.x when standing in for / sized like a tensor-core launch)
   unsigned long long* rerun_counter;  // b200rl_tc_fallback_count's device counter
   int train_log_std;       // Gaussian: partial rows carry dLoss/dlog_std in columns P .. P + A - 1 (row stride P + A)
 };
@@ -219,11 +219,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fused_kernel(const FusedAr
   if (p.run_if != nullptr) {
     if (*p.run_if != p.seq) return;  // the tensor-core result stands
     if (blockIdx.x == 0 && tid == 0 && p.rerun_counter != nullptr) atomicAdd(p.rerun_counter, 1ull);
-    for (int row = (int)gridDim.x + (int)blockIdx.x; row < p.total_rows; row += (int)gridDim.x) {
-      if (BACKWARD)
-        for (int i = tid; i < Y.P; i += MLP_THREADS) p.partials[(size_t)row * Y.P + i] = 0.f;
-      if (p.scalar_partials != nullptr && tid < B200RL_N_SCALARS) p.scalar_partials[(size_t)row * B200RL_N_SCALARS + tid] = 0.0;
-    }
+  }
+  // the consumer reduces total_rows partial rows: those beyond this grid are zero
+  for (int row = (int)gridDim.x + (int)blockIdx.x; row < p.total_rows; row += (int)gridDim.x) {
+    if (BACKWARD)
+      for (int i = tid; i < Y.P; i += MLP_THREADS) p.partials[(size_t)row * Y.P + i] = 0.f;
+    if (p.scalar_partials != nullptr && tid < B200RL_N_SCALARS) p.scalar_partials[(size_t)row * B200RL_N_SCALARS + tid] = 0.0;
   }
   const int L = Y.L;
 
@@ -640,10 +641,11 @@ int tc_grid(int64_t n_rows);
 int launch_mlp_tc(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s);
 // second-generation tensor-core path (mlp_tc2.cu): fp16 x 2 splits, two partial rows per CTA
 int tc2_grid(int64_t n_rows);
-int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s);
+int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, int total_rows, cudaStream_t s);
 // B200RL_TC_MODE=bf16 pins the bf16 x 3 kernel (A/B runs); default is the fp16 x 2 kernel with bf16 x 3 as its
 // wide-range fallback
 int tc_fvp_total_rows(const b200rl_mlp_desc& mlp, int64_t n_rows);
+int tc_fwd_total_rows(const b200rl_mlp_desc& mlp, int64_t n_rows);
 static bool use_tc2() {
   const char* e = getenv("B200RL_TC_MODE");
   return !(e != nullptr && e[0] == 'b');
@@ -673,7 +675,7 @@ extern "C" int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp) {
   return p;
 }
 
-// with_backward: 0 forward only, 1 forward + backward, 2 Fisher-vector product, 3 forward only on the fp32 kernel
+// with_backward: 0 forward only, 1 forward + backward, 2 Fisher-vector product, 3 forward only with out_full / old_out / NO_TC
 // (launches that use out_full / old_out / B200RL_FLAG_NO_TC)
 extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward) {
   if (!mlp) return -1;
@@ -683,6 +685,7 @@ extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int w
     return g > 0 ? 2 * g : -1;
   }
   if (with_backward == 2 && use_tc(*mlp) && use_tc2()) return tc_fvp_total_rows(*mlp, n_rows);
+  if (with_backward == 3 && use_tc(*mlp) && use_tc2()) return tc_fwd_total_rows(*mlp, n_rows);
   MlpLayout lay;
   if (build_layout(*mlp, with_backward == 1 || with_backward == 2 || with_backward == 4, &lay, with_backward == 2)) return -1;
   return fused_grid(lay, n_rows);
@@ -761,6 +764,16 @@ int launch_fused_fallback(const b200rl_mlp_loss_grad_args* a, const unsigned* ru
   return launch_fused(a, run_if, seq, total_rows, s);
 }
 
+// partial rows of a forward-only launch that carries out_full / old_out / B200RL_FLAG_NO_TC (b200rl_mlp_grid mode 3): the
+// fp16 kernel's two per CTA, or the fp32 kernel's grid (its re-run, or the launch itself under NO_TC) if that is larger
+int tc_fwd_total_rows(const b200rl_mlp_desc& mlp, int64_t n_rows) {
+  MlpLayout lay;
+  if (build_layout(mlp, false, &lay, false)) return -1;
+  const int g = tc2_grid(n_rows), f = fused_grid(lay, n_rows);
+  if (g <= 0 || f <= 0) return -1;
+  return 2 * g > f ? 2 * g : f;
+}
+
 // partial rows of a tensor-core FVP launch: its own two per CTA, or the fp32 re-run's grid if that is larger
 int tc_fvp_total_rows(const b200rl_mlp_desc& mlp, int64_t n_rows) {
   MlpLayout lay;
@@ -819,10 +832,15 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
     B200RL_REQUIRE(total > 0, "mlp_loss_grad: no CUDA device");
     return launch_mlp_tc_fvp(a, n_glob_all, total, s);
   }
-  const bool needs_fp32 = fvp || a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC) || a->train_log_std;
+  // raw outputs / the true KL exist on the fp16 kernel's forward-only variant (not on the bf16 x 3 kernel, not with backward)
+  const bool wants_out = a->out_full != nullptr || a->old_out != nullptr;
+  const bool out_on_tc = wants_out && forward_only && use_tc2();
+  const bool needs_fp32 = fvp || (wants_out && !out_on_tc) || (a->flags & B200RL_FLAG_NO_TC) || a->train_log_std;
+  const bool mode3 = forward_only && (wants_out || (a->flags & B200RL_FLAG_NO_TC));
+  const int rows3 = (mode3 && use_tc(a->mlp) && use_tc2()) ? tc_fwd_total_rows(a->mlp, a->n_rows) : 0;
   if (!needs_fp32 && use_tc(a->mlp)) {
     const int64_t n_glob_tc = a->n_global > 0 ? a->n_global : a->n_rows;
-    return use_tc2() ? launch_mlp_tc2(a, n_glob_tc, s) : launch_mlp_tc(a, n_glob_tc, s);
+    return use_tc2() ? launch_mlp_tc2(a, n_glob_tc, rows3, s) : launch_mlp_tc(a, n_glob_tc, s);
   }
-  return launch_fused(a, nullptr, 0u, 0, s);
+  return launch_fused(a, nullptr, 0u, rows3, s);
 }

@@ -63,8 +63,8 @@ constexpr uint32_t S2_DIST = S2_BIAS + 640;    // var[16], log_scale[16], 1/(2 v
 constexpr uint32_t S2_DB3 = S2_DIST + 256;     // [16 warps][16] floats: running sum_r dOut[r][a] per warp
 constexpr uint32_t S2_SCALE = S2_DB3 + 1024;   // scale factors (floats)
 constexpr uint32_t S2_RED = S2_SCALE + 64;     // block reduction scratch [17 warps][4] floats
-constexpr uint32_t S2_SC = S2_RED + 320;       // [16 warps][6] doubles: running scalar sums per warp
-constexpr uint32_t S2_BARS = S2_SC + 768;      // mbarriers: ready[2], chain[2], off[2]; tmem holder; bad flag
+constexpr uint32_t S2_SC = S2_RED + 320;       // [16 warps][7] doubles: running scalar sums per warp
+constexpr uint32_t S2_BARS = S2_SC + 896;      // mbarriers: ready[2], chain[2], off[2]; tmem holder; bad flag
 constexpr uint32_t S2_XS = S2_BARS + 64;       // per-feature observation scales 2^ex_k [32] and their inverses [32]
 constexpr uint32_t S2_ROWMAX = S2_XS + 256;    // [2 slots][128] largest scaled |obs| of each row (precision guard)
 constexpr uint32_t S2_TOTAL = S2_ROWMAX + 1024;
@@ -103,6 +103,9 @@ struct Tc2Args {
   const int* skip_flag;
   const float* obs_absmax;     // device [n_in]: per-feature max |obs|
   const float* target_absmax;  // device scalar (MSE) or NULL
+  float* out_full;             // forward-only launches: raw network outputs [n_rows, n_out]
+  const float* old_out;        // forward-only launches: outputs of the old policy -> true KL(old || new) in scalar 6
+  int total_rows;              // partial rows the consumer reduces when that is more than two per CTA (else 0)
   unsigned* status;            // status-ring slot of this launch
   unsigned seq;                // value to store there when the launch must be redone by the wide-range kernel
 };
@@ -409,6 +412,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     // a fixed order, at the end of the kernel -- a warp reduction per tile would put ~130 dependent shuffles on the
     // latency-bound loss job
     double sc[6] = {0, 0, 0, 0, 0, 0};
+    double sc_kl = 0.0;  // forward-only launches with old_out: sum of KL(old || new)
     float db3[15];
 #pragma unroll
     for (int a = 0; a < 15; ++a) db3[a] = 0.f;
@@ -581,6 +585,48 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
                   }
               }
               if (p.row_out) p.row_out[row] = lp;
+              if (!BACKWARD) {
+                if (p.out_full != nullptr) {
+#pragma unroll
+                  for (int a = 0; a < 15; ++a)
+                    if (a < A_out) p.out_full[row * A_out + a] = out[a];
+                }
+                if (p.old_out != nullptr) {  // kl_divergence(old_dist, dist), trpo.py:167-175
+                  const float* oo = p.old_out + row * A_out;
+                  float kl = 0.f;
+                  if (p.dist == B200RL_DIST_GAUSSIAN) {  // same std: 0.5 ((mu_old - mu) / std)^2 summed
+#pragma unroll
+                    for (int a = 0; a < 15; ++a)
+                      if (a < A_out) {
+                        const float d = __ldg(oo + a) - out[a];
+                        kl += 0.5f * ((d * d) * s_dist[48 + a]);
+                      }
+                  } else {
+                    float mo = __ldg(oo), mn = out[0];
+#pragma unroll
+                    for (int a = 1; a < 15; ++a)
+                      if (a < A_out) {
+                        mo = fmaxf(mo, __ldg(oo + a));
+                        mn = fmaxf(mn, out[a]);
+                      }
+                    float so = 0.f, sn = 0.f;
+#pragma unroll
+                    for (int a = 0; a < 15; ++a)
+                      if (a < A_out) {
+                        so += expf(__ldg(oo + a) - mo);
+                        sn += expf(out[a] - mn);
+                      }
+                    const float lo = mo + logf(so), ln = mn + logf(sn);
+#pragma unroll
+                    for (int a = 0; a < 15; ++a)
+                      if (a < A_out) {
+                        const float lpo = __ldg(oo + a) - lo;
+                        kl += expf(lpo) * (lpo - (out[a] - ln));
+                      }
+                  }
+                  sc_kl += (double)kl;
+                }
+              }
               float adv = 0.f, oldlp = 0.f;
               if (p.loss != B200RL_LOSS_EVAL) {
                 adv = pf_adv;
@@ -759,8 +805,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
 #pragma unroll
       for (int kk = 0; kk < 6; ++kk) {
         const double t = warp_sum(sc[kk]);
-        if (lane == 0) s_sc[warp * 6 + kk] = t;
+        if (lane == 0) s_sc[warp * 7 + kk] = t;
       }
+      const double t = warp_sum(sc_kl);
+      if (lane == 0) s_sc[warp * 7 + 6] = t;
     }
     asm volatile("bar.sync 2, %0;" ::"n"(T2_EPI_THREADS) : "memory");  // every warp's sums are in shared memory
     if (BACKWARD && tid < A_out) {  // db3: the 16 per-warp totals in warp order
@@ -771,10 +819,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) mlp_tc2_kernel(const Tc2Args p)
     }
     if (p.scalar_partials != nullptr && tid < B200RL_N_SCALARS) {
       double t = 0.0;
-      if (tid < 6)
-        for (int w = 0; w < T2_EPI_WARPS; ++w) t += s_sc[w * 6 + tid];
+      if (tid < 7)
+        for (int w = 0; w < T2_EPI_WARPS; ++w) t += s_sc[w * 7 + tid];
       p.scalar_partials[((size_t)blockIdx.x * 2) * B200RL_N_SCALARS + tid] = t;
       p.scalar_partials[((size_t)blockIdx.x * 2 + 1) * B200RL_N_SCALARS + tid] = 0.0;
+      // rows the consumer reduces beyond this grid's two per CTA (sized for the fp32 re-run): zero
+      for (int row = 2 * (int)gridDim.x + (int)blockIdx.x; row < p.total_rows; row += (int)gridDim.x)
+        p.scalar_partials[(size_t)row * B200RL_N_SCALARS + tid] = 0.0;
     }
     if (bad) *s_bad = 1;
   }
@@ -874,8 +925,10 @@ int tc2_grid(int64_t n_rows) {
 
 int launch_mlp_tc_fallback(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, const unsigned* run_if, unsigned seq,
                            int partial_rows, cudaStream_t s);
+int launch_fused_fallback(const b200rl_mlp_loss_grad_args* a, const unsigned* run_if, unsigned seq, int total_rows,
+                          cudaStream_t s);  // mlp_fused.cu: the fp32 kernel as the predicated re-run
 
-int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStream_t s) {
+int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, int total_rows, cudaStream_t s) {
   unsigned* status_slot = nullptr;
   unsigned seq = 0;
   float* scratch = nullptr;
@@ -914,7 +967,10 @@ int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStrea
   k.skip_flag = a->skip_flag;
   k.status = status_slot;
   k.seq = seq;
-  const bool backward = a->loss != B200RL_LOSS_EVAL;
+  const bool backward = a->loss != B200RL_LOSS_EVAL && !(a->flags & B200RL_FLAG_FORWARD_ONLY);
+  k.out_full = a->out_full;
+  k.old_out = a->old_out;
+  k.total_rows = total_rows;
   int launches = 0;
   // scale hints: use the caller's, else run the pre-pass (correct for any caller; the engine passes hints)
   const bool need_obs = a->obs_absmax == nullptr;
@@ -938,8 +994,12 @@ int launch_mlp_tc2(const b200rl_mlp_loss_grad_args* a, int64_t n_glob, cudaStrea
     mlp_tc2_kernel<false><<<grid, T2_THREADS, T2_SMEM_BYTES, s>>>(k);
   B200RL_CUDA(cudaGetLastError());
   count_launch(launches + 1);
-  // wide-range re-run, predicated on this launch's status slot (a few microseconds when it does not fire)
-  return launch_mlp_tc_fallback(a, n_glob, status_slot, seq, 2 * grid, s);
+  // wide-range re-run, predicated on this launch's status slot (a few microseconds when it does not fire); the bf16 x 3
+  // kernel does not produce raw outputs / the true KL, the fp32 kernel does
+  const int rows = total_rows > 2 * grid ? total_rows : 2 * grid;
+  if (a->out_full != nullptr || a->old_out != nullptr || (!backward && a->loss != B200RL_LOSS_EVAL))
+    return launch_fused_fallback(a, status_slot, seq, rows, s);
+  return launch_mlp_tc_fallback(a, n_glob, status_slot, seq, rows, s);
 }
 
 }  // namespace b200rl

@@ -860,9 +860,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
 // rank applies bit-identical updates, then runs Adam.  22 KB per rank: latency bound, ~2 us per peer read.
 // Buffers alternate between two parities: a rank can only be one exchange ahead of its slowest peer (it needs that
 // peer's next sequence number to finish its own), so the buffer it overwrites was read by everybody.
+// mode 5 = modes 3 and 4 in ONE launch (the blocks wait for the sequence numbers themselves): a data-parallel iteration
+// is then two launches, like a single-GPU one.  It needs every block resident at once (ra3_one_wave).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RA3_WARPS = 8;
-__global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3Args a) {
+__global__ void __launch_bounds__(RA3_WARPS * 32, 4) reduce_adam3_kernel(const Ra3Args a) {
   __shared__ float part[RA3_WARPS][32];
   __shared__ double spart[RA3_WARPS * 4][2 * B200RL_N_SCALARS];
   __shared__ double s_scal[2 * B200RL_N_SCALARS];
@@ -940,7 +942,7 @@ __global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3A
     if (blockIdx.x == 0 && threadIdx.x < 2 * B200RL_N_SCALARS) a.grad[Ptot + threadIdx.x] = (float)s_scal[threadIdx.x];
     return;
   }
-  if (a.mode == 3) {
+  if (a.mode == 3 || a.mode == 5) {
     float* mine = a.peers[a.rank] + parity * a.xchg_stride;
     if (warp == 0 && pidx < Ptot) mine[pidx] = g;
     if (blockIdx.x == 0 && threadIdx.x < 2 * B200RL_N_SCALARS) mine[Ptot + threadIdx.x] = (float)s_scal[threadIdx.x];
@@ -955,7 +957,47 @@ __global__ void __launch_bounds__(RA3_WARPS * 32) reduce_adam3_kernel(const Ra3A
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(a.seq) : "memory");
       }
     }
-    return;
+    if (a.mode == 3) return;
+    // mode 5: the same launch goes on to gather.  Lane r of warp 0 waits for rank r's sequence number -- this rank's own
+    // included, which is what tells a block that the OTHER blocks of this grid have written their parts (every block is
+    // resident: the host checked that the grid fits the device in one wave, so the spinning blocks cannot starve the
+    // publishing one).
+    if (warp == 0 && lane < a.world) {
+      const unsigned* flag = reinterpret_cast<const unsigned*>(a.peers[lane] + 2 * a.xchg_stride) + parity;
+      const long long t0 = clock64();
+      unsigned seen;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen == a.seq) break;
+        if (clock64() - t0 > 20000000000LL) {  // ~10 s: a rank died or never launched
+          *a.comm_error = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * B200RL_N_SCALARS) {
+      double t = 0.0;
+      for (int r = 0; r < a.world; ++r) {
+        float x;
+        const float* src = a.peers[r] + parity * a.xchg_stride + Ptot + threadIdx.x;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
+        t += (double)x;
+      }
+      s_scal[threadIdx.x] = t;
+    }
+    if (warp == 0 && pidx < Ptot) {
+      g = 0.f;
+      for (int r = 0; r < a.world; ++r) {  // rank order: the same sum on every rank
+        float x;
+        const float* src = a.peers[r] + parity * a.xchg_stride + pidx;
+        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
+        g += x;
+      }
+      if (a.grad != nullptr) a.grad[pidx] = g;
+    }
+    __syncthreads();
   }
   // early stop (ppo.py:176-181): the KL carried by this step's forward pass is the KL after the PREVIOUS update
   bool stop = !run_p;
@@ -1058,6 +1100,20 @@ int launch_mlp_tc3(const Tc3Args& k, cudaStream_t s) {
   B200RL_CUDA(cudaGetLastError());
   count_launch(1);
   return 0;
+}
+
+// mode 5 spins inside the grid: only when all of its blocks are resident together
+bool ra3_one_wave(long long p_total) {
+  static const int per_sm = []() -> int {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reduce_adam3_kernel, RA3_WARPS * 32, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return 0;
+    }
+    return n;
+  }();
+  const int sms = device_sm_count();
+  return sms > 0 && (p_total + 31) / 32 <= (long long)per_sm * sms;
 }
 
 int launch_reduce_adam3(const Ra3Args& a, cudaStream_t s) {

@@ -26,7 +26,7 @@
 namespace b200rl {
 
 constexpr int FV_ROWS = 128;
-constexpr int FV_EPI_WARPS = 8;
+constexpr int FV_EPI_WARPS = 16;  // 4 lane groups x 4 column groups of 16 (8 warps with 32 columns each: 0.59 ms per F v)
 constexpr int FV_EPI_THREADS = FV_EPI_WARPS * 32;
 constexpr int FV_THREADS = FV_EPI_THREADS + 32;
 
@@ -43,8 +43,8 @@ constexpr uint32_t SF_OPERANDS_END = SF_V3 + 2 * FV_W3;
 constexpr uint32_t SF_BIAS = SF_OPERANDS_END;   // b1[64] b2[64] b3[16] | vb1[64] vb2[64] vb3[16] floats
 constexpr uint32_t SF_DIST = SF_BIAS + 1152;    // 1/var[16] floats
 constexpr uint32_t SF_SCALE = SF_DIST + 64;     // scale factors
-constexpr uint32_t SF_RED = SF_SCALE + 128;     // block reduction scratch [9 warps][8] floats (+ 4 for the dOut max)
-constexpr uint32_t SF_BARS = SF_RED + 320;      // mbarriers ready, chain, off; tmem holder; bad flag
+constexpr uint32_t SF_RED = SF_SCALE + 128;     // block reduction scratch [17 warps][8] floats (read-out: [4][16] + 4 + 4)
+constexpr uint32_t SF_BARS = SF_RED + 576;      // mbarriers ready, chain, off; tmem holder; bad flag
 constexpr uint32_t SF_XS = SF_BARS + 64;        // per-feature observation scales [32] and inverses [32]
 constexpr uint32_t SF_ROWMAX = SF_XS + 256;     // [128] largest scaled |obs| of each row (precision guard)
 constexpr uint32_t SF_TOTAL = SF_ROWMAX + 512;
@@ -309,11 +309,11 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
     }
   } else {
     // =============================== epilogue warps ==================================================
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = warp >> 2;  // lane group, column group (16 columns each)
     const int r = 32 * q + lane;
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     const uint32_t tz = tmem + lane_addr;
-    const int c0 = 32 * half;
+    const int cs = 16 * half;
     uint32_t ph_chain = 0, ph_off = 0;
     const float sH = pow2i(T2_H_EXP);
     float sG = 0.f;  // gradient scale: set from the first tile's dOut (every CTA owns its accumulators, so the scale
@@ -337,9 +337,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
     // T = (1 - H^2) (TZ ut + vb) -> fp16 splits of the tangent buffer
     auto layer_epilogue = [&](uint32_t tm_z, const float* bias, const float* vbias, float unscale, float unscale_t,
                               float t_scale, uint32_t dst_h, uint32_t dst_t, bool keep_fp32) {
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int cs = c0 + 16 * sub;
+      {
         uint32_t v[16], w[16];
         tmem_ld16(tz + tm_z + cs, v);
         tmem_ld16(tz + MF_TZ + cs, w);
@@ -374,13 +372,10 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
       const long long row = tile * FV_ROWS + r;
       const bool valid = row < p.n_rows;
       {  // E0: observations
-        float x0[8], x1[8];
-        const float* src = p.obs + row * n_in + 16 * half;
+        float x0[8];
+        const float* src = p.obs + row * n_in + 8 * half;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          x0[j] = (valid && 16 * half + j < n_in) ? __ldg(src + j) : 0.f;
-          x1[j] = (valid && 16 * half + 8 + j < n_in) ? __ldg(src + 8 + j) : 0.f;
-        }
+        for (int j = 0; j < 8; ++j) x0[j] = (valid && 8 * half + j < n_in) ? __ldg(src + j) : 0.f;
         if (!first) {
           mbar_wait(bars + 16, ph_off);
           ph_off ^= 1u;
@@ -390,14 +385,12 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
         float rmax = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          x0[j] *= s_xs[16 * half + j];
-          x1[j] *= s_xs[16 * half + 8 + j];
-          rmax = fmaxf(rmax, fmaxf(fabsf(x0[j]), fabsf(x1[j])));
+          x0[j] *= s_xs[8 * half + j];
+          rmax = fmaxf(rmax, fabsf(x0[j]));
         }
         atomicMax(reinterpret_cast<int*>(s_rowmax + r), __float_as_int(rmax));
-        if (out_of_range8(x0) || out_of_range8(x1)) bad = true;
-        store_chunk2(sm, SF_XD, r, 2 * half, x0);
-        store_chunk2(sm, SF_XD, r, 2 * half + 1, x1);
+        if (out_of_range8(x0)) bad = true;
+        store_chunk2(sm, SF_XD, r, half, x0);
       }
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {  // one copy of the (large) layer epilogue: instruction-cache pressure
@@ -494,9 +487,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
       wait_chain();  // dH2 (and dW3)
       {
         const float unscale = s_scale[FS_UH2], hh = pow2i(-2 * T2_H_EXP);
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int cs = c0 + 16 * sub;
+        {
           uint32_t g[16];
           tmem_ld16(tz + MF_ZB + cs, g);
           tmem_wait_ld();
@@ -516,9 +507,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
       wait_chain();  // dH1 (and dW2 / db2)
       {
         const float unscale = s_scale[FS_UH1];
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int cs = c0 + 16 * sub;
+        {
           uint32_t g[16], h[16];
           tmem_ld16(tz + MF_ZB + cs, g);
           tmem_ld16(tz + MF_Z1 + cs, h);
@@ -548,10 +537,11 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
       float* dst = p.partials + ((size_t)blockIdx.x * 2 + (q >> 1)) * p.P;
       const int m = 32 * (q & 1) + lane;
       uint32_t v[16];
-      // half 0: dW2 (64 columns); half 1: dW1 + db1, dW3^T, db2
-      if (half == 0) {
+      // column groups 0, 1: dW2 (32 columns each); 2: dW1 + db1; 3: dW3^T, db2
+      if (half < 2) {
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int cb = 2 * half + c2;
           tmem_ld16(tz + MF_DW2 + 16 * cb, v);
           tmem_wait_ld();
           const float u = s_scale[FS_OW2];
@@ -560,7 +550,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
             for (int j = 0; j < 16; ++j)
               if (16 * cb + j < h1) dst[p.w_off[1] + m * h1 + 16 * cb + j] = __uint_as_float(v[j]) * u;
         }
-      } else {
+      } else if (half == 2) {
 #pragma unroll
         for (int cb = 0; cb < 3; ++cb) {
           tmem_ld16(tz + MF_DW1 + 16 * cb, v);
@@ -577,6 +567,7 @@ __global__ void __launch_bounds__(FV_THREADS, 1) mlp_tc_fvp_kernel(const FvpArgs
             }
           }
         }
+      } else {
         tmem_ld16(tz + MF_DW3, v);
         tmem_wait_ld();
         const float u = s_scale[FS_OW3];

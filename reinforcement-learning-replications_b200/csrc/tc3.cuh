@@ -44,7 +44,8 @@ constexpr int RA3_MAX_WORLD = 16;
 
 struct Ra3Args {
   // 0 reduce + Adam, 1 reduce only (scalars appended to grad), 2 Adam only (scalars from grad's tail),
-  // 3 reduce + publish into this rank's exchange buffer, 4 gather every rank's buffer over NVLink + Adam
+  // 3 reduce + publish into this rank's exchange buffer, 4 gather every rank's buffer over NVLink + Adam,
+  // 5 = 3 + wait + 4 in one launch
   int mode;
   const float* partials;
   const double* scalar_partials;
@@ -75,5 +76,6 @@ int launch_pack_obs(const float* obs, int64_t n_rows, int n_in, const float* abs
 int launch_mlp_tc3(const Tc3Args& k, cudaStream_t s);
 int launch_reduce_adam3(const Ra3Args& a, cudaStream_t s);
 int launch_wait_peers(const Ra3Args& a, cudaStream_t s);
+bool ra3_one_wave(long long p_total);
 
 }  // namespace b200rl

@@ -42,14 +42,18 @@ def main():
     # parameters (it does so between any two float32 implementations, the reference's CPU arithmetic included), so
     # that configuration is held to 1e-5 against the SAME engine on one GPU (identical arithmetic, different
     # reduction tree) and to 1e-4 against the oracle.
+    # peer: "1" publish + wait + gather + Adam in one launch per iteration, "3" the same as three launches, "0" NCCL
     cases = [(float("inf"), 1e9, "1"), (float("inf"), 0.2, "1"), (0.002, 0.2, "1"),
+             (float("inf"), 1e9, "3"), (0.002, 0.2, "3"),
              (float("inf"), 1e9, "0"), (float("inf"), 0.2, "0"), (0.002, 0.2, "0")]
     for max_kl, clip, peer in cases:
-        os.environ["B200RL_PEER_EXCHANGE"] = peer
+        os.environ["B200RL_PEER_EXCHANGE"] = "0" if peer == "0" else "1"
+        os.environ["B200RL_PEER_ONE_LAUNCH"] = "0" if peer == "3" else "1"
         dp = build(ps, vs, "gaussian", O.flatten_layers(pl), O.flatten_layers(vl), log_std, distributed=True,
                    max_kl_divergence=max_kl, clip_range=clip, **hp)
         dp.train_packed(synthetic.shard_batch(full, rank, world))
-        path = "peer-memory exchange" if dp._engine.peer_exchange else "NCCL all-reduce"
+        path = ("peer-memory exchange, " + ("one launch" if peer == "1" else "three launches")) if dp._engine.peer_exchange \
+            else "NCCL all-reduce"
         p_dp, v_dp = flat(dp.policy.network).copy(), flat(dp.value_function.network).copy()
         st = dp.last_update_stats
         # all ranks must hold bit-identical parameters
@@ -83,7 +87,7 @@ def main():
             bar_policy = 1e-5 if (clip > 1e6 or o["policy_steps"] <= 3) else 1e-4
             good = (same and ep < 1e-5 and ev < 1e-5 and eop < bar_policy and eov < 1e-5
                     and st.policy_steps_applied == rs.policy_steps_applied == o["policy_steps"]
-                    and dp._engine.peer_exchange == (peer == "1")
+                    and dp._engine.peer_exchange == (peer != "0")
                     and abs(st.kl_divergence - rs.kl_divergence) < 1e-4 * abs(rs.kl_divergence) + 1e-8
                     and abs(st.value_loss_mean - rs.value_loss_mean) < 1e-5 * rs.value_loss_mean
                     and abs(st.adv_std - rs.adv_std) < 1e-9 * rs.adv_std)

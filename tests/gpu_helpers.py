@@ -104,3 +104,34 @@ def fvp(sizes, flat, obs, dist, direction, log_std=None, hidden_act="tanh"):
     check(lib.b200rl_reduce_partials(p(partials), None, grid, P, p(out), None, 0, None, stream()), "reduce_partials")
     torch.cuda.synchronize()
     return out[:P].cpu().numpy()
+
+
+def forward_outputs(sizes, flat, obs, dist, act, log_std=None, old_out=None, adv_raw=None, old_logp=None, loss="eval",
+                    no_tc=False, hidden_act="tanh"):
+    """A forward-only launch that asks for the raw outputs (out_full) and, with old_out, the true KL(old || new):
+    returns dict(out, rows (log-probs), scalars[8])."""
+    lib = _lib.load()
+    a = LossGradArgs()
+    a.mlp = MlpDesc.make(sizes, hidden_act, "identity")
+    a.loss, a.dist = LOSS[loss], DIST[dist]
+    a.flags = 1 | (2 if no_tc else 0)  # B200RL_FLAG_FORWARD_ONLY | B200RL_FLAG_NO_TC
+    n = obs.shape[0]
+    a.n_rows, a.n_global = n, 0
+    grid = lib.b200rl_mlp_grid(a.mlp, n, 3)
+    assert grid > 0
+    keep = dict(params=dev(flat, np.float32), obs=dev(obs, np.float32), actions=dev(act, np.float32))
+    for k, v in (("log_std", log_std), ("old_out", old_out), ("adv_raw", adv_raw), ("old_logp", old_logp)):
+        if v is not None:
+            keep[k] = dev(v, np.float32)
+    out = torch.full((max(n, 1) * sizes[-1],), float("nan"), dtype=torch.float32, device="cuda")
+    rows = torch.full((max(n, 1),), float("nan"), dtype=torch.float32, device="cuda")
+    sp = torch.full((grid * N_SCALARS,), float("nan"), dtype=torch.float64, device="cuda")  # every row must be written
+    for k, t in keep.items():
+        setattr(a, k, t.data_ptr())
+    a.out_full, a.row_out, a.scalar_partials = out.data_ptr(), rows.data_ptr(), sp.data_ptr()
+    check(lib.b200rl_mlp_loss_grad(C.byref(a), stream()), "mlp_loss_grad(forward)")
+    scal = torch.zeros(N_SCALARS, dtype=torch.float64, device="cuda")
+    check(lib.b200rl_reduce_partials(None, p(sp), grid, 0, None, p(scal), 0, None, stream()), "reduce_partials")
+    torch.cuda.synchronize()
+    return dict(out=out[: n * sizes[-1]].cpu().numpy().reshape(n, sizes[-1]), rows=rows[:n].cpu().numpy(),
+                scalars=scal.cpu().numpy())

@@ -351,3 +351,43 @@ def test_empty_launch_contributes_zeros(loss):
     assert not r["scalars"].any()
     if loss == "mse":
         assert not r["grad"].any()
+
+
+# ---- forward-only launches with raw outputs / the true KL (TRPO: old policy's outputs, line-search evaluations) -----
+@pytest.mark.parametrize("sizes,dist", [([27, 64, 64, 8], "gaussian"), ([17, 64, 64, 6], "gaussian"),
+                                        ([4, 64, 64, 2], "categorical"), ([8, 64, 64, 15], "categorical"),
+                                        ([11, 64, 64, 64, 3], "gaussian")])  # last: 4 layers, fp32 kernel
+@pytest.mark.parametrize("n", [1, 129, 1000, 40000])
+@pytest.mark.parametrize("no_tc", [False, True])
+def test_forward_outputs_and_true_kl(sizes, dist, n, no_tc):
+    """trpo.py:158-175: out_full = the network's raw outputs, scalar 6 = sum KL(old || new), scalar 0 = the surrogate
+    loss of the forward-only launch.  Tensor-core variant and fp32 kernel against the oracle."""
+    from gpu_helpers import forward_outputs
+    rng = np.random.default_rng(n + 31 * sizes[-1] + int(no_tc))
+    layers = _net(rng, sizes)
+    old_layers = [(w + 0.03 * rng.standard_normal(w.shape).astype(np.float32), b) for w, b in layers]
+    obs = rng.standard_normal((n, sizes[0])).astype(np.float32)
+    A = sizes[-1]
+    log_std = (-0.5 + 0.1 * rng.standard_normal(A)).astype(np.float32) if dist == "gaussian" else None
+    out_old = O.mlp_forward(old_layers, obs)[0]
+    act = (out_old + np.exp(-0.5) * rng.standard_normal((n, A))).astype(np.float32) if dist == "gaussian" \
+        else rng.integers(0, A, n).astype(np.float32)
+    adv = rng.standard_normal(n).astype(np.float32)
+    old_logp = O.Dist(dist, out_old, log_std).log_prob(act)
+    before = _fallbacks()
+    r = forward_outputs(sizes, O.flatten_layers(layers), obs, dist, act, log_std=log_std, old_out=out_old, adv_raw=adv,
+                        old_logp=old_logp, loss="trpo_surrogate", no_tc=no_tc)
+    assert _fallbacks() == before
+    out_new = O.mlp_forward(layers, obs)[0]
+    assert rel_err(r["out"], out_new) < TOL
+    logp = O.Dist(dist, out_new, log_std).log_prob(act)
+    assert rel_err(r["rows"], logp) < TOL
+    kl = O.dist_kl(dist, out_old, out_new, log_std).astype(np.float64).sum()
+    np.testing.assert_allclose(r["scalars"][6], kl, rtol=2e-5, atol=1e-7 * n)
+    loss = -(np.exp(logp - old_logp).astype(np.float64) * adv).sum()
+    np.testing.assert_allclose(r["scalars"][0], loss, rtol=1e-5, atol=1e-5 * np.abs(adv).sum())
+    assert r["scalars"][5] == n
+    # plain evaluation with out_full only (the old policy's pass)
+    r2 = forward_outputs(sizes, O.flatten_layers(old_layers), obs, dist, act, log_std=log_std, no_tc=no_tc)
+    assert rel_err(r2["out"], out_old) < TOL and rel_err(r2["rows"], old_logp) < TOL
+    assert r2["scalars"][6] == 0.0

@@ -122,10 +122,13 @@ def test_data_parallel_update_matches_oracle_and_single_engine(max_kl):
         e.close()
 
 
-def test_data_parallel_peer_exchange_two_engines_one_gpu():
+def test_data_parallel_peer_exchange_two_engines_one_gpu(monkeypatch):
     """The one-shot gradient exchange over peer-mapped memory (reduce_adam3 modes 3 / 4 + wait_peers_kernel), driven
     by two engines on one GPU: each on its own stream and host thread, exchange buffers attached by raw pointer (on a
-    multi-GPU node the pointers come from CUDA IPC handles, tests/dist_check.py).  Same bars as the hook-based run."""
+    multi-GPU node the pointers come from CUDA IPC handles, tests/dist_check.py).  Same bars as the hook-based run.
+    The single-launch form (mode 5) waits inside a grid that fills the device; two ranks SHARING one GPU would starve
+    each other's step kernel, so this test pins the three-launch form -- mode 5 is covered by tests/dist_check.py."""
+    monkeypatch.setenv("B200RL_PEER_ONE_LAUNCH", "0")
     from rl_replicas_b200 import synthetic
     from rl_replicas_b200.engine import OLD_POLICY, POLICY, VALUE, OnPolicyEngine
     rng = np.random.default_rng(1)
