@@ -426,6 +426,18 @@ def main():
         ms_update = ev0.elapsed_time(ev1)
         eng = trpo._engine
         hp3 = trpo._hparams(eng, 0)
+        # the update alone, batch resident in HBM (what `value` is for PPO): b200rl_trpo_update on the loaded batch
+        cg_kw = trpo.policy.optimizer.hyper_parameters()
+        eng.trpo_update(hp3, **cg_kw)
+        torch.cuda.synchronize()
+        ms_res = []
+        for _ in range(3):
+            ev0.record()
+            eng.trpo_update(hp3, **cg_kw)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_res.append(ev0.elapsed_time(ev1))
+        ms_resident = float(np.median(ms_res))
         eng.run_stage("fvp", hp3)
         torch.cuda.synchronize()
         ev0.record()
@@ -437,7 +449,9 @@ def main():
         flop_fvp = 2 * 6336 * 2 + 2 * (6336 + 4608) + 2 * (6336 + 4608)  # tangent fwd (2 products/layer) + fwd + bwd
         ts = trpo.last_trpo_stats
         return {"workload": "TRPO synthetic Ant-shaped obs(27) act(8), 1024 envs x 1000 steps, 10 CG iterations",
+                "ms_per_update": ms_resident, "transitions_per_s": E * T / (ms_resident * 1e-3),
                 "ms_per_update_e2e": ms_update, "transitions_per_s_e2e": E * T / (ms_update * 1e-3),
+                "e2e_note": "TRPO.train on a batch of pageable numpy arrays: the 156 MB host-to-device copy is inside",
                 "ms_per_fvp": ms_fvp, "fvp_per_s": 1e3 / ms_fvp, "fvp_launches": int(ts.fvp_launches),
                 "fvp_tflops_fp32": flop_fvp * E * T / (ms_fvp * 1e-3) / 1e12,
                 "accepted_ratio_index": int(ts.accepted_index), "rejected": int(ts.rejected), "kl": ts.kl,

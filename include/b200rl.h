@@ -350,9 +350,10 @@ int b200rl_offpolicy_set_adam(b200rl_offpolicy* h, int which, const float* exp_a
                               int64_t step, void* stream);
 int b200rl_offpolicy_get_adam(b200rl_offpolicy* h, int which, float* exp_avg, float* exp_avg_sq, int64_t n,
                               int64_t* step, void* stream);
-/* The whole learner state in one call and one synchronisation (what TD3.train / DDPG.train move per call): blob = the
- * parameters of every present network 0..5 in order, then exp_avg and exp_avg_sq of optimizers 0..2; steps[3] = the
- * Adam step counts.  b200rl_offpolicy_state_floats = length of the blob. */
+/* The whole learner state in one call, one copy and one synchronisation (what TD3.train / DDPG.train move per call):
+ * blob = the parameters of every present network 0..5 in order, then exp_avg and exp_avg_sq of optimizers 0..2, EVERY
+ * SEGMENT PADDED to a multiple of 64 floats (the padding carries no meaning); steps[3] =
+ * the Adam step counts.  b200rl_offpolicy_state_floats = length of the blob.  Page-locked blobs copy by DMA. */
 int64_t b200rl_offpolicy_state_floats(b200rl_offpolicy* h);
 int b200rl_offpolicy_get_state(b200rl_offpolicy* h, float* blob, int64_t n_floats, int64_t* steps, void* stream);
 int b200rl_offpolicy_set_state(b200rl_offpolicy* h, const float* blob, int64_t n_floats, const int64_t* steps,

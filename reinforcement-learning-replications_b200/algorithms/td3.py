@@ -15,7 +15,7 @@ from .._lib import OffPolicyHparams
 from ..engine import OffPolicyEngine
 from ..metrics_manager import MetricsManager
 from ..utils import add_noise_to_get_action
-from ._onpolicy import adam_hparams, describe_mlp, flat_params, read_adam_state, write_adam_state, write_flat
+from ._onpolicy import adam_hparams, describe_mlp
 
 logger = logging.getLogger(__name__)
 
@@ -67,9 +67,16 @@ class _OffPolicyBase:
     # user may edit or load weights), so every call moves the whole learner state down and up again -- as ONE blob per
     # direction with one synchronisation each (24 separate synchronous copies per call before: the transfers cost more
     # than the 50 train steps between them).
-    def _tensor_slots(self, e, trainable, targets, lins):
-        """[(host tensor or (optimizer, param, key), offset, count)] in the engine's blob order."""
+    def _state_plan(self, e, trainable, targets, lins):
+        """[(kind, host parameter, owning module, view into the engine's host blob)] in blob order, built once per
+        (engine, networks): the blob is persistent (page-locked), so the views stay valid between calls."""
+        key = (id(e),) + tuple(id(l) for ls in lins for l in ls)
+        plan = getattr(self, "_plan", None)
+        if plan is not None and plan[0] == key:
+            return plan[1]
         layout, total = e.state_layout()
+        blob = e.state_buffer()
+        assert blob.numel() == total
         mods = {i: (m, l) for i, (m, l) in enumerate(zip(trainable, lins))}
         mods.update({3 + i: (m, l) for i, (m, l) in enumerate(zip(targets, lins[len(trainable):]))})
         slots = []
@@ -78,38 +85,51 @@ class _OffPolicyBase:
             o = off
             for lin in l:
                 for p_ in (lin.weight, lin.bias):
-                    slots.append((kind, p_, m, o, p_.numel()))
+                    slots.append((kind, p_, m, blob[o:o + p_.numel()].view_as(p_)))
                     o += p_.numel()
             assert o == off + count
-        return slots, total
+        self._plan = (key, slots)
+        return slots
+
+    @staticmethod
+    def _adam_step_count(optimizer, linears) -> int:
+        ps = [t for l in linears for t in (l.weight, l.bias)]
+        if not all(p_ in optimizer.state and "exp_avg" in optimizer.state[p_] for p_ in ps):
+            return 0
+        steps = {int(float(optimizer.state[p_]["step"])) for p_ in ps}
+        if len(steps) != 1:
+            raise NotImplementedError("parameters of one optimizer have different step counts")
+        return steps.pop()
 
     def _upload_state(self, e, trainable, targets, lins) -> None:
-        slots, total = self._tensor_slots(e, trainable, targets, lins)
+        slots = self._state_plan(e, trainable, targets, lins)
         steps = [0, 0, 0]
         for i, (m, l) in enumerate(zip(trainable, lins)):
             adam_hparams(m.optimizer, l, "optimizer")  # refuses anything but a plain Adam over exactly this network
-            _, _, steps[i] = read_adam_state(m.optimizer, l)
-        pieces = []
-        with torch.no_grad():
-            for kind, p_, m, off, n in slots:  # slots come in blob order: ONE concatenation builds the blob
-                if kind == "params":
-                    pieces.append(p_.detach().reshape(-1))
-                else:
-                    st = m.optimizer.state.get(p_)
-                    pieces.append(st["exp_avg" if kind == "m" else "exp_avg_sq"].reshape(-1)
-                                  if st and "exp_avg" in st else torch.zeros(n))
-            blob = torch.cat(pieces).float()
-        assert blob.numel() == total
-        e.set_state(blob.numpy(), steps)
-
-    def _download_state(self, e, trainable, targets, lins) -> None:
-        slots, _ = self._tensor_slots(e, trainable, targets, lins)
-        blob, steps = e.get_state()
-        src = torch.from_numpy(blob)
+            steps[i] = self._adam_step_count(m.optimizer, l)
         index = {id(m): i for i, m in enumerate(trainable)}
         dsts, srcs = [], []
-        for kind, p_, m, off, n in slots:
-            view = src[off:off + n].view_as(p_)
+        with torch.no_grad():
+            for kind, p_, m, view in slots:
+                if kind == "params":
+                    src = p_.detach()
+                else:
+                    st = m.optimizer.state.get(p_) if steps[index[id(m)]] > 0 else None
+                    src = st["exp_avg" if kind == "m" else "exp_avg_sq"] if st else None
+                if src is None:
+                    view.zero_()
+                else:
+                    dsts.append(view)
+                    srcs.append(src)
+            torch._foreach_copy_(dsts, srcs)  # one call fills the page-locked blob
+        e.set_state(None, steps)
+
+    def _download_state(self, e, trainable, targets, lins) -> None:
+        slots = self._state_plan(e, trainable, targets, lins)
+        _, steps = e.get_state()
+        index = {id(m): i for i, m in enumerate(trainable)}
+        dsts, srcs = [], []
+        for kind, p_, m, view in slots:
             if kind == "params":
                 dsts.append(p_.data)
                 srcs.append(view)
@@ -125,7 +145,11 @@ class _OffPolicyBase:
             else:
                 st[key] = view.clone()
             if kind == "m":
-                st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
+                cur = st.get("step")
+                if torch.is_tensor(cur) and cur.dim() == 0 and not cur.is_cuda:
+                    cur.fill_(float(step))
+                else:
+                    st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
         with torch.no_grad():
             torch._foreach_copy_(dsts, srcs)  # one call for all tensors
 

@@ -64,11 +64,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libb200rl.so")
-    r = subprocess.run([nvcc, "--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB]
+    tmp = LIB + ".tmp"  # link beside the target and rename: a reader never sees a half-written library
+    r = subprocess.run([nvcc, "--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp]
                        + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("linking libb200rl.so failed")
+    os.replace(tmp, LIB)
     return LIB
 
 

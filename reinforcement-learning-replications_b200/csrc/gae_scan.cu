@@ -18,6 +18,8 @@
 //           prefetches the next tile (cp.async) and finds its episode range while the scan warps work.
 // HBM traffic = algorithmic traffic: read r (4 or 8 B) + v (4 B), write adv (4 B) + ret (4 B) per transition.
 // All carries are float64 (the reference scans in float64, utils.py:28); outputs are cast to float32 like ppo.py:151,160.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200rl {
@@ -519,11 +521,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) gae_scan_kernel(const ScanArg
 // (hundreds to millions of episodes of up to a few thousand steps); the tile kernel above covers few / very long
 // episodes.  Per-episode advantage statistics go to ep_partial[e]; the last CTA sums them in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int EP_WARPS = 8;
-constexpr int EP_STAGES = 4;  // chunks in flight per warp (cp.async ring)
+#ifndef B200RL_EP_WARPS  // overridable for A/B builds (tools/scan_variants.sh)
+#define B200RL_EP_WARPS 8
+#endif
+#ifndef B200RL_EP_STAGES
+#define B200RL_EP_STAGES 4
+#endif
+#ifndef B200RL_EP_CTAS
+#define B200RL_EP_CTAS 2
+#endif
+constexpr int EP_WARPS = B200RL_EP_WARPS;
+constexpr int EP_STAGES = B200RL_EP_STAGES;  // chunks in flight per warp (cp.async ring)
+constexpr int EP_CTAS = B200RL_EP_CTAS;      // CTAs per SM the grid is sized for
+#ifndef B200RL_EP_MINB
+#define B200RL_EP_MINB 2                     // min resident CTAs per SM the compiler must fit (register cap)
+#endif
 
 template <typename RewT>
-__global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const ScanArgs p, double2* ep_partial) {
+__global__ void __launch_bounds__(EP_WARPS * 32, B200RL_EP_MINB) gae_scan_episode_kernel(const ScanArgs p, double2* ep_partial) {
   extern __shared__ __align__(16) unsigned char ep_smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: episode loops and bounds stay uniform
@@ -600,6 +615,7 @@ __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const S
   for (long long e = (long long)blockIdx.x * EP_WARPS + warp; e < p.n_ep; e += n_warps) {
     const long long beg = nbeg, end = nend;
     const long long bot = beg & ~7LL;
+    const bool aligned = ((beg | end) & 7LL) == 0;  // warp-uniform
     const float vl = nvl;
     const double boot = ndn ? 0.0 : p.gamma * (double)vl;  // utils.py:81-85 + ppo.py:149
     if (e + n_warps < p.n_ep) {
@@ -612,6 +628,10 @@ __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const S
     float v_first_prev = vl;              // value of that item (v_{i+1} of this chunk's last item)
     double s1 = 0.0, s2 = 0.0;
     long long cs = ((end + 7) & ~7LL) - 256;
+    // Two copies of the chunk loop: episodes whose bounds are multiples of 8 items (every fixed-horizon batch) never
+    // need the per-item masks of the general one.
+    auto run_chunks = [&](auto aligned_tag) {
+    constexpr bool ALIGNED = decltype(aligned_tag)::value;
     do {
       const long long i0 = cs + lane * SCAN_ITEMS;
       double r[SCAN_ITEMS];
@@ -658,7 +678,17 @@ __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const S
       }
       const bool edge = cs < beg || cs + 256 >= end;  // warp-uniform: chunk holds masked items or the last step
       int lo = 0, hi = SCAN_ITEMS;
-      if (edge) {
+      bool lane_off = false;
+      if (ALIGNED && edge) {
+        // episode bounds on multiples of 8 items (every fixed-horizon batch): a lane is wholly inside or wholly outside,
+        // and the last step is item 7 of one lane -- no per-item masks
+        lane_off = i0 < beg || i0 >= end;
+        if (lane_off) lo = hi = SCAN_ITEMS;
+        if (i0 + SCAN_ITEMS == end) {  // last step: delta uses V(last_obs) even when done; the return bootstraps if not done
+          d[SCAN_ITEMS - 1] = (r[SCAN_ITEMS - 1] + (double)__fmul_rn(p.gamma_f, vl)) - (double)v[SCAN_ITEMS - 1];
+          r[SCAN_ITEMS - 1] += boot;
+        }
+      } else if (!ALIGNED && edge) {
         lo = (int)min(max(beg - i0, 0LL), (long long)SCAN_ITEMS);
         hi = (int)max(min(end - i0, (long long)SCAN_ITEMS), 0LL);
         const long long jl64 = end - 1 - i0;
@@ -679,6 +709,10 @@ __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const S
       for (int j = SCAN_ITEMS - 2; j >= 0; --j) {
         tr = r[j] + p.gamma * tr;
         ta = d[j] + p.gl * ta;
+      }
+      if (ALIGNED && lane_off) {  // a lane outside the episode contributes nothing (select, not multiply: its data may be anything)
+        tr = 0.0;
+        ta = 0.0;
       }
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
@@ -734,6 +768,9 @@ __global__ void __launch_bounds__(EP_WARPS * 32) gae_scan_episode_kernel(const S
       v_first_prev = __shfl_sync(0xffffffffu, v[0], 0);
       cs -= 256;
     } while (cs + 256 > bot);
+    };
+    if (aligned) run_chunks(std::true_type{});
+    else run_chunks(std::false_type{});
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) ep_partial[e] = make_double2(s1, s2);
@@ -851,7 +888,7 @@ extern "C" int b200rl_gae_scan(const void* rewards, int rewards_f64, const float
   const bool by_episode = n_ep >= 256 && n_ep <= n / 16 && n / n_ep <= 32768;
   if (by_episode) {
     double2* ep_partial = reinterpret_cast<double2*>(reinterpret_cast<char*>(a.partial) + (size_t)tiles * sizeof(double2));
-    const int grid = (int)std::min<long long>((n_ep + EP_WARPS - 1) / EP_WARPS, 2LL * device_sm_count());
+    const int grid = (int)std::min<long long>((n_ep + EP_WARPS - 1) / EP_WARPS, (long long)EP_CTAS * device_sm_count());
     const int smem64 = EP_WARPS * EP_STAGES * (256 * 8 + 1024), smem32 = EP_WARPS * EP_STAGES * (256 * 4 + 1024);
     static bool configured = false;
     if (!configured) {

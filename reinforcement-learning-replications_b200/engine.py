@@ -373,30 +373,52 @@ class OffPolicyEngine:
 
     # ---- whole state in one transfer ----
     def state_layout(self):
-        """[(kind, net index, offset, count)] of the state blob: ("params", 0..5) then ("m" / "v", 0..2)."""
+        """[(kind, net index, offset, count)] of the state blob: ("params", 0..5) then ("m" / "v", 0..2); every
+        segment starts on a multiple of 64 floats (b200rl.h)."""
+        pad = lambda n: (n + 63) & ~63
         present = [0, 1] + ([2] if self.n_q == 2 else []) + [3, 4] + ([5] if self.n_q == 2 else [])
         out, off = [], 0
         for i in present:
             out.append(("params", i, off, self._n(i)))
-            off += self._n(i)
+            off += pad(self._n(i))
         for i in [0, 1] + ([2] if self.n_q == 2 else []):
             for kind in ("m", "v"):
                 out.append((kind, i, off, self._n(i)))
-                off += self._n(i)
+                off += pad(self._n(i))
         assert off == int(self.lib.b200rl_offpolicy_state_floats(self.h))
         return out, off
 
-    def get_state(self):
-        _, n = self.state_layout()
-        blob = np.empty(n, dtype=np.float32)
-        steps = (C.c_int64 * 3)()
-        check(self.lib.b200rl_offpolicy_get_state(self.h, _ptr(blob), n, steps, current_stream_handle()), "get_state")
-        return blob, [int(x) for x in steps]
+    def state_buffer(self):
+        """The engine's persistent host-side state blob (a float32 torch tensor, page-locked when CUDA allows it): filled
+        by ``get_state()``, sent by ``set_state()``.  Views into it stay valid for the engine's lifetime."""
+        import torch
+        buf = getattr(self, "_state_buf", None)
+        if buf is None:
+            n = int(self.lib.b200rl_offpolicy_state_floats(self.h))
+            buf = torch.zeros(n, dtype=torch.float32)
+            try:
+                buf = buf.pin_memory()
+            except RuntimeError:  # pragma: no cover  (no page-locked memory available)
+                pass
+            self._state_buf = buf
+        return buf
 
-    def set_state(self, blob: np.ndarray, steps):
-        blob = _c(blob, np.float32)
+    def get_state(self):
+        """Device -> the persistent blob; returns (blob as numpy view, [3 Adam step counts])."""
+        buf = self.state_buffer()
+        steps = (C.c_int64 * 3)()
+        check(self.lib.b200rl_offpolicy_get_state(self.h, C.c_void_p(buf.data_ptr()), buf.numel(), steps,
+                                                  current_stream_handle()), "get_state")
+        return buf.numpy(), [int(x) for x in steps]
+
+    def set_state(self, blob, steps):
+        """``blob`` = None sends the persistent blob (fill ``state_buffer()`` first), else any float32 array of that size."""
+        buf = self.state_buffer()
+        if blob is not None and not (isinstance(blob, np.ndarray) and blob.ctypes.data == buf.data_ptr()):
+            buf.numpy()[:] = np.asarray(blob, dtype=np.float32).reshape(-1)
         st = (C.c_int64 * 3)(*[int(x) for x in steps])
-        check(self.lib.b200rl_offpolicy_set_state(self.h, _ptr(blob), blob.size, st, current_stream_handle()), "set_state")
+        check(self.lib.b200rl_offpolicy_set_state(self.h, C.c_void_p(buf.data_ptr()), buf.numel(), st,
+                                                  current_stream_handle()), "set_state")
 
     def train(self, hp, obs, act, rew, next_obs, done, noise=None):
         """obs/next_obs [S,B,O], act [S,B,A], rew/done [S,B], noise [S,B,A] or None -> dict of logged quantities."""

@@ -131,7 +131,8 @@ def forward_outputs(sizes, flat, obs, dist, act, log_std=None, old_out=None, adv
     a.out_full, a.row_out, a.scalar_partials = out.data_ptr(), rows.data_ptr(), sp.data_ptr()
     check(lib.b200rl_mlp_loss_grad(C.byref(a), stream()), "mlp_loss_grad(forward)")
     scal = torch.zeros(N_SCALARS, dtype=torch.float64, device="cuda")
-    check(lib.b200rl_reduce_partials(None, p(sp), grid, 0, None, p(scal), 0, None, stream()), "reduce_partials")
+    check(lib.b200rl_reduce_partials(None, p(sp), grid, int(lib.b200rl_mlp_param_count(a.mlp)), None, p(scal), 0, None,
+                                     stream()), "reduce_partials")
     torch.cuda.synchronize()
     return dict(out=out[: n * sizes[-1]].cpu().numpy().reshape(n, sizes[-1]), rows=rows[:n].cpu().numpy(),
                 scalars=scal.cpu().numpy())

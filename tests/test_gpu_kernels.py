@@ -383,7 +383,8 @@ def test_forward_outputs_and_true_kl(sizes, dist, n, no_tc):
     logp = O.Dist(dist, out_new, log_std).log_prob(act)
     assert rel_err(r["rows"], logp) < TOL
     kl = O.dist_kl(dist, out_old, out_new, log_std).astype(np.float64).sum()
-    np.testing.assert_allclose(r["scalars"][6], kl, rtol=2e-5, atol=1e-7 * n)
+    # per-row KL is a sum of terms that cancel to ~1e-3 of their size: 5e-7 absolute per row is float32 rounding
+    np.testing.assert_allclose(r["scalars"][6], kl, rtol=2e-5, atol=5e-7 * n)
     loss = -(np.exp(logp - old_logp).astype(np.float64) * adv).sum()
     np.testing.assert_allclose(r["scalars"][0], loss, rtol=1e-5, atol=1e-5 * np.abs(adv).sum())
     assert r["scalars"][5] == n

@@ -148,11 +148,13 @@ def test_train_vs_oracle_benchmark_shape(twin):
         assert v < 2e-5, (k, v, errs)  # north_star: 1e-5 per tensor; 2e-5 after ten Adam steps of three networks
 
 
-def test_device_replay_gather_and_graph_replay_match_the_staged_path():
-    """b200rl_offpolicy_train_gather (replay columns in HBM, only indices uploaded) and the CUDA-graph replay of the
-    S-step loop give bit-identical results to host-staged minibatches run with plain launches."""
+@pytest.mark.parametrize("twin", [True, False])
+def test_device_replay_graph_replay_and_the_persistent_kernel_match_the_staged_path(twin):
+    """b200rl_offpolicy_train_gather (replay columns in HBM, only indices uploaded), the CUDA-graph replay of the
+    S-step loop and the persistent step kernel (one cooperative launch for all S steps, concat / target smoothing /
+    TD target fused into its GEMM tiles) give BIT-IDENTICAL results to host-staged minibatches run with plain launches
+    of one kernel per operation.  TD3 (twin critics, delayed policy step, smoothing noise) and DDPG."""
     import os
-    from rl_replicas_b200.algorithms._onpolicy import describe_mlp, flat_params
     from rl_replicas_b200.experience import Experience
     rng = np.random.default_rng(3)
     H, S, B = 64, 6, 32
@@ -168,31 +170,36 @@ def test_device_replay_gather_and_graph_replay_match_the_staged_path():
     ex.dones = [[bool(x) for x in (rng.random(n) < 0.01)]]
     ex.last_observations = [obs[n]]
 
-    def run(device_replay, graph):
+    def run(device_replay, graph, mega):
         os.environ["B200RL_OFFPOLICY_GRAPH"] = "1" if graph else "0"
-        algo, rb = build(True, H, p0, [q10, q20])
+        os.environ["B200RL_OFFPOLICY_MEGAKERNEL"] = "1" if mega else "0"
+        algo, rb = build(twin, H, p0, [q10, q20] if twin else [q10])
         rb.add_experience(ex)
         algo.use_device_replay = device_replay  # False: minibatches gathered on the host and uploaded
         outs = []
-        for call in range(3):  # the 2nd and 3rd calls replay the captured graph
+        for call in range(3):  # the 2nd and 3rd calls replay the captured graph / the compiled program
             np.random.seed(10 + call)
             torch.manual_seed(10 + call)
-            algo.train(rb, S, B)
+            algo.train(rb, S + (call == 2), B)  # the third call changes the shape: graph / program are rebuilt
             outs.append(algo.last_train_output)
-        nets = [flat(m.network) for m in (algo.policy, algo.q_function_1, algo.q_function_2)]
+        qs = (algo.q_function_1, algo.q_function_2) if twin else (algo.q_function,)
+        tq = (algo.target_q_function_1, algo.target_q_function_2) if twin else (algo.target_q_function,)
+        nets = [flat(m.network) for m in (algo.policy, algo.target_policy) + qs + tq]
         return outs, nets
 
     try:
-        ref_outs, ref_nets = run(False, False)
-        for dev, graph in ((True, True), (False, True), (True, False)):
-            outs, nets = run(dev, graph)
+        ref_outs, ref_nets = run(False, False, False)
+        for dev, graph, mega in ((True, True, False), (False, True, False), (True, False, False), (True, False, True),
+                                 (False, False, True)):
+            outs, nets = run(dev, graph, mega)
             for a, b in zip(outs, ref_outs):
                 for k in a:
-                    np.testing.assert_array_equal(a[k], b[k])
-            for a, b in zip(nets, ref_nets):
-                np.testing.assert_array_equal(a, b)
+                    np.testing.assert_array_equal(a[k], b[k], err_msg=f"{k} dev={dev} graph={graph} mega={mega}")
+            for i, (a, b) in enumerate(zip(nets, ref_nets)):
+                np.testing.assert_array_equal(a, b, err_msg=f"net {i} dev={dev} graph={graph} mega={mega}")
     finally:
         os.environ.pop("B200RL_OFFPOLICY_GRAPH", None)
+        os.environ.pop("B200RL_OFFPOLICY_MEGAKERNEL", None)
 
 
 def test_train_gather_rejects_indices_outside_the_replay_columns():
@@ -210,3 +217,40 @@ def test_train_gather_rejects_indices_outside_the_replay_columns():
     idx[1, 3] = rows  # one past the end
     with pytest.raises(B200RLError, match="outside"):
         eng.train_gather(algo._hparams(True, 2), cols, rows, idx, np.zeros((2, 8, A_DIM), np.float32))
+
+
+@pytest.mark.parametrize("n_q", [1, 2])
+def test_state_blob_round_trip_matches_the_per_network_accessors(n_q):
+    """b200rl_offpolicy_get_state / set_state move every network and Adam state in one copy (segments padded to 64
+    floats); the per-network accessors see the same values, and a blob written back reproduces itself."""
+    from rl_replicas_b200.engine import OffPolicyEngine
+    rng = np.random.default_rng(n_q)
+    e = OffPolicyEngine([11, 40, 24, 3], [14, 40, 24, 1], n_q, 32, 4)
+    layout, total = e.state_layout()
+    assert total % 64 == 0 and all(off % 64 == 0 for _, _, off, _ in layout)
+    blob = np.full(total, np.nan, np.float32)  # padding stays NaN: it must never be read
+    want = {}
+    for kind, i, off, n in layout:
+        x = rng.standard_normal(n).astype(np.float32)
+        if kind == "v":
+            x = np.abs(x)
+        blob[off:off + n] = x
+        want[(kind, i)] = x
+    steps = [3, 5, 7 if n_q == 2 else 0]
+    e.set_state(blob, steps)
+    for (kind, i), x in want.items():
+        if kind == "params":
+            np.testing.assert_array_equal(e.get_params(i), x)
+    for i in range(1 + n_q):
+        m, v, step = e.get_adam(i)
+        np.testing.assert_array_equal(m, want[("m", i)])
+        np.testing.assert_array_equal(v, want[("v", i)])
+        assert step == steps[i]
+    # per-network writes show up in the blob
+    newp = rng.standard_normal(want[("params", 1)].size).astype(np.float32)
+    e.set_params(1, newp)
+    back, steps_back = e.get_state()
+    assert steps_back[:1 + n_q] == steps[:1 + n_q]
+    for kind, i, off, n in layout:
+        np.testing.assert_array_equal(back[off:off + n], newp if (kind, i) == ("params", 1) else want[(kind, i)])
+    e.close()

@@ -26,3 +26,21 @@ trpo.train_packed(b)
 z.record()
 torch.cuda.synchronize()
 print("TRPO update ms", a.elapsed_time(z), "launches", trpo.last_update_stats.kernel_launches, "accepted", trpo.last_trpo_stats.accepted_index)
+eng = trpo._engine
+hp = trpo._hparams(eng, 0)
+kw = trpo.policy.optimizer.hyper_parameters()
+eng.trpo_update(hp, **kw)
+torch.cuda.synchronize()
+a.record()
+stats, ts = eng.trpo_update(hp, **kw)
+z.record()
+torch.cuda.synchronize()
+print("TRPO update, batch resident: ms", a.elapsed_time(z), "launches", stats.kernel_launches, "fvp", ts.fvp_launches)
+eng.run_stage("fvp", hp)
+torch.cuda.synchronize()
+a.record()
+for _ in range(10):
+    eng.run_stage("fvp", hp)
+z.record()
+torch.cuda.synchronize()
+print("F v launch: ms", a.elapsed_time(z) / 10)
