@@ -364,6 +364,12 @@ def main():
             ncu = json.load(f)
     except Exception:
         pass
+    ncu_scan = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_scan_ncu.json")) as f:
+            ncu_scan = json.load(f)
+    except Exception:
+        pass
     scan_reps = 20
     engine.run_stage("values", hp)
     ms_scan_pair = stage_ms("scan", scan_reps)
@@ -479,12 +485,13 @@ def main():
         rb.add_experience(store)
         S4, B4 = 50, 256
         algo.train(rb, S4, B4)
-        t0 = time.perf_counter()
         reps = 5
-        for _ in range(reps):
-            algo.train(rb, S4, B4)
-        torch.cuda.synchronize()
-        ms_call = (time.perf_counter() - t0) * 1e3 / reps
+        calls = []
+        for _ in range(12):
+            t0 = time.perf_counter()
+            algo.train(rb, S4, B4)  # returns after the read-back of the logged values: synchronous
+            calls.append((time.perf_counter() - t0) * 1e3)
+        ms_call = float(np.median(calls))
         # device part only: replay the last staged minibatches through the engine
         eng = algo._engine
         mbs = [rb.sample_minibatch(B4) for _ in range(S4)]
@@ -501,6 +508,7 @@ def main():
         return {"workload": "TD3 synthetic Hopper-shaped (obs 11, act 3), minibatch 256, MLP(256,256), 50 train steps/call, "
                             "replay 1 M transitions (device-resident columns)",
                 "ms_per_train_call_e2e": ms_call, "train_steps_per_s_e2e": S4 / (ms_call * 1e-3),
+                "ms_per_train_call_e2e_mean": float(np.mean(calls)), "ms_per_train_call_e2e_max": float(np.max(calls)),
                 "transitions_per_s_e2e": S4 * B4 / (ms_call * 1e-3),
                 "ms_per_train_call_engine": ms_dev, "train_steps_per_s_engine": S4 / (ms_dev * 1e-3),
                 "note": "e2e = TD3.train(replay_buffer, 50, 256): host index draws with the reference's numpy stream, "
@@ -564,9 +572,11 @@ def main():
                               "bytes_per_transition": 20, "ms_per_launch": ms_scan_pair,
                               "note": "16.4 MB problem: launch-latency bound at this size (SURVEY 7.3-3)"},
             "roofline_scan_large": {"kernel": "gae_scan_episode_kernel<double>", "bound": "hbm", "achieved": gbs_big,
-                                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_big / pk["hbm"], "traffic": 1.269e9,
-                                    "traffic_note": "ncu --set full, profiles/r01_tc2_summary.md section 5 "
-                                                    "(algorithmic 1.311 GB)",
+                                    "peak": pk["hbm"], "unit": "GB/s", "frac": gbs_big / pk["hbm"],
+                                    "traffic": ncu_scan.get("dram_bytes_per_launch"),
+                                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                                    "capture at this shape (profiles/r02_scan_ncu.json; algorithmic "
+                                                    "1.311 GB, the last written lines are still in L2 when it ends)",
                                     "transitions": n_big, "bytes_per_transition": 20, "ms_per_launch": ms_big,
                                     "note": "65536 episodes x 1000 steps: 1.31 GB of algorithmic traffic (> L2)"},
             "update_flops_per_transition": FLOP_PER_TRANSITION,

@@ -68,7 +68,7 @@ class _OffPolicyBase:
     # direction with one synchronisation each (24 separate synchronous copies per call before: the transfers cost more
     # than the 50 train steps between them).
     def _state_plan(self, e, trainable, targets, lins):
-        """[(kind, host parameter, owning module, view into the engine's host blob)] in blob order, built once per
+        """[(kind, host parameter, owning module, numpy view into the engine's host blob)] in blob order, built once per
         (engine, networks): the blob is persistent (page-locked), so the views stay valid between calls."""
         key = (id(e),) + tuple(id(l) for ls in lins for l in ls)
         plan = getattr(self, "_plan", None)
@@ -77,6 +77,7 @@ class _OffPolicyBase:
         layout, total = e.state_layout()
         blob = e.state_buffer()
         assert blob.numel() == total
+        blob_np = blob.numpy()  # shares the page-locked memory
         mods = {i: (m, l) for i, (m, l) in enumerate(zip(trainable, lins))}
         mods.update({3 + i: (m, l) for i, (m, l) in enumerate(zip(targets, lins[len(trainable):]))})
         slots = []
@@ -85,7 +86,7 @@ class _OffPolicyBase:
             o = off
             for lin in l:
                 for p_ in (lin.weight, lin.bias):
-                    slots.append((kind, p_, m, blob[o:o + p_.numel()].view_as(p_)))
+                    slots.append((kind, p_, m, blob_np[o:o + p_.numel()].reshape(tuple(p_.shape))))
                     o += p_.numel()
             assert o == off + count
         self._plan = (key, slots)
@@ -101,6 +102,9 @@ class _OffPolicyBase:
             raise NotImplementedError("parameters of one optimizer have different step counts")
         return steps.pop()
 
+    # The copies between the host modules and the page-locked blob are plain numpy copies on purpose: torch's CPU copy
+    # kernels go parallel above 32768 elements (the 256 x 256 weights), and on a many-core host the OpenMP workers that
+    # linger after such a region cost the calling thread tens of milliseconds every few train() calls.
     def _upload_state(self, e, trainable, targets, lins) -> None:
         slots = self._state_plan(e, trainable, targets, lins)
         steps = [0, 0, 0]
@@ -108,50 +112,41 @@ class _OffPolicyBase:
             adam_hparams(m.optimizer, l, "optimizer")  # refuses anything but a plain Adam over exactly this network
             steps[i] = self._adam_step_count(m.optimizer, l)
         index = {id(m): i for i, m in enumerate(trainable)}
-        dsts, srcs = [], []
-        with torch.no_grad():
-            for kind, p_, m, view in slots:
-                if kind == "params":
-                    src = p_.detach()
-                else:
-                    st = m.optimizer.state.get(p_) if steps[index[id(m)]] > 0 else None
-                    src = st["exp_avg" if kind == "m" else "exp_avg_sq"] if st else None
-                if src is None:
-                    view.zero_()
-                else:
-                    dsts.append(view)
-                    srcs.append(src)
-            torch._foreach_copy_(dsts, srcs)  # one call fills the page-locked blob
+        for kind, p_, m, view in slots:
+            if kind == "params":
+                src = p_.detach()
+            else:
+                st = m.optimizer.state.get(p_) if steps[index[id(m)]] > 0 else None
+                src = st["exp_avg" if kind == "m" else "exp_avg_sq"] if st else None
+            if src is None:
+                view.fill(0.0)
+            else:
+                np.copyto(view, src.numpy(), casting="same_kind")
         e.set_state(None, steps)
 
     def _download_state(self, e, trainable, targets, lins) -> None:
         slots = self._state_plan(e, trainable, targets, lins)
         _, steps = e.get_state()
         index = {id(m): i for i, m in enumerate(trainable)}
-        dsts, srcs = [], []
         for kind, p_, m, view in slots:
             if kind == "params":
-                dsts.append(p_.data)
-                srcs.append(view)
+                np.copyto(p_.detach().numpy(), view, casting="same_kind")
                 continue
             step = steps[index[id(m)]]
             if step == 0:
                 continue
             st = m.optimizer.state[p_]
             key = "exp_avg" if kind == "m" else "exp_avg_sq"
-            if key in st and st[key].shape == p_.shape:
-                dsts.append(st[key])
-                srcs.append(view)
+            if key in st and st[key].shape == p_.shape and not st[key].is_cuda:
+                np.copyto(st[key].numpy(), view, casting="same_kind")
             else:
-                st[key] = view.clone()
+                st[key] = torch.from_numpy(view.copy())
             if kind == "m":
                 cur = st.get("step")
                 if torch.is_tensor(cur) and cur.dim() == 0 and not cur.is_cuda:
                     cur.fill_(float(step))
                 else:
                     st["step"] = torch.tensor(float(step))  # torch keeps the step as a float32 scalar tensor
-        with torch.no_grad():
-            torch._foreach_copy_(dsts, srcs)  # one call for all tensors
 
     def _hparams(self, noisy: bool, delay: int) -> OffPolicyHparams:
         trainable, _ = self._nets()
@@ -181,7 +176,13 @@ class _OffPolicyBase:
         A = self.policy.network.sizes[-1] if hasattr(self.policy.network, "sizes") else describe_mlp(self.policy.network)[0][-1]
         device_replay = (S > 0 and getattr(self, "use_device_replay", True) and hasattr(replay_buffer, "device_columns")
                          and hasattr(replay_buffer, "sample_indices"))
-        noise_of = lambda: torch.stack([torch.randn(B, A) for _ in range(S)]).numpy() if (noisy and S > 0) else None
+        def noise_of():  # S draws of torch.randn(B, A), the reference's stream (td3.py:328), gathered without torch.stack
+            if not (noisy and S > 0):
+                return None
+            out = np.empty((S, B, A), dtype=np.float32)
+            for i in range(S):
+                out[i] = torch.randn(B, A).numpy()
+            return out
         if device_replay:
             # device-resident replay columns: S index draws on the host (the same numpy stream as S sample_minibatch
             # calls); the gather happens on the GPU, only indices and noise cross PCIe

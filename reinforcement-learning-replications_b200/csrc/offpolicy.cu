@@ -175,25 +175,25 @@ __global__ void gather_rows_kernel(const float* table, const long long* idx, int
 }
 
 // y = r + gamma * (1 - d) * min(q1t, q2t)   (td3.py:337-339; ddpg.py:280: single target Q)
-__global__ void td_target_kernel(const float* rew, const float* done, const float* q1t, const float* q2t, float gamma,
-                                 int n, float* y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float q = q2t ? fminf(q1t[i], q2t[i]) : q1t[i];
-  y[i] = rew[i] + gamma * (1.f - done[i]) * q;
+__device__ __forceinline__ float td_target(float rew, float done, float q1t, const float* q2t, int i, float gamma) {
+  const float q = q2t ? fminf(q1t, q2t[i]) : q1t;
+  return rew + gamma * (1.f - done) * q;
 }
 
-// One CTA: loss = mean((q - y)^2), dq = 2 (q - y) / B   (F.mse_loss + backward);  or policy: loss = -mean(q), dq = -1/B
-__global__ void __launch_bounds__(GTHREADS) q_loss_kernel(const float* q, const float* y, int n, float* dq, float* loss_out,
-                                                      float* q_copy) {
+// One CTA: the critic's loss with its TD target computed on the fly: y as above, loss = mean((q - y)^2),
+// dq = 2 (q - y) / B (F.mse_loss + backward), q_copy = q (the logged Q-values);  rew == NULL: the policy loss
+// -mean(q), dq = -1/B
+__global__ void __launch_bounds__(GTHREADS) q_loss_kernel(const float* q, const float* rew, const float* done,
+                                                         const float* q1t, const float* q2t, float gamma, int n,
+                                                         float* dq, float* loss_out, float* q_copy) {
   __shared__ double red[32];
   double acc = 0.0;
   const float inv = 1.0f / (float)n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float qi = q[i];
     if (q_copy) q_copy[i] = qi;
-    if (y) {
-      const float d = qi - y[i];
+    if (rew) {
+      const float d = qi - td_target(rew[i], done[i], q1t[i], q2t, i, gamma);
       acc += (double)d * (double)d;
       dq[i] = (2.f * d) * inv;
     } else {
@@ -212,9 +212,16 @@ __global__ void __launch_bounds__(GTHREADS) q_loss_kernel(const float* q, const 
 }
 
 // target <- rho * target + (1 - rho) * param   (utils.py:47-57: f32 tensors tensor(rho), tensor(1 - rho))
-__global__ void polyak_kernel(float* target, const float* param, float rho, float one_minus_rho, int n) {
+struct PolyakArgs {
+  float* target[3];
+  const float* param[3];
+  int n[3];
+  int n_nets;
+};
+__global__ void polyak_kernel(const PolyakArgs a, float rho, float one_minus_rho) {  // every network in one launch
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) target[i] = rho * target[i] + one_minus_rho * param[i];
+  for (int k = 0; k < a.n_nets; ++k)
+    if (i < a.n[k]) a.target[k][i] = rho * a.target[k][i] + one_minus_rho * a.param[k][i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -311,16 +318,14 @@ __global__ void __launch_bounds__(GTHREADS, 2) offpolicy_mega_kernel(const MkBlo
         if (type == MK_GEMM_NT) gemm_tile<0, 4>(op.g, bx, by, As, Bs);
         else if (type == MK_GEMM_NN) gemm_tile<1, 4>(op.g, bx, by, As, Bs);
         else gemm_tile<2, 4>(op.g, bx, by, As, Bs);
-      } else if (type == MK_TD_LOSS) {  // td_target_kernel + q_loss_kernel of one critic
+      } else if (type == MK_TD_LOSS) {  // q_loss_kernel of one critic
         const int n = op.n;
         const float inv = 1.0f / (float)n;
         double acc = 0.0;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-          const float qt = op.p4 ? fminf(op.p3[i], op.p4[i]) : op.p3[i];
-          const float y = op.p1[i] + op.f0 * (1.f - op.p2[i]) * qt;
           const float qi = op.p0[i];
           op.o2[i] = qi;
-          const float d = qi - y;
+          const float d = qi - td_target(op.p1[i], op.p2[i], op.p3[i], op.p4, i, op.f0);
           acc += (double)d * (double)d;
           op.o0[i] = (2.f * d) * inv;
         }
@@ -394,11 +399,13 @@ struct b200rl_offpolicy {
                                           // 3 target Q2, 4 Q2 (the twin critic runs on a second stream)
   float* acts_tq[B200RL_MAX_LAYERS + 1];  // the persistent kernel: Q1's target critic gets a stack of its own (there the
                                           // critics' first layers run beside the target policy's, which owns stack 0)
-  float *x_cat = nullptr, *x_cat2 = nullptr, *qt1 = nullptr, *qt2 = nullptr, *y = nullptr, *dq = nullptr;
+  float *x_cat = nullptr, *x_cat2 = nullptr, *qt1 = nullptr, *qt2 = nullptr, *dq = nullptr;
   float *dbuf0 = nullptr, *dbuf1 = nullptr;  // gradient ping-pong [B, maxw]
   float *dbuf2 = nullptr, *dbuf3 = nullptr, *dq2 = nullptr;  // the same for the twin critic's branch
   cudaStream_t s2 = nullptr;                // side stream of the twin critic (forked / joined with events)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t s3 = nullptr, s4 = nullptr;  // the critics' forward passes on [s | a] beside the target path; the
+                                            // weight-gradient products beside the dX chains
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr;
   // outputs
   float *out_q1 = nullptr, *out_q2 = nullptr, *out_l1 = nullptr, *out_l2 = nullptr, *out_lp = nullptr;
   // CUDA graph of the S-step loop: node arguments are fixed per (S, B, hyper-parameters); what changes between calls
@@ -477,10 +484,14 @@ int net_forward(const NetBuf& nb, float* const* acts, int rows, cudaStream_t s, 
 
 // backward: dOut = gradient w.r.t. the network OUTPUT (after the output activation) [rows, nL] with ld ld_dout.
 // want_param_grads: write nb.grad (flat).  dx_out (optional): gradient w.r.t. the input [rows, n0].
+// s_dw != NULL (and at most 3 layers: the two ping-pong buffers then never see a writer while a reader is pending): the
+// weight-gradient products go to that stream, behind the gradient they read, and the dX chain -- the critical path --
+// stays on `s`; both are joined before returning.
 int net_backward(b200rl_offpolicy* h, const NetBuf& nb, float* const* acts, const float* dOut, int ld_dout, int rows,
                  bool want_param_grads, float* dx_out, cudaStream_t s, bool twin_branch = false,
-                 const float* in_b = nullptr, int ld_b = 0, int ksplit = 0) {
+                 const float* in_b = nullptr, int ld_b = 0, int ksplit = 0, cudaStream_t s_dw = nullptr) {
   const int L = nb.d.n_layers;
+  const bool side = s_dw != nullptr && want_param_grads && L <= 3;
   const float* dY = dOut;
   int ldd = ld_dout;
   float* pp[2] = {twin_branch ? h->dbuf2 : h->dbuf0, twin_branch ? h->dbuf3 : h->dbuf1};
@@ -499,7 +510,11 @@ int net_backward(b200rl_offpolicy* h, const NetBuf& nb, float* const* acts, cons
       g.C = nb.grad + nb.w_off[l]; g.ldc = nin;
       g.M = nout; g.N = nin; g.K = rows;
       g.dbias = nb.grad + nb.b_off[l];  // db = column sums of dZ, accumulated by the same kernel
-      if (gemm<2>(g, s)) return 1;
+      if (side) {  // dY of this layer is complete on `s` at this point
+        B200RL_CUDA(cudaEventRecord(h->ev_side, s));
+        B200RL_CUDA(cudaStreamWaitEvent(s_dw, h->ev_side, 0));
+      }
+      if (gemm<2>(g, side ? s_dw : s)) return 1;
     }
     if (l > 0 || dx_out) {
       float* dst = (l == 0) ? dx_out : pp[l & 1];
@@ -512,6 +527,10 @@ int net_backward(b200rl_offpolicy* h, const NetBuf& nb, float* const* acts, cons
       dY = dst;
       ldd = nin;
     }
+  }
+  if (side) {
+    B200RL_CUDA(cudaEventRecord(h->ev_side, s_dw));
+    B200RL_CUDA(cudaStreamWaitEvent(s, h->ev_side, 0));
   }
   return 0;
 }
@@ -596,7 +615,6 @@ extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200r
   rc |= oalloc(h, &h->x_cat2, B * (size_t)(O + A));
   rc |= oalloc(h, &h->qt1, B);
   rc |= oalloc(h, &h->qt2, B);
-  rc |= oalloc(h, &h->y, B);
   rc |= oalloc(h, &h->dq, B);
   rc |= oalloc(h, &h->dbuf0, B * (size_t)maxw);
   rc |= oalloc(h, &h->dbuf1, B * (size_t)maxw);
@@ -616,6 +634,9 @@ extern "C" int b200rl_offpolicy_create(const b200rl_offpolicy_config* cfg, b200r
   if (!rc && cudaStreamCreateWithFlags(&h->gs, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
   if (!rc && cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming) != cudaSuccess) rc = 1;
   if (!rc && cudaStreamCreateWithFlags(&h->s2, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
+  if (!rc && cudaStreamCreateWithFlags(&h->s3, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
+  if (!rc && cudaStreamCreateWithFlags(&h->s4, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
+  if (!rc && cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess) rc = 1;
   if (!rc && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = 1;
   if (!rc && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) rc = 1;
   if (rc) {
@@ -633,7 +654,10 @@ extern "C" void b200rl_offpolicy_destroy(b200rl_offpolicy* h) {
   if (h->ev) cudaEventDestroy(h->ev);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
   if (h->s2) cudaStreamDestroy(h->s2);
+  if (h->s3) cudaStreamDestroy(h->s3);
+  if (h->s4) cudaStreamDestroy(h->s4);
   if (h->gs) cudaStreamDestroy(h->gs);
   if (h->h_adam_tab) cudaFreeHost(h->h_adam_tab);
   for (void* p : h->allocs) cudaFree(p);
@@ -726,89 +750,105 @@ static int enqueue_steps(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp
   NetBuf &pi = h->net[0], &q1 = h->net[1], &q2 = h->net[2], &pit = h->net[3], &q1t = h->net[4], &q2t = h->net[5];
   const int Lq = q1.d.n_layers, Lp = pi.d.n_layers;
   const int ew = 256;
+  cudaStream_t s2 = h->s2, s3 = h->s3, s4 = h->s4;
+  // work queued on `to` from here on waits for everything queued on `from` so far (a graph edge under capture)
+  auto edge = [&](cudaStream_t from, cudaStream_t to) -> int {
+    B200RL_CUDA(cudaEventRecord(h->ev_fork, from));
+    B200RL_CUDA(cudaStreamWaitEvent(to, h->ev_fork, 0));
+    return 0;
+  };
   int n_pol = 0;
+  // A step is a dependency graph, not a sequence; the branches below are what the kernels actually need:
+  //   s  : target policy -> Q1 target ---------+-> Q1 loss -> Q1 dX chain -----+-> Adam(Q1) -> [policy step] -> polyak
+  //   s2 :               -> Q2 target ---------+-> Q2 loss -> Q2 dX chain -----+-> Adam(Q2)
+  //   s3 : Q1 forward on [s | a] (independent of the targets) ..... Q1's dW products (pi's in the policy step)
+  //   s4 : Q2 forward on [s | a] .................................. Q2's dW products
+  // Critical path per step: 6 + 1 + 3 + 1 kernels (was 7 + 10 in a single chain), policy steps 14 more (was 19).
   for (int st = 0; st < S; ++st) {
     const float* s_obs = h->obs + (size_t)st * B * O;
     const float* s_act = h->act + (size_t)st * B * A;
     const float* s_rew = h->rew + (size_t)st * B;
     const float* s_nobs = h->nobs + (size_t)st * B * O;
     const float* s_done = h->done + (size_t)st * B;
-    // ---- targets (td3.py:325-341 / ddpg.py:275-282) ----
+    // ---- the critics' forward passes on [s | a]: their values are also the logged Q-values (td3.py:231-235) ----
+    float* qa[2][B200RL_MAX_LAYERS + 1];
+    for (int qi = 0; qi < (td3 ? 2 : 1); ++qi) {
+      qa[qi][0] = const_cast<float*>(s_obs);
+      for (int l = 1; l <= Lq; ++l) qa[qi][l] = h->acts[qi == 0 ? 1 : 4][l];
+      cudaStream_t qs = qi == 0 ? s3 : s4;
+      if (edge(s, qs)) return 1;
+      if (net_forward(qi == 0 ? q1 : q2, qa[qi], B, qs, s_act, A, O)) return 1;
+    }
+    // ---- targets (td3.py:325-341 / ddpg.py:275-282): the smoothing noise rides on the last layer's epilogue;
+    //      [s' | a'] is read in place by the target critics' first layer ----
     float* ta[B200RL_MAX_LAYERS + 1];
     ta[0] = const_cast<float*>(s_nobs);
     for (int l = 1; l <= Lp; ++l) ta[l] = h->acts[0][l];
-    // the smoothing noise rides on the last layer's epilogue; [s' | a'] is read in place by the critics' first layer
     if (net_forward(pit, ta, B, s, nullptr, 0, 0, hp->use_target_noise ? h->eps + (size_t)st * B * A : nullptr, hp))
       return 1;
     float* tq[B200RL_MAX_LAYERS + 1];
     tq[0] = const_cast<float*>(s_nobs);
+    for (int l = 1; l < Lq; ++l) tq[l] = h->acts_tq[l];  // apart from the target policy's stack, whose output it reads
     tq[Lq] = h->qt1;
-    if (td3) {  // the twin target critic runs concurrently on the side stream (its own activation stack)
-      B200RL_CUDA(cudaEventRecord(h->ev_fork, s));
-      B200RL_CUDA(cudaStreamWaitEvent(h->s2, h->ev_fork, 0));
+    if (td3) {
+      if (edge(s, s2)) return 1;
       float* tq2[B200RL_MAX_LAYERS + 1];
       tq2[0] = const_cast<float*>(s_nobs);
       for (int l = 1; l < Lq; ++l) tq2[l] = h->acts[3][l];
       tq2[Lq] = h->qt2;
-      if (net_forward(q2t, tq2, B, h->s2, ta[Lp], A, O)) return 1;
-      B200RL_CUDA(cudaEventRecord(h->ev_join, h->s2));
+      if (net_forward(q2t, tq2, B, s2, ta[Lp], A, O)) return 1;
     }
-    // Q1's target critic keeps its hidden activations apart from the target policy's (whose output it reads)
-    for (int l = 1; l < Lq; ++l) tq[l] = h->acts_tq[l];
     if (net_forward(q1t, tq, B, s, ta[Lp], A, O)) return 1;
-    if (td3) B200RL_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-    td_target_kernel<<<(B + ew - 1) / ew, ew, 0, s>>>(s_rew, s_done, h->qt1, td3 ? h->qt2 : nullptr, (float)hp->gamma, B,
-                                                      h->y);
-    B200RL_CUDA(cudaGetLastError());
-    count_launch(1);
-    // ---- Q steps (td3.py:343-358): forward on [s | a], MSE, backward, Adam.  The forward values are also the logged
-    //      Q-values (td3.py:231-235: same parameters, same inputs) ----
+    if (td3 && edge(s2, s)) return 1;  // both target values are complete on `s`
+    // ---- Q steps (td3.py:343-358): TD target + MSE + dq in one kernel, backward, Adam ----
     if (td3) {
-      B200RL_CUDA(cudaEventRecord(h->ev_fork, s));
-      B200RL_CUDA(cudaStreamWaitEvent(h->s2, h->ev_fork, 0));
+      if (edge(s, s2)) return 1;   // the targets
+      if (edge(s4, s2)) return 1;  // Q2's forward pass
     }
-    for (int qi = (td3 ? 1 : 0); qi >= 0; --qi) {  // twin critic first: it goes to the side stream, Q1 stays on `s`
+    if (edge(s3, s)) return 1;     // Q1's forward pass
+    for (int qi = (td3 ? 1 : 0); qi >= 0; --qi) {
       NetBuf& qn = qi == 0 ? q1 : q2;
-      cudaStream_t qs = qi == 0 ? s : h->s2;
+      cudaStream_t qs = qi == 0 ? s : s2;
       float* dq = qi == 0 ? h->dq : h->dq2;
-      float* qa[B200RL_MAX_LAYERS + 1];
-      qa[0] = const_cast<float*>(s_obs);
-      for (int l = 1; l <= Lq; ++l) qa[l] = h->acts[qi == 0 ? 1 : 4][l];
-      if (net_forward(qn, qa, B, qs, s_act, A, O)) return 1;
-      q_loss_kernel<<<1, GTHREADS, 0, qs>>>(qa[Lq], h->y, B, dq, (qi == 0 ? h->out_l1 : h->out_l2) + st,
-                                        (qi == 0 ? h->out_q1 : h->out_q2) + (size_t)st * B);
+      q_loss_kernel<<<1, GTHREADS, 0, qs>>>(qa[qi][Lq], s_rew, s_done, h->qt1, td3 ? h->qt2 : nullptr, (float)hp->gamma, B,
+                                            dq, (qi == 0 ? h->out_l1 : h->out_l2) + st,
+                                            (qi == 0 ? h->out_q1 : h->out_q2) + (size_t)st * B);
       B200RL_CUDA(cudaGetLastError());
       count_launch(1);
-      if (net_backward(h, qn, qa, dq, 1, B, true, nullptr, qs, qi != 0, s_act, A, O)) return 1;
+      if (net_backward(h, qn, qa[qi], dq, 1, B, true, nullptr, qs, qi != 0, s_act, A, O, qi == 0 ? s3 : s4)) return 1;
       if (adam_net(qn, h->adam_tab + (size_t)(1 + qi) * maxS, st, hp->q_beta1, hp->q_beta2, hp->q_eps, qs)) return 1;
-      if (qi != 0) B200RL_CUDA(cudaEventRecord(h->ev_join, h->s2));
     }
-    if (td3) B200RL_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (td3 && edge(s2, s)) return 1;
     // ---- delayed policy step + polyak (td3.py:244-263, 301-323; ddpg: every step) ----
     if (st % hp->policy_delay == 0) {
       float* pa[B200RL_MAX_LAYERS + 1];
       pa[0] = const_cast<float*>(s_obs);
       for (int l = 1; l <= Lp; ++l) pa[l] = h->acts[2][l];
       if (net_forward(pi, pa, B, s)) return 1;
-      float* qa[B200RL_MAX_LAYERS + 1];
-      qa[0] = const_cast<float*>(s_obs);
-      for (int l = 1; l <= Lq; ++l) qa[l] = h->acts[1][l];
-      if (net_forward(q1, qa, B, s, pa[Lp], A, O)) return 1;  // Q1 with its freshly updated parameters (td3.py:309)
-      q_loss_kernel<<<1, GTHREADS, 0, s>>>(qa[Lq], nullptr, B, h->dq, h->out_lp + n_pol, nullptr);
+      float* qp[B200RL_MAX_LAYERS + 1];
+      qp[0] = const_cast<float*>(s_obs);
+      for (int l = 1; l <= Lq; ++l) qp[l] = h->acts[1][l];
+      if (net_forward(q1, qp, B, s, pa[Lp], A, O)) return 1;  // Q1 with its freshly updated parameters (td3.py:309)
+      q_loss_kernel<<<1, GTHREADS, 0, s>>>(qp[Lq], nullptr, nullptr, nullptr, nullptr, 0.f, B, h->dq, h->out_lp + n_pol,
+                                           nullptr);
       B200RL_CUDA(cudaGetLastError());
       count_launch(1);
       // gradient w.r.t. Q1's input; its action columns are the gradient w.r.t. pi(s) (Q parameters frozen)
-      if (net_backward(h, q1, qa, h->dq, 1, B, false, h->x_cat, s)) return 1;
-      if (net_backward(h, pi, pa, h->x_cat + O, O + A, B, true, nullptr, s)) return 1;
+      if (net_backward(h, q1, qp, h->dq, 1, B, false, h->x_cat, s)) return 1;
+      if (net_backward(h, pi, pa, h->x_cat + O, O + A, B, true, nullptr, s, false, nullptr, 0, 0, s3)) return 1;
       if (adam_net(pi, h->adam_tab, n_pol, hp->policy_beta1, hp->policy_beta2, hp->policy_eps, s)) return 1;
-      const float rho = (float)hp->polyak_rho, omr = (float)(1.0 - hp->polyak_rho);
-      for (int k = 0; k < (td3 ? 3 : 2); ++k) {
-        NetBuf& src = h->net[k];
-        NetBuf& dst = h->net[3 + k];
-        polyak_kernel<<<(int)((src.P + ew - 1) / ew), ew, 0, s>>>(dst.params, src.params, rho, omr, (int)src.P);
-        B200RL_CUDA(cudaGetLastError());
-        count_launch(1);
+      PolyakArgs pk{};
+      pk.n_nets = td3 ? 3 : 2;
+      int nmax = 0;
+      for (int k = 0; k < pk.n_nets; ++k) {
+        pk.target[k] = h->net[3 + k].params;
+        pk.param[k] = h->net[k].params;
+        pk.n[k] = (int)h->net[k].P;
+        nmax = pk.n[k] > nmax ? pk.n[k] : nmax;
       }
+      polyak_kernel<<<(nmax + ew - 1) / ew, ew, 0, s>>>(pk, (float)hp->polyak_rho, (float)(1.0 - hp->polyak_rho));
+      B200RL_CUDA(cudaGetLastError());
+      count_launch(1);
       ++n_pol;
     }
   }

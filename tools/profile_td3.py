@@ -31,35 +31,37 @@ ex.dones = [[bool(x) for x in (rng.random(n_rb) < 0.001)]]
 ex.last_observations = [obs_rb[n_rb]]
 rb.add_experience(ex)
 algo.train(rb, 50, 256)
-if len(sys.argv) > 1 and sys.argv[1] == "time":  # wall-clock of train() calls, persistent kernel vs CUDA-graph replay
+if len(sys.argv) > 1 and sys.argv[1] == "time":  # wall-clock of train() calls and of their three parts
     import time
-    for mega in ("1", "0"):
-        os.environ["B200RL_OFFPOLICY_MEGAKERNEL"] = mega
-        algo.train(rb, 50, 256)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(20):
+    T = {"upload": [], "engine": [], "download": []}
+
+    def wrap(obj, name, key):
+        f = getattr(obj, name)
+
+        def g(*a, **k):
+            t0 = time.perf_counter()
+            r = f(*a, **k)
+            T[key].append((time.perf_counter() - t0) * 1e3)
+            return r
+        setattr(obj, name, g)
+    wrap(algo, "_upload_state", "upload")
+    wrap(algo, "_download_state", "download")
+    wrap(algo._engine, "train_gather", "engine")
+    for threads in (None, 1):
+        if threads:
+            torch.set_num_threads(threads)
+        for v in T.values():
+            v.clear()
+        per_call = []
+        for _ in range(24):
+            t1 = time.perf_counter()
             algo.train(rb, 50, 256)
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3 / 20
-        print(f"B200RL_OFFPOLICY_MEGAKERNEL={mega}: {ms:.3f} ms per TD3.train(rb, 50, 256) = {50 / ms * 1e3:.0f} train steps/s")
-    # the engine alone: host-staged minibatches, one upload + the S steps + one read-back
-    eng = algo._engine
-    mbs = [rb.sample_minibatch(256) for _ in range(50)]
-    st = lambda k: np.stack([np.asarray(m[k]) for m in mbs]).astype(np.float32)
-    noise = torch.stack([torch.randn(256, 3) for _ in range(50)]).numpy()
-    args = (algo._hparams(True, 2), st("observations"), st("actions"), st("rewards"), st("next_observations"), st("dones"), noise)
-    for mega, graph in (("1", "1"), ("0", "1"), ("0", "0")):
-        os.environ["B200RL_OFFPOLICY_MEGAKERNEL"], os.environ["B200RL_OFFPOLICY_GRAPH"] = mega, graph
-        eng.train(*args)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(20):
-            out = eng.train(*args)
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3 / 20
-        print(f"engine, megakernel={mega} graph={graph}: {ms:.3f} ms per 50 steps = {50 / ms * 1e3:.0f} train steps/s; "
-              f"kernel launches per call {out.get('kernel_launches')}")
+            per_call.append((time.perf_counter() - t1) * 1e3)
+        print("torch threads", torch.get_num_threads())
+        print(" per call ms:", " ".join(f"{x:.1f}" for x in per_call))
+        for k, v in T.items():
+            print(f" {k:9s}", " ".join(f"{x:.1f}" for x in v))
+        print(f" median {np.median(per_call):.2f} ms = {50 / np.median(per_call) * 1e3:.0f} train steps/s; mean {np.mean(per_call):.2f} ms")
     sys.exit(0)
 pr = cProfile.Profile()
 pr.enable()
