@@ -864,7 +864,25 @@ __global__ void __launch_bounds__(T3_THREADS, 1) mlp_tc3_kernel(const Tc3Args p)
 // is then two launches, like a single-GPU one.  It needs every block resident at once (ra3_one_wave).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int RA3_WARPS = 8;
-__global__ void __launch_bounds__(RA3_WARPS * 32, 4) reduce_adam3_kernel(const Ra3Args a) {
+
+// One float from every rank's exchange buffer.  The loads are issued back to back (a peer read over NVLink is ~2 us:
+// a loop with one load per trip would pay that once per rank) and added in rank order, the same sum on every rank.
+template <typename Acc>
+__device__ __forceinline__ Acc ra3_gather(float* const* peers, int world, long long offset) {
+  float x[RA3_MAX_WORLD];
+#pragma unroll
+  for (int r = 0; r < RA3_MAX_WORLD; ++r) {
+    x[r] = 0.f;
+    if (r < world) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x[r]) : "l"(peers[r] + offset) : "memory");
+  }
+  Acc t = (Acc)0;
+#pragma unroll
+  for (int r = 0; r < RA3_MAX_WORLD; ++r)
+    if (r < world) t += (Acc)x[r];
+  return t;
+}
+
+__global__ void __launch_bounds__(RA3_WARPS * 32, 3) reduce_adam3_kernel(const Ra3Args a) {
   __shared__ float part[RA3_WARPS][32];
   __shared__ double spart[RA3_WARPS * 4][2 * B200RL_N_SCALARS];
   __shared__ double s_scal[2 * B200RL_N_SCALARS];
@@ -875,16 +893,8 @@ __global__ void __launch_bounds__(RA3_WARPS * 32, 4) reduce_adam3_kernel(const R
   const bool run_p = a.run_policy != 0 && !stopped_before, run_v = a.run_value != 0;
   const unsigned parity = a.seq & 1u;
   if (a.mode == 4) {  // every rank's buffer of this exchange has arrived (wait_peers_kernel ran before this launch)
-    if (threadIdx.x < 2 * B200RL_N_SCALARS) {
-      double t = 0.0;
-      for (int r = 0; r < a.world; ++r) {
-        float x;
-        const float* src = a.peers[r] + parity * a.xchg_stride + Ptot + threadIdx.x;
-        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
-        t += (double)x;
-      }
-      s_scal[threadIdx.x] = t;
-    }
+    if (threadIdx.x < 2 * B200RL_N_SCALARS)
+      s_scal[threadIdx.x] = ra3_gather<double>(a.peers, a.world, parity * a.xchg_stride + Ptot + threadIdx.x);
   } else if (a.mode != 2) {
     // scalar sums: 32 row classes x 16 scalars, then the classes in order (same in every block)
     const int k = lane & 15, cls = warp * 4 + (lane >> 4) * 2;  // two classes per half-warp pass
@@ -906,12 +916,7 @@ __global__ void __launch_bounds__(RA3_WARPS * 32, 4) reduce_adam3_kernel(const R
   float g = 0.f;
   if (a.mode == 4) {
     if (warp == 0 && pidx < Ptot) {
-      for (int r = 0; r < a.world; ++r) {  // rank order: the same sum on every rank
-        float x;
-        const float* src = a.peers[r] + parity * a.xchg_stride + pidx;
-        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
-        g += x;
-      }
+      g = ra3_gather<float>(a.peers, a.world, parity * a.xchg_stride + pidx);
       if (a.grad != nullptr) a.grad[pidx] = g;
     }
   } else if (a.mode != 2) {
@@ -977,24 +982,10 @@ __global__ void __launch_bounds__(RA3_WARPS * 32, 4) reduce_adam3_kernel(const R
       }
     }
     __syncthreads();
-    if (threadIdx.x < 2 * B200RL_N_SCALARS) {
-      double t = 0.0;
-      for (int r = 0; r < a.world; ++r) {
-        float x;
-        const float* src = a.peers[r] + parity * a.xchg_stride + Ptot + threadIdx.x;
-        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
-        t += (double)x;
-      }
-      s_scal[threadIdx.x] = t;
-    }
+    if (threadIdx.x < 2 * B200RL_N_SCALARS)
+      s_scal[threadIdx.x] = ra3_gather<double>(a.peers, a.world, parity * a.xchg_stride + Ptot + threadIdx.x);
     if (warp == 0 && pidx < Ptot) {
-      g = 0.f;
-      for (int r = 0; r < a.world; ++r) {  // rank order: the same sum on every rank
-        float x;
-        const float* src = a.peers[r] + parity * a.xchg_stride + pidx;
-        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(src) : "memory");
-        g += x;
-      }
+      g = ra3_gather<float>(a.peers, a.world, parity * a.xchg_stride + pidx);
       if (a.grad != nullptr) a.grad[pidx] = g;
     }
     __syncthreads();
