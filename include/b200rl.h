@@ -377,6 +377,21 @@ int b200rl_offpolicy_train_gather(b200rl_offpolicy* h, const b200rl_offpolicy_hp
                                   float* q1_values, float* q2_values, float* q1_losses, float* q2_losses,
                                   float* policy_losses, int32_t* n_policy_updates, void* stream);
 
+/* Opt-in: the same with the minibatch indices and the target-smoothing noise DRAWN ON THE DEVICE
+ * (Philox4x32-10 keyed by `seed`, block `call`): nothing but the hyper-parameters crosses PCIe on the way in.  The
+ * streams are not the reference's (numpy MT19937 / torch CPU generator): same distributions, different numbers.  The
+ * replay ring: `ring_size` live rows, logical row u at physical (ring_start + u) % rows.
+ *   replaces: replay_buffer.py:58 (np.random.randint) + td3.py:328 (torch.randn_like) for callers that opt in. */
+int b200rl_offpolicy_train_gather_rng(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S, int32_t B,
+                                      const float* d_obs, const float* d_act, const float* d_rew,
+                                      const float* d_next_obs, const float* d_done, int64_t rows, int64_t ring_start,
+                                      int64_t ring_size, uint64_t seed, uint64_t call, float* q1_values,
+                                      float* q2_values, float* q1_losses, float* q2_losses, float* policy_losses,
+                                      int32_t* n_policy_updates, void* stream);
+/* The draws of the last train_gather / train_gather_rng call: physical rows idx [S*B] (host int64), noise [S*B*A]
+ * (host float32, or NULL) -- what a test replays through the oracle. */
+int b200rl_offpolicy_get_draws(b200rl_offpolicy* h, int32_t S, int32_t B, int64_t* idx, float* noise, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Diagnostics (not on the product path): issue a chain of tcgen05.mma kind::tf32 instructions on a caller-supplied
  * shared-memory image and return the raw TMEM contents [128 lanes, read_cols]; tests use it to pin the descriptor

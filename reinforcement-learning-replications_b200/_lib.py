@@ -147,6 +147,10 @@ SIGNATURES = {
     "b200rl_offpolicy_train_gather": (C.c_int, [C.c_void_p, C.POINTER(OffPolicyHparams), C.c_int32, C.c_int32] +
                                       [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 7 +
                                       [C.POINTER(C.c_int32), C.c_void_p]),
+    "b200rl_offpolicy_train_gather_rng": (C.c_int, [C.c_void_p, C.POINTER(OffPolicyHparams), C.c_int32, C.c_int32] +
+                                          [C.c_void_p] * 5 + [C.c_int64] * 3 + [C.c_uint64] * 2 + [C.c_void_p] * 5 +
+                                          [C.POINTER(C.c_int32), C.c_void_p]),
+    "b200rl_offpolicy_get_draws": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200rl_tc_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b200rl_discounted_cumsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
     "b200rl_gae_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_double, C.c_void_p,

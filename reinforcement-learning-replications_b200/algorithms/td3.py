@@ -22,6 +22,9 @@ logger = logging.getLogger(__name__)
 
 class _OffPolicyBase:
     n_q = 1
+    use_device_replay = True  # replay columns mirrored in HBM, minibatches gathered on the device
+    use_device_rng = False    # opt-in: indices and target-smoothing noise drawn on the device (Philox) instead of with
+    device_rng_seed = 0       # the reference's numpy / torch CPU streams -- same distributions, different numbers
 
     def _trainable(self):
         return [self.policy] + ([self.q_function_1, self.q_function_2] if self.n_q == 2 else [self.q_function])
@@ -176,6 +179,8 @@ class _OffPolicyBase:
         A = self.policy.network.sizes[-1] if hasattr(self.policy.network, "sizes") else describe_mlp(self.policy.network)[0][-1]
         device_replay = (S > 0 and getattr(self, "use_device_replay", True) and hasattr(replay_buffer, "device_columns")
                          and hasattr(replay_buffer, "sample_indices"))
+        # opt-in: indices and smoothing noise drawn on the device -- not the reference's random streams
+        device_rng = device_replay and getattr(self, "use_device_rng", False) and hasattr(replay_buffer, "ring")
         def noise_of():  # S draws of torch.randn(B, A), the reference's stream (td3.py:328), gathered without torch.stack
             if not (noisy and S > 0):
                 return None
@@ -183,7 +188,9 @@ class _OffPolicyBase:
             for i in range(S):
                 out[i] = torch.randn(B, A).numpy()
             return out
-        if device_replay:
+        if device_rng:
+            idx = noise = None
+        elif device_replay:
             # device-resident replay columns: S index draws on the host (the same numpy stream as S sample_minibatch
             # calls); the gather happens on the GPU, only indices and noise cross PCIe
             idx = replay_buffer.physical_rows(np.stack([replay_buffer.sample_indices(B) for _ in range(S)]))
@@ -206,6 +213,12 @@ class _OffPolicyBase:
         self._upload_state(e, trainable, targets, lins)
         if S == 0:
             out = None
+        elif device_rng:
+            columns, rows = replay_buffer.device_columns()
+            start, size, _ = replay_buffer.ring()
+            self._device_rng_calls = getattr(self, "_device_rng_calls", 0) + 1
+            out = e.train_gather_rng(self._hparams(noisy, delay), columns, rows, start, size, S, B,
+                                     getattr(self, "device_rng_seed", 0), self._device_rng_calls)
         elif device_replay:
             columns, rows = replay_buffer.device_columns()
             out = e.train_gather(self._hparams(noisy, delay), columns, rows, idx, noise)

@@ -166,6 +166,51 @@ __global__ void __launch_bounds__(GTHREADS) gemm_kernel(const GemmArgs g) {
   gemm_tile<MODE, 8>(g, blockIdx.x, blockIdx.y, As, Bs);  // K = 256 is ONE round of loads
 }
 
+// ---- device-side draws (opt-in): Philox4x32-10, counter-based, so a (seed, call) pair names the whole
+// [S, B] index block and the [S, B, A] noise block of one train() call whatever the launch geometry.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c.x, p1 = (unsigned long long)0xCD9E8D57u * c.z;
+    c = make_uint4((unsigned)(p1 >> 32) ^ c.y ^ k.x, (unsigned)p1, (unsigned)(p0 >> 32) ^ c.w ^ k.y, (unsigned)p0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// idx[j] = physical row of a uniform draw over the `size` live rows of the ring (logical row u sits at
+// (start + u) % capacity);  eps[j] = N(0, 1) by Box-Muller.  One thread = one Philox block = 4 values of each.
+__global__ void draw_minibatches_kernel(long long* idx, long long n_idx, float* eps, long long n_eps,
+                                        unsigned long long seed, unsigned long long call, long long start,
+                                        long long size, long long capacity) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  if (4 * t < n_idx) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)t, (unsigned)(t >> 32), (unsigned)call, 0x1D5u), key);
+    const unsigned v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * t + j < n_idx) {
+        const long long u = (long long)(((unsigned long long)v[j] * (unsigned long long)size) >> 32);  // [0, size)
+        idx[4 * t + j] = (start + u) % capacity;
+      }
+  }
+  if (eps != nullptr && 4 * t < n_eps) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)t, (unsigned)(t >> 32), (unsigned)call, 0xE95u), key);
+    const float u1 = ((float)r.x + 1.0f) * 2.3283064365386963e-10f, u2 = (float)r.y * 2.3283064365386963e-10f;
+    const float u3 = ((float)r.z + 1.0f) * 2.3283064365386963e-10f, u4 = (float)r.w * 2.3283064365386963e-10f;
+    const float m1 = sqrtf(-2.f * logf(u1)), m2 = sqrtf(-2.f * logf(u3));
+    float s1, c1, s2, c2;
+    sincospif(2.f * u2, &s1, &c1);
+    sincospif(2.f * u4, &s2, &c2);
+    const float z[4] = {m1 * c1, m1 * s1, m2 * c2, m2 * s2};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * t + j < n_eps) eps[4 * t + j] = z[j];
+  }
+}
+
 // staged[i, :] = table[idx[i], :]  (replay-buffer gather; one launch per column)
 __global__ void gather_rows_kernel(const float* table, const long long* idx, int width, long long n_out, float* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1314,4 +1359,66 @@ extern "C" int b200rl_offpolicy_train_gather(b200rl_offpolicy* h, const b200rl_o
     count_launch(1);
   }
   return run_staged(h, hp, S, B, q1_values, q2_values, q1_losses, q2_losses, policy_losses, n_policy_updates);
+}
+
+/* Opt-in: the minibatch indices and the target-smoothing noise are DRAWN ON THE DEVICE (Philox4x32-10 keyed by `seed`,
+ * block `call`), so nothing but the hyper-parameters crosses PCIe on the way in.  The streams are not the reference's
+ * (numpy's MT19937 / torch's CPU generator): same distributions, different numbers -- callers that need the reference's
+ * draws use b200rl_offpolicy_train_gather.  The ring: `size` live rows, logical row u at physical (start + u) % rows. */
+extern "C" int b200rl_offpolicy_train_gather_rng(b200rl_offpolicy* h, const b200rl_offpolicy_hparams* hp, int32_t S,
+                                                 int32_t B, const float* d_obs, const float* d_act, const float* d_rew,
+                                                 const float* d_next_obs, const float* d_done, int64_t rows,
+                                                 int64_t ring_start, int64_t ring_size, uint64_t seed, uint64_t call,
+                                                 float* q1_values, float* q2_values, float* q1_losses,
+                                                 float* q2_losses, float* policy_losses, int32_t* n_policy_updates,
+                                                 void* stream) {
+  B200RL_REQUIRE(h && hp && d_obs && d_act && d_rew && d_next_obs && d_done && q1_values && q1_losses &&
+                     policy_losses && n_policy_updates, "offpolicy_train_gather_rng: NULL argument");
+  B200RL_REQUIRE(S >= 0 && S <= h->cfg.max_steps && B >= 1 && B <= h->cfg.max_minibatch,
+                 "offpolicy_train_gather_rng: S=%d B=%d exceed the capacities", S, B);
+  B200RL_REQUIRE(rows >= 1 && ring_size >= 1 && ring_size <= rows && ring_start >= 0 && ring_start < rows,
+                 "offpolicy_train_gather_rng: bad ring (rows %lld, start %lld, size %lld)", (long long)rows,
+                 (long long)ring_start, (long long)ring_size);
+  const bool td3 = h->cfg.n_q == 2;
+  B200RL_REQUIRE(!td3 || (q2_values && q2_losses), "offpolicy_train_gather_rng: TD3 needs the Q2 outputs");
+  B200RL_REQUIRE(hp->policy_delay >= 1, "offpolicy_train_gather_rng: policy_delay must be >= 1");
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  cudaStream_t s = h->gs;
+  const int O = h->O, A = h->A;
+  const long long SB = (long long)S * B;
+  *n_policy_updates = 0;
+  if (S == 0) return 0;
+  B200RL_CUDA(cudaEventRecord(h->ev, user));
+  B200RL_CUDA(cudaStreamWaitEvent(s, h->ev, 0));
+  const long long n_eps = hp->use_target_noise ? SB * A : 0;
+  const long long n_thr = ((SB > n_eps ? SB : n_eps) + 3) / 4;
+  draw_minibatches_kernel<<<(int)((n_thr + 255) / 256), 256, 0, s>>>(h->idx, SB, n_eps ? h->eps : nullptr, n_eps, seed, call,
+                                                                    ring_start, ring_size, rows);
+  B200RL_CUDA(cudaGetLastError());
+  count_launch(1);
+  const struct { const float* src; float* dst; int w; } cols[5] = {
+      {d_obs, h->obs, O}, {d_act, h->act, A}, {d_rew, h->rew, 1}, {d_next_obs, h->nobs, O}, {d_done, h->done, 1}};
+  for (const auto& c : cols) {
+    const long long n = SB * c.w;
+    gather_rows_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(c.src, h->idx, c.w, SB, c.dst);
+    B200RL_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
+  return run_staged(h, hp, S, B, q1_values, q2_values, q1_losses, q2_losses, policy_losses, n_policy_updates);
+}
+
+/* The draws of the last train_gather / train_gather_rng call (physical rows [S*B], noise [S*B*A] or NULL): what a test
+ * replays through the oracle. */
+extern "C" int b200rl_offpolicy_get_draws(b200rl_offpolicy* h, int32_t S, int32_t B, int64_t* idx, float* noise,
+                                          void* stream) {
+  B200RL_REQUIRE(h && idx && S >= 0 && S <= h->cfg.max_steps && B >= 1 && B <= h->cfg.max_minibatch,
+                 "offpolicy_get_draws: bad arguments");
+  cudaStream_t s = h->gs;
+  (void)stream;
+  const size_t SB = (size_t)S * B;
+  static_assert(sizeof(long long) == sizeof(int64_t), "index width");
+  B200RL_CUDA(cudaMemcpyAsync(idx, h->idx, SB * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (noise) B200RL_CUDA(cudaMemcpyAsync(noise, h->eps, SB * h->A * 4, cudaMemcpyDeviceToHost, s));
+  B200RL_CUDA(cudaStreamSynchronize(s));
+  return 0;
 }

@@ -434,6 +434,28 @@ class OffPolicyEngine:
                                               C.byref(npol), current_stream_handle()), "offpolicy_train")
         return dict(q1_values=q1v, q2_values=q2v, q1_losses=l1, q2_losses=l2, policy_losses=lp[:npol.value])
 
+    def train_gather_rng(self, hp, columns, rows: int, ring_start: int, ring_size: int, S: int, B: int, seed: int, call: int):
+        """``train_gather`` with the indices and the smoothing noise drawn on the device (Philox keyed by ``seed``, block
+        ``call``); ``ring_size`` live rows, logical row u at physical ``(ring_start + u) % rows``.  Opt-in: the streams
+        are not the reference's numpy / torch ones."""
+        q1v, q2v = np.zeros((S, B), np.float32), np.zeros((S, B), np.float32)
+        l1, l2, lp = np.zeros(S, np.float32), np.zeros(S, np.float32), np.zeros(max(S, 1), np.float32)
+        npol = C.c_int32()
+        ptrs = [C.c_void_p(t.data_ptr()) for t in columns]
+        check(self.lib.b200rl_offpolicy_train_gather_rng(self.h, C.byref(hp), S, B, *ptrs, int(rows), int(ring_start),
+                                                         int(ring_size), int(seed) & (2 ** 64 - 1), int(call), _ptr(q1v),
+                                                         _ptr(q2v), _ptr(l1), _ptr(l2), _ptr(lp), C.byref(npol),
+                                                         current_stream_handle()), "offpolicy_train_gather_rng")
+        return dict(q1_values=q1v, q2_values=q2v, q1_losses=l1, q2_losses=l2, policy_losses=lp[:npol.value])
+
+    def get_draws(self, S: int, B: int, with_noise: bool = True):
+        """(physical rows [S,B] int64, noise [S,B,A] float32 or None) of the last train_gather / train_gather_rng call."""
+        idx = np.empty((S, B), np.int64)
+        A = self.policy_sizes[-1]
+        noise = np.empty((S, B, A), np.float32) if with_noise else None
+        check(self.lib.b200rl_offpolicy_get_draws(self.h, S, B, _ptr(idx), _ptr(noise), current_stream_handle()), "get_draws")
+        return idx, noise
+
     def train_gather(self, hp, columns, rows: int, idx, noise=None):
         """Minibatches gathered on the device: ``columns`` = CUDA float32 tensors (obs [rows,O], act [rows,A], rew [rows],
         next_obs [rows,O], done [rows]) of a device-resident replay buffer, ``idx`` [S,B] int64 physical rows (host)."""

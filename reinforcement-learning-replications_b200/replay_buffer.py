@@ -100,6 +100,10 @@ class ReplayBuffer:
     def physical_rows(self, logical: np.ndarray) -> np.ndarray:
         return self._physical(np.asarray(logical)).astype(np.int64)
 
+    def ring(self):
+        """(physical row of logical index 0, live rows, allocated rows): what a device-side index draw needs."""
+        return self._head, self.current_size, self._capacity
+
     def device_columns(self):
         """(obs, act, rew, next_obs, done) float32 CUDA tensors with ``capacity`` rows each, in PHYSICAL row order
         (use ``physical_rows`` on the logical indices).  rewards float64 -> float32 and dones bool -> 0/1 are the casts

@@ -254,3 +254,83 @@ def test_state_blob_round_trip_matches_the_per_network_accessors(n_q):
     for kind, i, off, n in layout:
         np.testing.assert_array_equal(back[off:off + n], newp if (kind, i) == ("params", 1) else want[(kind, i)])
     e.close()
+
+
+@pytest.mark.parametrize("twin", [True, False])
+def test_device_side_draws_opt_in(twin):
+    """use_device_rng: indices (uniform over the live rows of the replay ring, physical addressing across the wrap) and
+    target-smoothing noise come from a Philox generator on the device.  The draws are read back and replayed through
+    the numpy oracle (2e-5 like the host-drawn path); they are reproducible per (seed, call), differ between calls, and
+    have the right distributions."""
+    from rl_replicas_b200.experience import Experience
+    from rl_replicas_b200.replay_buffer import ReplayBuffer
+    rng = np.random.default_rng(11)
+    H, S, B = 64, 8, 64
+    mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), 0.05 * rng.standard_normal(o).astype(np.float32))
+                     for i, o in zip(sz[:-1], sz[1:])]
+    pl, q1l, q2l = mk([O_DIM, H, H, A_DIM]), mk([O_DIM + A_DIM, H, H, 1]), mk([O_DIM + A_DIM, H, H, 1])
+
+    def fresh():
+        algo, _ = build(twin, H, O.flatten_layers(pl), [O.flatten_layers(q1l)] + ([O.flatten_layers(q2l)] if twin else []))
+        rb = ReplayBuffer(buffer_size=3000)  # 4000 rows into 3000: the ring has wrapped, head != 0
+        r2 = np.random.default_rng(5)
+        for chunk in range(4):
+            n = 1000
+            e = Experience()
+            obs = r2.standard_normal((n + 1, O_DIM)).astype(np.float32)
+            e.observations = [[obs[i] for i in range(n)]]
+            e.actions = [[r2.uniform(-1, 1, A_DIM).astype(np.float32) for _ in range(n)]]
+            e.rewards = [[float(x) for x in r2.standard_normal(n)]]
+            e.dones = [[bool(x) for x in (r2.random(n) < 0.01)]]
+            e.last_observations = [obs[n]]
+            rb.add_experience(e)
+        algo.use_device_rng, algo.device_rng_seed = True, 1234
+        return algo, rb
+
+    algo, rb = fresh()
+    start, size, cap = rb.ring()
+    assert size == 3000 and start != 0
+    algo.train(rb, S, B)
+    idx, noise = algo._engine.get_draws(S, B, with_noise=twin)
+    assert (((idx - start) % cap) < size).all() and idx.min() >= 0 and idx.max() < cap
+    # the oracle on exactly these draws
+    mbs = [{k: rb._cols[k][idx[s]] for k in rb.COLUMNS} for s in range(S)]
+    nets = {"policy": [(w.copy(), b.copy()) for w, b in pl], "q1": [(w.copy(), b.copy()) for w, b in q1l],
+            "target_policy": [(w.copy(), b.copy()) for w, b in pl], "target_q1": [(w.copy(), b.copy()) for w, b in q1l]}
+    names = ["policy", "q1"]
+    if twin:
+        nets["q2"], nets["target_q2"] = [(w.copy(), b.copy()) for w, b in q2l], [(w.copy(), b.copy()) for w, b in q2l]
+        names.append("q2")
+    adams = {k: O.AdamState(O.flatten_layers(nets[k]).size, 1e-3) for k in names}
+    logs = OP.offpolicy_train(nets, adams, mbs, noise, policy_delay=2 if twin else 1, twin=twin)
+    out = algo.last_train_output
+    assert rel_err(out["q1_values"], np.stack(logs["q1_values"])) < 2e-5
+    assert rel_err(out["q1_losses"], np.asarray(logs["q1_losses"])) < 2e-5
+    assert rel_err(flat(algo.policy.network), O.flatten_layers(nets["policy"])) < 2e-5
+    q_nets = [algo.q_function_1, algo.q_function_2] if twin else [algo.q_function]
+    for i, q in enumerate(q_nets):
+        assert rel_err(flat(q.network), O.flatten_layers(nets[f"q{i + 1}"])) < 2e-5
+    # reproducible per (seed, call); the next call draws a different block
+    algo2, rb2 = fresh()
+    algo2.train(rb2, S, B)
+    idx2, noise2 = algo2._engine.get_draws(S, B, with_noise=twin)
+    np.testing.assert_array_equal(idx, idx2)
+    if twin:
+        np.testing.assert_array_equal(noise, noise2)
+    algo2.train(rb2, S, B)
+    idx3, _ = algo2._engine.get_draws(S, B, with_noise=False)
+    assert (idx3 != idx).mean() > 0.9
+    algo2.device_rng_seed = 99
+    algo2._device_rng_calls = 0
+    algo2.train(rb2, S, B)
+    assert (algo2._engine.get_draws(S, B, with_noise=False)[0] != idx).mean() > 0.9
+    # distributions over a larger block: 50 x 256 indices, 38400 normal draws
+    algo2.train(rb2, 50, 256)
+    big, eps = algo2._engine.get_draws(50, 256, with_noise=twin)
+    logical = (big - rb2.ring()[0]) % cap
+    assert abs(logical.mean() / size - 0.5) < 0.02 and logical.min() < 30 and logical.max() > size - 30
+    counts = np.bincount(logical.ravel() * 10 // size, minlength=10)
+    assert counts.min() > 0.85 * big.size / 10 and counts.max() < 1.15 * big.size / 10
+    if twin:
+        assert abs(eps.mean()) < 0.03 and abs(eps.std() - 1.0) < 0.03 and np.abs(eps).max() < 6.5
+        assert abs(np.mean(eps ** 3)) < 0.1 and abs(np.mean(eps ** 4) - 3.0) < 0.25  # skewness, kurtosis of N(0, 1)
