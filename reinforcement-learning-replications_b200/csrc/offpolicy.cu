@@ -8,8 +8,12 @@
 // launch-latency bound, not throughput bound.  The design therefore minimises host involvement:
 // ALL `num_train_steps` minibatches (and the target-smoothing noise) are uploaded once, every step runs as a fixed
 // sequence of small fp32 kernels with no host synchronisation, and losses / Q-values are read back once at the end.
-// GEMMs are one generic 32x32x16 shared-memory-tiled fp32 kernel in three operand arrangements (forward NT, dX NN,
-// dW TN) with the activation derivative fused into the operand load, so activations are never rewritten.
+// GEMMs are one generic 32x32x32 shared-memory-tiled fp32 kernel in three operand arrangements (forward NT, dX NN,
+// dW TN) with the activation derivative fused into the operand load, so activations are never rewritten; torch.cat of
+// [s | a] is a split operand, the target-smoothing noise an epilogue.  File map: tile function and elementwise kernels;
+// the opt-in persistent step kernel (offpolicy_mega_kernel) and its program builder; the engine (one state slab);
+// enqueue_steps = the S steps as a four-stream dependency graph (captured once, replayed); the three entry points
+// train (host-staged minibatches), train_gather (host-drawn indices, device gather), train_gather_rng (device draws).
 #include <cmath>
 #include <cstring>
 #include <vector>
