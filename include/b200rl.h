@@ -258,6 +258,13 @@ typedef struct {
 
 int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, const b200rl_trpo_hparams* cg,
                        b200rl_update_stats* stats, b200rl_trpo_stats* trpo_stats, void* stream);
+/* The same step data-parallel: every batch-derived sum (advantage statistics, surrogate gradient + scalar sums, every
+ * Fisher-vector product, the scalar sums of every line-search evaluation, the value gradients) goes through `allreduce`
+ * where it is formed; hp->n_global_rows = the global row count.  All ranks take identical CG / line-search decisions.
+ * allreduce == NULL: b200rl_trpo_update. */
+int b200rl_trpo_update_dp(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, const b200rl_trpo_hparams* cg,
+                          b200rl_allreduce_fn allreduce, void* user, b200rl_update_stats* stats,
+                          b200rl_trpo_stats* ts, void* stream);
 /* One Fisher-vector product on the loaded batch at the current policy parameters: out = F v + damping * v (host
  * vectors of policy-parameter length); for tests against the reference's double-backprop Hessian-vector product. */
 int b200rl_onpolicy_fvp(b200rl_onpolicy* h, const float* host_v, float* host_out, int64_t n, double damping,

@@ -129,6 +129,8 @@ SIGNATURES = {
                                     C.POINTER(UpdateStats), C.c_void_p]),
     "b200rl_trpo_update": (C.c_int, [C.c_void_p, C.POINTER(PpoHparams), C.POINTER(TrpoHparams), C.POINTER(UpdateStats),
                                      C.POINTER(TrpoStats), C.c_void_p]),
+    "b200rl_trpo_update_dp": (C.c_int, [C.c_void_p, C.POINTER(PpoHparams), C.POINTER(TrpoHparams), C.c_void_p, C.c_void_p,
+                                        C.POINTER(UpdateStats), C.POINTER(TrpoStats), C.c_void_p]),
     "b200rl_onpolicy_fvp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p]),
     "b200rl_onpolicy_device_view": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                               C.POINTER(C.c_int32)]),

@@ -15,9 +15,13 @@ class TRPO(PPO):
     """Same constructor as ref algorithms/trpo.py:43-52; ``policy.optimizer`` must be a ConjugateGradientOptimizer."""
 
     def __init__(self, policy, value_function, env, sampler, gamma: float = 0.99, gae_lambda: float = 0.97,
-                 num_value_gradients: int = 80) -> None:
+                 num_value_gradients: int = 80, distributed: bool = False, process_group=None) -> None:
+        """``distributed`` / ``process_group`` (not in the reference): one process per GPU, each training on its own
+        block of episodes; the constrained step all-reduces every batch-derived sum (the surrogate gradient, each
+        Fisher-vector product, each line-search evaluation, the value gradients), so all ranks take the same step."""
         super().__init__(policy, value_function, env, sampler, gamma=gamma, gae_lambda=gae_lambda,
-                         num_policy_gradients=1, num_value_gradients=num_value_gradients)
+                         num_policy_gradients=1, num_value_gradients=num_value_gradients, distributed=distributed,
+                         process_group=process_group)
         self.last_trpo_stats = None
 
     def _hparams(self, engine, n_global: int):
@@ -43,7 +47,9 @@ class TRPO(PPO):
         result = {}
 
         def native_step(optimizer):  # runs inside optimizer.step (ref trpo.py:180-185 calls it the same way)
-            result["out"] = engine.trpo_update(self._hparams(engine, 0), **optimizer.hyper_parameters())
+            result["out"] = engine.trpo_update(self._hparams(engine, self._global_rows(engine.n_rows)),
+                                               process_group=self.process_group, distributed=self.distributed,
+                                               **optimizer.hyper_parameters())
 
         opt.step(NativeClosure("surrogate loss", native_step), NativeClosure("KL divergence", native_step))
         stats, ts = result["out"]

@@ -56,6 +56,7 @@ int trpo_ls_set_params(float* params, const float* prev, const float* descent, f
 int trpo_ls_check(const double* slot, double n_rows, float delta, double* sc, int* flags, int index, cudaStream_t s);
 int trpo_ls_final(float* params, const float* prev, int n, float delta, const double* sc, int* flags, cudaStream_t s);
 int trpo_set_scalar(double* dst, const double* slot, int k, double inv, cudaStream_t s);
+int trpo_tail_to_slot(const float* tail, double* slot, cudaStream_t s);
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

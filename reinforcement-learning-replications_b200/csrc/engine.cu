@@ -778,6 +778,17 @@ extern "C" int b200rl_onpolicy_fvp(b200rl_onpolicy* h, const float* host_v, floa
 
 extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, const b200rl_trpo_hparams* cg,
                                   b200rl_update_stats* stats, b200rl_trpo_stats* ts, void* stream) {
+  return b200rl_trpo_update_dp(h, hp, cg, nullptr, nullptr, stats, ts, stream);
+}
+
+// Data-parallel TRPO (each rank holds a block of episodes, hp->n_global_rows = the global row count): every quantity the
+// step derives from the batch is a sum over rows, so it is all-reduced where it is formed -- the advantage statistics,
+// the surrogate gradient with its scalar sums, every Fisher-vector product, the scalar sums of every line-search
+// evaluation, the value gradients -- and the conjugate-gradient / line-search decisions, taken on the device from those
+// reduced values, come out identical on every rank.  ~30 small all-reduces per update.
+extern "C" int b200rl_trpo_update_dp(b200rl_onpolicy* h, const b200rl_ppo_hparams* hp, const b200rl_trpo_hparams* cg,
+                                     b200rl_allreduce_fn ar, void* user, b200rl_update_stats* stats,
+                                     b200rl_trpo_stats* ts, void* stream) {
   B200RL_REQUIRE(h && hp && cg && stats && ts, "trpo_update: NULL argument");
   B200RL_REQUIRE(h->n_rows > 0, "trpo_update: no batch loaded");
   B200RL_REQUIRE(cg->n_conjugate_gradients >= 1 && cg->max_backtracks >= 1, "trpo_update: bad CG parameters");
@@ -786,13 +797,14 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t launches0 = launches_total();
   const int64_t n = h->n_rows;
+  const int64_t n_glob = hp->n_global_rows > 0 ? hp->n_global_rows : n;
   const int Kv = hp->num_value_gradients, nb = cg->max_backtracks;
   const int n_slots = 1 + nb + Kv + 2;
   if (ensure_slots(h, n_slots)) return 1;
   B200RL_CUDA(cudaMemsetAsync(h->flags, 0, 8 * sizeof(int), s));
   B200RL_CUDA(cudaMemsetAsync(h->slots, 0, (size_t)n_slots * B200RL_N_SCALARS * sizeof(double), s));
   B200RL_CUDA(cudaMemsetAsync(h->cg_sc, 0, 8 * sizeof(double), s));
-  if (run_preamble(h, hp, nullptr, nullptr, s)) return 1;
+  if (run_preamble(h, hp, ar, user, s)) return 1;
   const int dist = h->cfg.dist;
   const int P = (int)h->Pp;
   const float delta = (float)cg->max_constraint, damping = (float)cg->hvp_damping_coefficient;
@@ -814,22 +826,38 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
   if (h->hints_valid) a.obs_absmax = h->absmax;
   if (b200rl_mlp_loss_grad(&a, s)) return 1;
   // (2) surrogate loss and its gradient at theta (trpo.py:228-239); slot 0 also carries the logged statistics
-  if (launch_fused(h, h->cfg.policy, B200RL_LOSS_TRPO_SURROGATE, dist, h->pol, h->obs, n, n, 0.0, true, true, nullptr,
+  if (launch_fused(h, h->cfg.policy, B200RL_LOSS_TRPO_SURROGATE, dist, h->pol, h->obs, n, n_glob, 0.0, true, true, nullptr,
                    true, nullptr, s)) return 1;
   if (b200rl_reduce_partials(h->partials, h->scalar_partials, b200rl_mlp_grid(&h->cfg.policy, n, 1), h->Pp, h->pol_grad,
-                             h->slots, 0, nullptr, s)) return 1;
-  if (trpo_set_scalar(h->cg_sc + 1, h->slots, 0, 1.0 / (double)n, s)) return 1;  // loss_before
+                             h->slots, ar ? 1 : 0, nullptr, s)) return 1;
+  if (ar) {  // gradient and scalar sums in one buffer
+    if (ar(user, h->pol_grad, h->Pp + B200RL_N_SCALARS, 0, s)) {
+      set_error("allreduce callback failed (surrogate gradient)");
+      return 1;
+    }
+    if (trpo_tail_to_slot(h->pol_grad + h->Pp, h->slots, s)) return 1;
+  }
+  if (trpo_set_scalar(h->cg_sc + 1, h->slots, 0, 1.0 / (double)n_glob, s)) return 1;  // loss_before
   // (3) conjugate gradient: x ~ H^-1 g
   if (trpo_cg_init(h->pol_grad, h->cg_x, h->cg_r, h->cg_p, P, h->cg_sc, h->cg_flags, s)) return 1;
   int fvps = 0;
+  auto fvp_allreduce = [&]() -> int {
+    if (ar && ar(user, h->cg_z, h->Pp, 0, s)) {
+      set_error("allreduce callback failed (Fisher-vector product)");
+      return 1;
+    }
+    return 0;
+  };
   for (int it = 0; it < cg->n_conjugate_gradients; ++it) {
-    if (launch_fvp(h, h->cg_p, h->cg_z, n, s)) return 1;
+    if (launch_fvp(h, h->cg_p, h->cg_z, n_glob, s)) return 1;
+    if (fvp_allreduce()) return 1;
     ++fvps;
     if (trpo_cg_update(h->cg_z, damping, h->cg_x, h->cg_r, h->cg_p, P, h->cg_sc, h->cg_flags, s)) return 1;
   }
   // (4) step size and descent step
   if (trpo_nan_to_zero(h->cg_x, P, s)) return 1;
-  if (launch_fvp(h, h->cg_x, h->cg_z, n, s)) return 1;
+  if (launch_fvp(h, h->cg_x, h->cg_z, n_glob, s)) return 1;
+  if (fvp_allreduce()) return 1;
   ++fvps;
   if (trpo_step_size(h->cg_x, h->cg_z, damping, delta, h->cg_descent, h->pol, h->cg_prev, P, h->cg_sc, s)) return 1;
   // (5) backtracking line search (device-side accept flag: later iterations become no-ops)
@@ -844,7 +872,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
     a.flags = B200RL_FLAG_FORWARD_ONLY;
     a.dist = dist;
     a.n_rows = n;
-    a.n_global = n;
+    a.n_global = n_glob;
     a.params = h->pol;
     a.obs = h->obs;
     a.actions = h->act;
@@ -858,13 +886,17 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
     a.skip_flag = h->cg_flags + 1;
     if (b200rl_mlp_loss_grad(&a, s)) return 1;
     if (b200rl_reduce_partials(nullptr, h->scalar_partials, grid_f, h->Pp, nullptr, slot, 0, h->cg_flags + 1, s)) return 1;
-    if (trpo_ls_check(slot, (double)n, delta, h->cg_sc, h->cg_flags, k, s)) return 1;
+    if (ar && ar(user, slot, B200RL_N_SCALARS, 1, s)) {  // zeros once the search has accepted (skipped launches)
+      set_error("allreduce callback failed (line-search evaluation)");
+      return 1;
+    }
+    if (trpo_ls_check(slot, (double)n_glob, delta, h->cg_sc, h->cg_flags, k, s)) return 1;
   }
   if (trpo_ls_final(h->pol, h->cg_prev, P, delta, h->cg_sc, h->cg_flags, s)) return 1;
   // (6) trpo.py:192 old_policy.load_state_dict(policy.state_dict()); then the value steps (:195-201)
   B200RL_CUDA(cudaMemcpyAsync(h->old_pol, h->pol, (size_t)h->Pp * 4, cudaMemcpyDeviceToDevice, s));
   const int vslot0 = 1 + nb;
-  if (run_value_loop(h, hp, nullptr, nullptr, n, vslot0, s)) return 1;
+  if (run_value_loop(h, hp, ar, user, n_glob, vslot0, s)) return 1;
 
   B200RL_CUDA(cudaMemcpyAsync(h->h_slots, h->slots, (size_t)n_slots * B200RL_N_SCALARS * sizeof(double),
                               cudaMemcpyDeviceToHost, s));
@@ -877,7 +909,7 @@ extern "C" int b200rl_trpo_update(b200rl_onpolicy* h, const b200rl_ppo_hparams* 
 
   memset(stats, 0, sizeof(*stats));
   memset(ts, 0, sizeof(*ts));
-  const double ng = (double)n;
+  const double ng = (double)n_glob;
   const double* s0 = h->h_slots;
   stats->policy_loss_before = s0[0] / ng;
   stats->entropy_before = s0[2] / ng;

@@ -171,6 +171,16 @@ int trpo_ls_final(float* params, const float* prev, int n, float delta, const do
   LAUNCH1(ls_final_kernel, s, params, prev, n, delta, sc, flags);
   return 0;
 }
+// the float32 scalar sums piggy-backed behind an all-reduced gradient -> a float64 scalar slot
+__global__ void tail_to_slot_kernel(const float* tail, double* slot) {
+  if (threadIdx.x < B200RL_N_SCALARS) slot[threadIdx.x] = (double)tail[threadIdx.x];
+}
+int trpo_tail_to_slot(const float* tail, double* slot, cudaStream_t s) {
+  tail_to_slot_kernel<<<1, 32, 0, s>>>(tail, slot);
+  B200RL_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
 int trpo_set_scalar(double* dst, const double* slot, int k, double inv, cudaStream_t s) {
   set_scalar_from_slot_kernel<<<1, 32, 0, s>>>(dst, slot, k, inv);
   B200RL_CUDA(cudaGetLastError());

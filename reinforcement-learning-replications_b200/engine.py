@@ -267,15 +267,25 @@ class OnPolicyEngine:
         return stats
 
     def trpo_update(self, hp: PpoHparams, max_constraint=0.01, n_conjugate_gradients=10, max_backtracks=15,
-                    backtrack_ratio=0.8, hvp_damping_coefficient=1e-5):
-        """The reference's TRPO.train on the loaded batch; returns (UpdateStats, TrpoStats)."""
+                    backtrack_ratio=0.8, hvp_damping_coefficient=1e-5, process_group=None, distributed: bool = False,
+                    allreduce=None):
+        """The reference's TRPO.train on the loaded batch; returns (UpdateStats, TrpoStats).  ``distributed`` /
+        ``allreduce`` as in ``update``: every rank holds a block of episodes, ``hp.n_global_rows`` the global row count,
+        and every batch-derived sum of the step is all-reduced (b200rl_trpo_update_dp)."""
         cg = TrpoHparams()
         cg.max_constraint, cg.n_conjugate_gradients = float(max_constraint), int(n_conjugate_gradients)
         cg.max_backtracks, cg.backtrack_ratio = int(max_backtracks), float(backtrack_ratio)
         cg.hvp_damping_coefficient = float(hvp_damping_coefficient)
         stats, ts = UpdateStats(), TrpoStats()
-        check(self.lib.b200rl_trpo_update(self.h, C.byref(hp), C.byref(cg), C.byref(stats), C.byref(ts),
-                                          current_stream_handle()), "trpo_update")
+        cb = None
+        if allreduce is not None:
+            self._allreduce_cb = self._make_allreduce_from(allreduce)
+            cb = C.cast(self._allreduce_cb, C.c_void_p)
+        elif distributed:
+            self._allreduce_cb = self._make_allreduce(process_group)
+            cb = C.cast(self._allreduce_cb, C.c_void_p)
+        check(self.lib.b200rl_trpo_update_dp(self.h, C.byref(hp), C.byref(cg), cb, None, C.byref(stats), C.byref(ts),
+                                             current_stream_handle()), "trpo_update")
         self._keep.clear()
         return stats, ts
 

@@ -164,3 +164,95 @@ def test_fvp_mixed_feature_magnitudes_stay_on_the_tensor_cores():
     assert int(_lib.load().b200rl_tc_fallback_count()) == before
     want = O.fisher_vector_product(layers, "gaussian", log_std, obs, v, damping=0.0)
     assert rel_err(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("dist", ["gaussian", "categorical"])
+def test_data_parallel_trpo_two_engines_one_gpu(dist):
+    """b200rl_trpo_update_dp: two engines with half the episodes each and a test all-reduce hook against ONE engine on
+    the whole batch.  Both ranks must hold bit-identical parameters and take the same line-search decision; against
+    the single engine the surrogate gradient agrees at 1e-5 and the step at the conjugate-gradient bar of this file
+    (2e-3: ten CG iterations amplify the different summation order of the reduced vectors)."""
+    import threading
+
+    import torch
+    from rl_replicas_b200 import synthetic
+    from rl_replicas_b200.engine import OLD_POLICY, POLICY, VALUE, OnPolicyEngine
+    rng = np.random.default_rng(4)
+    A = 6 if dist == "gaussian" else 5
+    ps, vs = [17, 64, 64, A], [17, 64, 64, 1]
+    mk = lambda sz: [(rng.standard_normal((o, i)).astype(np.float32) / np.sqrt(i), np.zeros(o, np.float32))
+                     for i, o in zip(sz[:-1], sz[1:])]
+    pl, vl = mk(ps), mk(vs)
+    log_std = np.full(A, -0.5, np.float32) if dist == "gaussian" else None
+    full = synthetic.ragged_batch(24000, 17, A, dist == "categorical", seed=6, min_len=50, max_len=400,
+                                  mean_fn=(lambda o: O.mlp_forward(pl, o)[0]) if dist == "gaussian" else None)
+    n = full["obs"].shape[0]
+    Kv = 4
+
+    def make(batch):
+        e = OnPolicyEngine(ps, vs, dist, batch["obs"].shape[0], batch["ep_done"].shape[0])
+        e.set_params(POLICY, O.flatten_layers(pl))
+        e.set_params(OLD_POLICY, O.flatten_layers(pl))
+        e.set_params(VALUE, O.flatten_layers(vl))
+        if log_std is not None:
+            e.set_log_std(log_std)
+        e.set_adam(VALUE, None, None, 0)
+        e.load_batch(batch)
+        return e
+
+    single = make(full)
+    st1, ts1 = single.trpo_update(OnPolicyEngine.hparams(num_value_gradients=Kv))
+    p1, v1 = single.get_params(POLICY), single.get_params(VALUE)
+    g1 = single.view("policy_grad").cpu().numpy()[:single.n_policy].copy()
+
+    barrier, bufs, calls = threading.Barrier(2), [None, None], [0]
+
+    def hook(rank):
+        def fn(t):
+            torch.cuda.current_stream().synchronize()
+            bufs[rank] = t
+            barrier.wait()
+            if rank == 0:
+                total = bufs[0] + bufs[1]
+                bufs[0].copy_(total)
+                bufs[1].copy_(total)
+                torch.cuda.current_stream().synchronize()
+                calls[0] += 1
+            barrier.wait()
+        return fn
+
+    engines = [make(synthetic.shard_batch(full, r, 2)) for r in range(2)]
+    torch.cuda.synchronize()
+    out, errors = [None, None], []
+
+    def work(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                out[r] = engines[r].trpo_update(OnPolicyEngine.hparams(n_global_rows=n, num_value_gradients=Kv),
+                                                allreduce=hook(r))
+                torch.cuda.current_stream().synchronize()
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+            barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    pd, vd = [e.get_params(POLICY) for e in engines], [e.get_params(VALUE) for e in engines]
+    np.testing.assert_array_equal(pd[0], pd[1])
+    np.testing.assert_array_equal(vd[0], vd[1])
+    (sa, ta), (sb, tb) = out
+    assert ta.accepted_index == tb.accepted_index == ts1.accepted_index and ta.rejected == tb.rejected == ts1.rejected == 0
+    assert ta.fvp_launches == ts1.fvp_launches
+    assert calls[0] >= 1 + 1 + ta.fvp_launches + 1 + Kv  # adv stats, gradient, every F v, >= 1 evaluation, value steps
+    gd = engines[0].view("policy_grad").cpu().numpy()[:engines[0].n_policy]
+    assert rel_err(gd, g1) < 1e-5
+    assert abs(sa.policy_loss_before - st1.policy_loss_before) < 1e-5 * max(1.0, abs(st1.policy_loss_before))
+    assert abs(sa.adv_std - st1.adv_std) < 1e-9 * st1.adv_std
+    assert rel_err(pd[0], p1) < 2e-3 and rel_err(vd[0], v1) < 2e-5
+    assert abs(ta.kl - ts1.kl) < 2e-2 * abs(ts1.kl) + 1e-7
+    for e in engines + [single]:
+        e.close()
