@@ -5,7 +5,7 @@ result must match the numpy ORACLE on the whole batch at 1e-5 of max|ref| (north
 mask below), and a single-GPU run of the same engine at 1e-5: the sharded engine computes the same global
 mean / std / KL and applies the same reduced gradient on every rank.  Both gradient-exchange
 paths are exercised: the one-shot exchange over peer-mapped memory (default) and the NCCL all-reduce per iteration
-(B200RL_PEER_EXCHANGE=0)."""
+(B200RL_PEER_EXCHANGE=0).  A data-parallel TRPO step is checked against the single-GPU one at the end."""
 import os
 import sys
 
@@ -96,6 +96,32 @@ def main():
                   f"steps {st.policy_steps_applied}/{rs.policy_steps_applied} kl {st.kl_divergence:.6g}/{rs.kl_divergence:.6g} "
                   f"vloss {st.value_loss_mean:.6g}/{rs.value_loss_mean:.6g} -> {'OK' if good else 'FAIL'}")
             ok = ok and good
+    # ---- TRPO: the constrained step with every batch-derived sum all-reduced (b200rl_trpo_update_dp) ----
+    from test_gpu_trpo import build_trpo
+    g = dict(policy_sizes=np.asarray(ps), value_sizes=np.asarray(vs), policy_flat0=O.flatten_layers(pl),
+             value_flat0=O.flatten_layers(vl), log_std=log_std)
+    dp = build_trpo(g, num_value_gradients=4, distributed=True)
+    dp.train_packed(synthetic.shard_batch(full, rank, world))
+    p_dp, v_dp = flat(dp.policy.network).copy(), flat(dp.value_function.network).copy()
+    t = torch.from_numpy(np.concatenate([p_dp, v_dp])).cuda()
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool(torch.equal(lo, hi))
+    if rank == 0:
+        ref = build_trpo(g, num_value_gradients=4)
+        ref.train_packed(full)
+        ts_d, ts_r = dp.last_trpo_stats, ref.last_trpo_stats
+        ep = np.abs(p_dp - flat(ref.policy.network)).max() / np.abs(flat(ref.policy.network)).max()
+        ev = np.abs(v_dp - flat(ref.value_function.network)).max() / np.abs(flat(ref.value_function.network)).max()
+        # ten CG iterations amplify the different summation order of the reduced vectors: 2e-3 on the step (the bar of
+        # tests/test_gpu_trpo.py), decisions exact
+        good = (same and ep < 2e-3 and ev < 2e-5 and ts_d.accepted_index == ts_r.accepted_index
+                and ts_d.rejected == ts_r.rejected == 0 and ts_d.fvp_launches == ts_r.fvp_launches)
+        print(f"TRPO [NCCL all-reduce per reduced quantity]: world={world} ranks_identical={same} vs 1-GPU run: "
+              f"policy_err={ep:.2e} value_err={ev:.2e} accepted {ts_d.accepted_index}/{ts_r.accepted_index} "
+              f"kl {ts_d.kl:.6g}/{ts_r.kl:.6g} -> {'OK' if good else 'FAIL'}")
+        ok = ok and good
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
