@@ -60,8 +60,9 @@ int64_t b200rl_launch_count(void);
 /* number of float32 parameters of the MLP (sum of out*in + out); -1 if the description is invalid */
 int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp);
 /* CTAs the fused MLP kernels use for n_rows rows on the current device (= rows of `partials`); -1 on error.
- * with_backward: 0 forward only, 1 forward + backward, 2 Fisher-vector product, 3 forward-only launches that set
- * out_full / old_out / B200RL_FLAG_NO_TC (the larger of the tensor-core and the fp32 kernel's row counts),
+ * with_backward: 0 forward only with B200RL_LOSS_EVAL, 1 forward + backward, 2 Fisher-vector product, 3 forward-only
+ * launches that set out_full / old_out / B200RL_FLAG_NO_TC or evaluate a loss other than EVAL (B200RL_FLAG_FORWARD_ONLY;
+ * the larger of the tensor-core and the fp32 kernel's row counts),
  * 4 forward + backward on the fp32 kernel (B200RL_FLAG_NO_TC or train_log_std). */
 int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward);
 

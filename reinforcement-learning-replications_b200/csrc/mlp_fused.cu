@@ -675,7 +675,8 @@ extern "C" int64_t b200rl_mlp_param_count(const b200rl_mlp_desc* mlp) {
   return p;
 }
 
-// with_backward: 0 forward only, 1 forward + backward, 2 Fisher-vector product, 3 forward only with out_full / old_out / NO_TC
+// with_backward: 0 forward only (EVAL), 1 forward + backward, 2 Fisher-vector product, 3 forward only with out_full / old_out /
+// NO_TC / a loss other than EVAL
 // (launches that use out_full / old_out / B200RL_FLAG_NO_TC)
 extern "C" int b200rl_mlp_grid(const b200rl_mlp_desc* mlp, int64_t n_rows, int with_backward) {
   if (!mlp) return -1;
@@ -796,7 +797,7 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
   const int L = k.lay.L;
   B200RL_REQUIRE(a->n_rows >= 0, "mlp_loss_grad: negative n_rows");
   if (a->n_rows == 0) {  // an empty shard (data-parallel ranks may hold none): every partial row is zero
-    const int rows = b200rl_mlp_grid(&a->mlp, 0, fvp ? 2 : (backward ? 1 : ((a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC)) ? 3 : 0)));
+    const int rows = b200rl_mlp_grid(&a->mlp, 0, fvp ? 2 : (backward ? 1 : ((a->out_full || a->old_out || (a->flags & B200RL_FLAG_NO_TC) || a->loss != B200RL_LOSS_EVAL) ? 3 : 0)));
     B200RL_REQUIRE(rows > 0, "mlp_loss_grad: no CUDA device");
     if (backward) B200RL_REQUIRE(a->partials, "mlp_loss_grad: partials is NULL");
     if (backward)
@@ -836,7 +837,9 @@ extern "C" int b200rl_mlp_loss_grad(const b200rl_mlp_loss_grad_args* a, void* st
   const bool wants_out = a->out_full != nullptr || a->old_out != nullptr;
   const bool out_on_tc = wants_out && forward_only && use_tc2();
   const bool needs_fp32 = fvp || (wants_out && !out_on_tc) || (a->flags & B200RL_FLAG_NO_TC) || a->train_log_std;
-  const bool mode3 = forward_only && (wants_out || (a->flags & B200RL_FLAG_NO_TC));
+  // forward-only launches whose re-run is the fp32 kernel (raw outputs / true KL, a loss other than EVAL) or that run on
+  // it outright (NO_TC) write b200rl_mlp_grid(mode 3) partial rows
+  const bool mode3 = forward_only && (wants_out || (a->flags & B200RL_FLAG_NO_TC) || a->loss != B200RL_LOSS_EVAL);
   const int rows3 = (mode3 && use_tc(a->mlp) && use_tc2()) ? tc_fwd_total_rows(a->mlp, a->n_rows) : 0;
   if (!needs_fp32 && use_tc(a->mlp)) {
     const int64_t n_glob_tc = a->n_global > 0 ? a->n_global : a->n_rows;
