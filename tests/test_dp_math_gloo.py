@@ -1,6 +1,7 @@
 """CPU test of the data-parallel decomposition (world_size 2, gloo): shard by environment, local sums scaled by the
 GLOBAL row count, all-reduce(sum) of [gradient + scalar tail] and of the 3 advantage statistics == single-process
-result.  This is the host-side contract the engine's all-reduce callback implements; the
+result; likewise TRPO's surrogate gradient, Fisher-vector product and line-search KL (b200rl_trpo_update_dp).  This is
+the host-side contract the engine's all-reduce callback implements; the
 arithmetic inside each rank is the numpy oracle here (the CUDA path is covered by tests/dist_check.py on GPUs)."""
 import os
 import sys
@@ -50,7 +51,33 @@ def _worker(rank, world, port, out):
     rv = O.value_loss_and_grad(vl, b["obs"], ret, n_global=n_glob)
     vbuf = torch.from_numpy(rv["grad"].copy())
     dist.all_reduce(vbuf)
+    # TRPO (b200rl_trpo_update_dp): the surrogate gradient, a Fisher-vector product and the true KL of a line-search
+    # evaluation are sums over rows too -- local sums scaled by the GLOBAL row count, one all-reduce each
+    rt = O.policy_loss_and_grad(pl, "gaussian", log_std, b["obs"], b["act"], adv, old_logp, "trpo", 0.2, n_global=n_glob)
+    tbuf = torch.from_numpy(np.concatenate([rt["grad"], np.asarray([rt["loss"] * n_glob], np.float32)]))
+    dist.all_reduce(tbuf)
+    probe = np.random.default_rng(5).standard_normal(rt["grad"].size).astype(np.float32)
+    n_loc = b["obs"].shape[0]
+    # the oracle's F v divides by its own row count and adds damping * v: undo both, rescale by 1 / N_global
+    fv_local = (O.fisher_vector_product(pl, "gaussian", log_std, b["obs"], probe, damping=0.0) * np.float32(n_loc / n_glob))
+    fbuf = torch.from_numpy(fv_local.astype(np.float32).copy())
+    dist.all_reduce(fbuf)
+    moved = [(w + 0.01 * np.random.default_rng(6).standard_normal(w.shape).astype(np.float32), bb) for w, bb in pl]
+    kl_local = O.dist_kl("gaussian", O.mlp_forward(pl, b["obs"])[0], O.mlp_forward(moved, b["obs"])[0], log_std)
+    kbuf = torch.tensor([float(kl_local.astype(np.float64).sum())], dtype=torch.float64)
+    dist.all_reduce(kbuf)
     if rank == 0:
+        rtf_adv, _ = local_preamble(full)
+        rtf_old = O.Dist("gaussian", O.mlp_forward(pl, full["obs"])[0], log_std).log_prob(full["act"])
+        rtf = O.policy_loss_and_grad(pl, "gaussian", log_std, full["obs"], full["act"], O.normalize(rtf_adv), rtf_old,
+                                     "trpo", 0.2)
+        tg = tbuf.numpy()
+        out["trpo_grad_err"] = float(np.abs(tg[:-1] - rtf["grad"]).max() / np.abs(rtf["grad"]).max())
+        out["trpo_loss_err"] = float(abs(tg[-1] / n_glob - rtf["loss"]))
+        fv_full = O.fisher_vector_product(pl, "gaussian", log_std, full["obs"], probe, damping=0.0)
+        out["fvp_err"] = float(np.abs(fbuf.numpy() - fv_full).max() / np.abs(fv_full).max())
+        kl_full = O.dist_kl("gaussian", O.mlp_forward(pl, full["obs"])[0], O.mlp_forward(moved, full["obs"])[0], log_std)
+        out["kl_err"] = float(abs(kbuf.item() / n_glob - kl_full.astype(np.float64).mean()) / kl_full.mean())
         adv_f, ret_f = local_preamble(full)
         adv_n = O.normalize(adv_f)
         old_f = O.Dist("gaussian", O.mlp_forward(pl, full["obs"])[0], log_std).log_prob(full["act"])
@@ -72,3 +99,4 @@ def test_dp_decomposition_world2_gloo():
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out["n_glob"] == 3000
     assert out["grad_err"] < 1e-5 and out["vgrad_err"] < 1e-5 and out["loss_err"] < 1e-6
+    assert out["trpo_grad_err"] < 1e-5 and out["trpo_loss_err"] < 1e-6 and out["fvp_err"] < 1e-5 and out["kl_err"] < 1e-5
